@@ -1,0 +1,1012 @@
+/* clive_b200.cu — libclive_b200.so: the C ABI of include/clive_b200.h on sm_100a.
+ *
+ * Build (see __graft_entry__.build / clive2_b200/build.py):
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC ...
+ * -fmad=false is part of the arithmetic contract (clv_device.cuh): results equal the oracle's bit for bit.
+ *
+ * There is no host execution path in this library: every entry point that computes launches a kernel and reports
+ * CLV_ERR_NO_DEVICE / CLV_ERR_CUDA when that is impossible.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "clv_device.cuh"
+#include "clv_accel_build.h"
+
+using namespace clv;
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * errors
+ * ------------------------------------------------------------------------------------------------------------- */
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? CLV_ERR_NOMEM : CLV_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+#define REQUIRE(cond, msg)                                           \
+    do {                                                             \
+        if (!(cond)) return fail(CLV_ERR_INVALID, "%s: %s", __func__, msg); \
+    } while (0)
+
+extern "C" const char *clv_last_error(void) { return g_err; }
+extern "C" const char *clv_version(void) { return "clive_b200 0.1 (sm_100a, fmad=false)"; }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * context + memory
+ * ------------------------------------------------------------------------------------------------------------- */
+struct clv_ctx {
+    int device;
+    cudaStream_t stream;
+    Counters *d_counters;
+    int counting;
+    unsigned long long launches;
+    int sm_count;
+};
+
+extern "C" int clv_device_count(int *count) {
+    REQUIRE(count, "null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(CLV_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return CLV_OK;
+}
+
+extern "C" int clv_ctx_create(int device, clv_ctx **out) {
+    REQUIRE(out, "null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(CLV_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    REQUIRE(device >= 0 && device < n, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(CLV_ERR_NO_DEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+    clv_ctx *c = new (std::nothrow) clv_ctx();
+    if (!c) return fail(CLV_ERR_NOMEM, "host allocation");
+    c->device = device;
+    c->counting = 0;
+    c->launches = 0;
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_counters, COUNTERS_CLASSES * sizeof(Counters)));
+    CK(cudaMemsetAsync(c->d_counters, 0, COUNTERS_CLASSES * sizeof(Counters), c->stream));
+    *out = c;
+    return CLV_OK;
+}
+
+extern "C" int clv_ctx_destroy(clv_ctx *c) {
+    if (!c) return CLV_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_counters);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return CLV_OK;
+}
+
+extern "C" int clv_ctx_synchronize(clv_ctx *c) {
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return CLV_OK;
+}
+
+extern "C" int clv_ctx_stream(clv_ctx *c, void **stream) {
+    REQUIRE(c && stream, "null");
+    *stream = (void *)c->stream;
+    return CLV_OK;
+}
+
+extern "C" int clv_mem_alloc(clv_ctx *c, size_t nbytes, void **d_ptr) {
+    REQUIRE(c && d_ptr, "null");
+    CK(cudaSetDevice(c->device));
+    *d_ptr = nullptr;
+    if (nbytes == 0) nbytes = 16;
+    CK(cudaMalloc(d_ptr, nbytes));
+    CK(cudaMemsetAsync(*d_ptr, 0, nbytes, c->stream));
+    return CLV_OK;
+}
+extern "C" int clv_mem_free(clv_ctx *c, void *d_ptr) {
+    REQUIRE(c, "null ctx");
+    if (!d_ptr) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d_ptr));
+    return CLV_OK;
+}
+extern "C" int clv_mem_upload(clv_ctx *c, void *d_dst, const void *h_src, size_t nbytes) {
+    REQUIRE(c && (nbytes == 0 || (d_dst && h_src)), "null");
+    if (!nbytes) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); /* the host array is only borrowed for the duration of the call */
+    return CLV_OK;
+}
+extern "C" int clv_mem_download(clv_ctx *c, void *h_dst, const void *d_src, size_t nbytes) {
+    REQUIRE(c && (nbytes == 0 || (h_dst && d_src)), "null");
+    if (!nbytes) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(h_dst, d_src, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CLV_OK;
+}
+
+__global__ void k_fill32(uint32_t *dst, uint32_t value, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] = value;
+}
+static inline unsigned grid_for(size_t n, unsigned block, unsigned cap = 148u * 32u) {
+    size_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (unsigned)std::min<size_t>(g, cap);
+}
+#define LAUNCHED(c)                  \
+    do {                             \
+        (c)->launches++;             \
+        CK(cudaGetLastError());      \
+    } while (0)
+
+extern "C" int clv_mem_fill32(clv_ctx *c, void *d_dst, uint32_t value, size_t count) {
+    REQUIRE(c && (count == 0 || d_dst), "null");
+    if (!count) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_fill32<<<grid_for(count, 256), 256, 0, c->stream>>>((uint32_t *)d_dst, value, count);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+extern "C" int clv_host_alloc(size_t nbytes, void **h_ptr) {
+    REQUIRE(h_ptr, "null");
+    CK(cudaHostAlloc(h_ptr, nbytes ? nbytes : 16, cudaHostAllocDefault));
+    return CLV_OK;
+}
+extern "C" int clv_host_free(void *h_ptr) {
+    if (h_ptr) CK(cudaFreeHost(h_ptr));
+    return CLV_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * acceleration structure: reference Box[]/Triangle[] -> compact traversal layout (clv_device.cuh AccelView)
+ * ------------------------------------------------------------------------------------------------------------- */
+struct clv_accel {
+    clv_ctx *ctx;
+    V4 *d_nodes, *d_tris;
+    Triangle *d_ref_triangles;
+    int32_t *d_camera_tris;
+    AccelView view;
+    uint64_t n_nodes, n_tris;
+};
+
+extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_boxes, const clv_Triangle *h_tris_,
+                                int32_t n_tris, clv_accel **out) {
+    REQUIRE(c && out && h_boxes_ && h_tris_, "null");
+    REQUIRE(n_boxes > 0 && n_tris > 0, "empty scene");
+    REQUIRE(n_tris < (1 << 27), "more than 2^27 triangles");
+    *out = nullptr;
+    CK(cudaSetDevice(c->device));
+    const Box *boxes = reinterpret_cast<const Box *>(h_boxes_);
+    const Triangle *tris = reinterpret_cast<const Triangle *>(h_tris_);
+
+    HostAccel H;
+    const char *why = build_host_accel(boxes, n_boxes, tris, n_tris, H);
+    if (why) return fail(CLV_ERR_INVALID, "clv_accel_create: %s", why);
+    std::vector<NodeRec> &nodes = H.nodes;
+    std::vector<V4> &ctris = H.tris;
+    std::vector<int32_t> &camera_tris = H.camera_tris;
+    int32_t root_ref = H.root_ref;
+
+    clv_accel *a = new (std::nothrow) clv_accel();
+    if (!a) return fail(CLV_ERR_NOMEM, "host allocation");
+    memset(a, 0, sizeof *a);
+    a->ctx = c;
+    a->n_nodes = nodes.size();
+    a->n_tris = (uint64_t)n_tris;
+    size_t nb_nodes = std::max<size_t>(nodes.size(), 1) * sizeof(NodeRec);
+    size_t nb_tris = ctris.size() * sizeof(V4);
+    size_t nb_ref = (size_t)n_tris * sizeof(Triangle);
+    size_t nb_cam = std::max<size_t>(camera_tris.size(), 1) * sizeof(int32_t);
+    CK(cudaMalloc(&a->d_nodes, nb_nodes));
+    CK(cudaMalloc(&a->d_tris, nb_tris));
+    CK(cudaMalloc(&a->d_ref_triangles, nb_ref));
+    CK(cudaMalloc(&a->d_camera_tris, nb_cam));
+    if (!nodes.empty()) CK(cudaMemcpyAsync(a->d_nodes, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(a->d_tris, ctris.data(), nb_tris, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(a->d_ref_triangles, tris, nb_ref, cudaMemcpyHostToDevice, c->stream));
+    if (!camera_tris.empty()) CK(cudaMemcpyAsync(a->d_camera_tris, camera_tris.data(), camera_tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    a->view.nodes = a->d_nodes;
+    a->view.tris = a->d_tris;
+    a->view.ref_triangles = a->d_ref_triangles;
+    a->view.root_min = boxes[0].min;
+    a->view.root_max = boxes[0].max;
+    a->view.root_ref = root_ref;
+    a->view.n_camera_tris = (int32_t)camera_tris.size();
+    a->view.camera_tris = a->d_camera_tris;
+    *out = a;
+    return CLV_OK;
+}
+
+extern "C" int clv_accel_destroy(clv_accel *a) {
+    if (!a) return CLV_OK;
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
+    cudaFree(a->d_nodes);
+    cudaFree(a->d_tris);
+    cudaFree(a->d_ref_triangles);
+    cudaFree(a->d_camera_tris);
+    delete a;
+    return CLV_OK;
+}
+
+extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[4]) {
+    REQUIRE(a && out, "null");
+    out[0] = a->n_nodes * sizeof(NodeRec);
+    out[1] = a->n_tris * 3 * sizeof(V4);
+    out[2] = a->n_nodes;
+    out[3] = a->n_tris;
+    return CLV_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * kernels
+ * ------------------------------------------------------------------------------------------------------------- */
+#define CLV_BLOCK 128
+
+template <bool COUNT> __device__ __forceinline__ void flush_counters(Cnt<COUNT> &, Counters *) {}
+template <> __device__ __forceinline__ void flush_counters<true>(Cnt<true> &cnt, Counters *dst) {
+    /* warp-aggregate, then one atomic per counter per warp */
+    unsigned rr = cnt.rr, rt = cnt.rt, nf = cnt.nf, tf = cnt.tf, vx = cnt.vx;
+    for (int o = 16; o > 0; o >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        rt += __shfl_xor_sync(0xffffffffu, rt, o);
+        nf += __shfl_xor_sync(0xffffffffu, nf, o);
+        tf += __shfl_xor_sync(0xffffffffu, tf, o);
+        vx += __shfl_xor_sync(0xffffffffu, vx, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&dst->rays_ref, (unsigned long long)rr);
+        atomicAdd(&dst->rays_traced, (unsigned long long)rt);
+        atomicAdd(&dst->node_fetches, (unsigned long long)nf);
+        atomicAdd(&dst->tri_fetches, (unsigned long long)tf);
+        atomicAdd(&dst->vertices, (unsigned long long)vx);
+    }
+}
+
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_generate_light_rays(uint32_t n, const Triangle *light_triangles, const float *surface_areas,
+                      const int32_t *light_triangle_indices, const Material *materials, uint32_t *random_buffer,
+                      Ray *out, const int32_t *counts) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    uint2 sd = reinterpret_cast<uint2 *>(random_buffer)[id];
+    uint32_t seed0 = sd.x, seed1 = sd.y;
+    out[id] = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, counts[0], seed0, seed1);
+    reinterpret_cast<uint2 *>(random_buffer)[id] = make_uint2(seed0, seed1);
+}
+
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_generate_camera_rays(uint32_t n, const Camera *camera, uint32_t *random_buffer, const uint32_t *indices, Ray *out) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    Camera c = camera[0];
+    uint2 sd = reinterpret_cast<uint2 *>(random_buffer)[id];
+    uint32_t seed0 = sd.x, seed1 = sd.y;
+    out[id] = make_camera_ray(c, (int)indices[id], seed0, seed1);
+    reinterpret_cast<uint2 *>(random_buffer)[id] = make_uint2(seed0, seed1);
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_generate_paths(uint32_t n, const Ray *rays, AccelView A, const Material *materials, uint32_t *random_buffer, V4 *out,
+                 Path *output_paths, V4 *float_debug, Counters *counters) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id < n) {
+        uint2 sd = reinterpret_cast<uint2 *>(random_buffer)[id];
+        uint32_t seed0 = sd.x, seed1 = sd.y;
+        V4 uni;
+        random_walk<MODE, COUNT>(rays[id], A, materials, seed0, seed1, output_paths + id, &uni, cnt);
+        out[id] = uni;
+        if (float_debug) float_debug[id] = v4(100.0f, 100.0f, 100.0f, 100.0f);
+        reinterpret_cast<uint2 *>(random_buffer)[id] = make_uint2(seed0, seed1);
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+__global__ void k_reset_light_indices(uint32_t n, int32_t *pix, int32_t *path, int32_t *ray, float *w, float *shade) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    pix[id] = -1; path[id] = 0; ray[id] = 0; w[id] = 0.0f; shade[id] = 0.0f;
+}
+
+template <int MODE, bool SPLAT, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_connect_paths(uint32_t n, const uint32_t *sample_ids, const Path *camera_paths, const Path *light_paths, AccelView A,
+                const Material *materials, const Camera *camera, WeightAggregator *aggs, V4 *out, LightSink sink,
+                Counters *counters) {
+    __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id < n) {
+        Camera c = camera[0];
+        TArr S;
+        S.base = scratch + threadIdx.x;
+        S.stride = CLV_BLOCK;
+        /* staged ABI: slot == id.  Fused renderer: paths are per local slot, aggregators/out are per pixel */
+        uint32_t agg_slot = sample_ids ? sample_ids[id] : id;
+        connect_sample<MODE, SPLAT, COUNT>(id, id, agg_slot, camera_paths, light_paths, A, materials, c, aggs, out, sink,
+                                           S, cnt);
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_adaptive_finalize_samples(uint32_t n, const WeightAggregator *aggs, const Camera *camera, V4 *out,
+                            uint32_t *sample_counts, const uint32_t *bin_offsets, float *sample_weights) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    Camera c = camera[0];
+    V3 total;
+    float wsum;
+    uint32_t count;
+    finalize_pixel(id, aggs, c, bin_offsets, total, wsum, count);
+    sample_counts[id] = count;
+    out[id] = v4(total.x, total.y, total.z, 1.0f);
+    sample_weights[id] = wsum;
+}
+
+/* one bitonic compare-exchange step, trace.metal:872-934 */
+__global__ void k_light_sort(uint32_t n_threads, int32_t *pix, int32_t *path, int32_t *ray, float *w, float *shade,
+                             uint32_t stage, uint32_t pass_of_stage, uint32_t n, uint32_t pairs_per_thread) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_threads) return;
+    for (uint32_t p = 0; p < pairs_per_thread; ++p) {
+        uint32_t gp = id * pairs_per_thread + p;
+        uint32_t dist = 1u << (pass_of_stage - 1);
+        uint32_t block_width = 1u << stage;
+        uint32_t l = (gp / dist) * dist * 2u + (gp % dist);
+        uint32_t r = l + dist;
+        if (r >= n || l >= n) continue;
+        bool ascending = ((gp & (block_width >> 1)) == 0u);
+        int32_t lp = pix[l], rp = pix[r];
+        if ((ascending && lp > rp) || (!ascending && lp < rp)) {
+            pix[l] = rp; pix[r] = lp;
+            int32_t ti = path[l]; path[l] = path[r]; path[r] = ti;
+            ti = ray[l]; ray[l] = ray[r]; ray[r] = ti;
+            float tf = w[l]; w[l] = w[r]; w[r] = tf;
+            tf = shade[l]; shade[l] = shade[r]; shade[r] = tf;
+        }
+    }
+}
+
+/* light_image_gather, trace.metal:937-964 */
+__global__ void k_light_image_gather(uint32_t n, const Path *light_paths, const Material *materials,
+                                     const int32_t *path_indices, const int32_t *ray_indices, const int32_t *bins,
+                                     uint32_t offset, const float *weights, const float *shades, V4 *light_image,
+                                     float *sum_weights) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    uint32_t start = (uint32_t)bins[id] + offset, end = (uint32_t)bins[id + 1] + offset;
+    V3 total = v3(0, 0, 0);
+    float weight_sum = 0.0f;
+    for (uint32_t i = start; i < end; i++) {
+        const Path *path = light_paths + path_indices[i];
+        int ray_idx = ray_indices[i];
+        const Ray *ray = path->rays + ray_idx;
+        const Ray *prior = path->rays + (ray_idx - 1 > 0 ? ray_idx - 1 : 0);
+        V3 mc = xyz(ld4(&materials[ray->material].color));
+        total = total + (xyz(prior->color) * (weights[i] * shades[i])) * mc;
+        weight_sum += weights[i];
+    }
+    light_image[id] = v4(total.x, total.y, total.z, 1.0f);
+    sum_weights[id] += weight_sum;
+}
+
+/* device-side replacement of sort + host bins + gather for the staged arrays: one thread per entry, atomics */
+__global__ void k_light_image_splat(uint32_t n_entries, uint32_t n_pixels, const Path *light_paths,
+                                    const Material *materials, const int32_t *pixel_indices, const int32_t *path_indices,
+                                    const int32_t *ray_indices, const float *weights, const float *shades,
+                                    V4 *light_image, float *sum_weights) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    int32_t px = pixel_indices[i];
+    if (px < 0 || (uint32_t)px >= n_pixels) return;
+    const Path *path = light_paths + path_indices[i];
+    int ray_idx = ray_indices[i];
+    const Ray *ray = path->rays + ray_idx;
+    const Ray *prior = path->rays + (ray_idx - 1 > 0 ? ray_idx - 1 : 0);
+    V3 mc = xyz(ld4(&materials[ray->material].color));
+    V3 contrib = (xyz(prior->color) * (weights[i] * shades[i])) * mc;
+    atomicAdd(&light_image[px].x, contrib.x);
+    atomicAdd(&light_image[px].y, contrib.y);
+    atomicAdd(&light_image[px].z, contrib.z);
+    atomicAdd(&sum_weights[px], weights[i]);
+}
+__global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather writes (0,0,0,1) for empty pixels */
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) light_image[i] = v4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+
+/* ---- fused per-pass kernels (Renderer.run_sample without host round trips) ---------------------------------------- */
+/* stages 1-4: both ray generators and both random walks of one sample, RNG streams in the reference's order
+ * (light gen, camera gen, light walk, camera walk; renderer.py:281-285) */
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_fused_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
+              const int32_t *light_triangle_indices, int light_count, const Material *materials, const Camera *camera,
+              AccelView A, uint32_t *seeds, Path *light_paths, Path *camera_paths, Accum *accum, Counters *counters) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id < n_local) {
+        Camera c = camera[0];
+        uint32_t gid = sample_ids ? sample_ids[id] : id;
+        uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
+        uint32_t seed0 = sd.x, seed1 = sd.y;
+        fused_walk_sample<MODE, COUNT>(id, gid, light_triangles, surface_areas, light_triangle_indices, light_count,
+                                       materials, c, A, seed0, seed1, light_paths, camera_paths, accum, cnt);
+        reinterpret_cast<uint2 *>(seeds)[id] = make_uint2(seed0, seed1);
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+/* stages 6-8: finalize (identity sample bins) + light image + accumulation; clears the per-pass light image */
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_fused_finalize(uint32_t n_pixels, const WeightAggregator *aggs, const Camera *camera, V4 *light_image, Accum *accum,
+                 float *pass_weight_sum) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    float wpass = 0.0f;
+    if (id < n_pixels) {
+        Camera c = camera[0];
+        wpass = fused_finalize_pixel(id, aggs, c, light_image, accum);
+    }
+    if (pass_weight_sum) {
+        wpass = nan_to_num0(wpass);
+        for (int o = 16; o > 0; o >>= 1) wpass += __shfl_xor_sync(0xffffffffu, wpass, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(pass_weight_sum, wpass);
+    }
+}
+
+/* ---- parity hooks -------------------------------------------------------------------------------------------------- */
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_traverse(uint32_t n, const Ray *rays, AccelView A, int32_t *tri, float *t, float *u, float *v, Counters *counters) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id < n) {
+        const Ray *r = rays + id;
+        int best_i = -1;
+        float best_t = CLV_INF, bu = 0.0f, bv = 0.0f;
+        cnt.ray_ref();
+        closest_hit<MODE, COUNT>(A, xyz(ld4(&r->origin)), xyz(ld4(&r->direction)), xyz(ld4(&r->inv_direction)), best_i,
+                                 best_t, bu, bv, cnt, -CLV_INF, -1);
+        tri[id] = best_i; t[id] = best_t; u[id] = bu; v[id] = bv;
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_visibility(uint32_t n, const Ray *a, const Ray *b, AccelView A, int32_t *visible, Counters *counters) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id < n)
+        visible[id] = visibility_test<MODE, COUNT>(A, xyz(ld4(&a[id].origin)), a[id].triangle, xyz(ld4(&b[id].origin)),
+                                                   b[id].triangle, cnt) ? 1 : 0;
+    flush_counters<COUNT>(cnt, counters);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * section 4: stage-level entry points (reference argument order)
+ * ------------------------------------------------------------------------------------------------------------- */
+#define GRID(n) (((n) + CLV_BLOCK - 1) / CLV_BLOCK)
+/* dispatch on (traversal mode, counting) */
+#define DISPATCH_MC(mode, counting, CALL)                                              \
+    do {                                                                               \
+        if ((mode) == CLV_TRAVERSE_REFERENCE_ORDER) {                                  \
+            if (counting) { CALL(TRAVERSE_REFERENCE, true); } else { CALL(TRAVERSE_REFERENCE, false); } \
+        } else {                                                                       \
+            if (counting) { CALL(TRAVERSE_ORDERED, true); } else { CALL(TRAVERSE_ORDERED, false); }     \
+        }                                                                              \
+    } while (0)
+
+static int g_stage_mode = CLV_TRAVERSE_ORDERED;
+extern "C" int clv_set_stage_traverse_mode(int mode) {
+    REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
+    g_stage_mode = mode;
+    return CLV_OK;
+}
+
+extern "C" int clv_generate_light_rays(clv_ctx *c, uint32_t n, const clv_Triangle *lt, const float *areas,
+                                       const int32_t *lti, const clv_Material *mats, uint32_t *rnd, clv_Ray *out,
+                                       const int32_t *counts) {
+    REQUIRE(c && lt && areas && lti && mats && rnd && out && counts, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_generate_light_rays<<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const Triangle *)lt, areas, lti, (const Material *)mats, rnd, (Ray *)out, counts);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_generate_camera_rays(clv_ctx *c, uint32_t n, const clv_Camera *cam, uint32_t *rnd,
+                                        const uint32_t *indices, clv_Ray *out) {
+    REQUIRE(c && cam && rnd && indices && out, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_generate_camera_rays<<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const Camera *)cam, rnd, indices, (Ray *)out);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_generate_paths(clv_ctx *c, uint32_t n, const clv_Ray *rays, const clv_accel *accel,
+                                  const clv_Material *mats, uint32_t *rnd, float *out, clv_Path *paths, float *debug) {
+    REQUIRE(c && rays && accel && mats && rnd && out && paths, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+#define CALL(M, CT) k_generate_paths<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const Ray *)rays, accel->view, (const Material *)mats, rnd, (V4 *)out, (Path *)paths, (V4 *)debug, c->d_counters)
+    DISPATCH_MC(g_stage_mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_reset_light_indices(clv_ctx *c, uint32_t n, int32_t *pix, int32_t *path, int32_t *ray, float *w,
+                                       float *shade) {
+    REQUIRE(c && pix && path && ray && w && shade, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_reset_light_indices<<<(n + 255) / 256, 256, 0, c->stream>>>(n, pix, path, ray, w, shade);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, const clv_Path *lp, const clv_accel *accel,
+                                 const clv_Material *mats, const clv_Camera *cam, clv_WeightAggregator *aggs, float *out,
+                                 int32_t *pix, int32_t *path, int32_t *ray, float *w, float *shade) {
+    REQUIRE(c && cp && lp && accel && mats && cam && aggs && out && pix && path && ray && w && shade, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    LightSink sink;
+    memset(&sink, 0, sizeof sink);
+    sink.pixel_indices = pix; sink.path_indices = path; sink.ray_indices = ray; sink.weights = w; sink.shade = shade;
+#define CALL(M, CT) k_connect_paths<M, false, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, nullptr, (const Path *)cp, (const Path *)lp, accel->view, (const Material *)mats, (const Camera *)cam, (WeightAggregator *)aggs, (V4 *)out, sink, c->d_counters + COUNTERS_CONNECT)
+    DISPATCH_MC(g_stage_mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_adaptive_finalize_samples(clv_ctx *c, uint32_t n, const clv_WeightAggregator *aggs,
+                                             const clv_Camera *cam, float *out, uint32_t *counts,
+                                             const uint32_t *bin_offsets, float *weights) {
+    REQUIRE(c && aggs && cam && out && counts && bin_offsets && weights, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_adaptive_finalize_samples<<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const WeightAggregator *)aggs, (const Camera *)cam, (V4 *)out, counts, bin_offsets, weights);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_light_sort(clv_ctx *c, uint32_t n_threads, int32_t *pix, int32_t *path, int32_t *ray, float *w,
+                              float *shade, uint32_t stage, uint32_t pass_of_stage, uint32_t n, uint32_t ppt) {
+    REQUIRE(c && pix && path && ray && w && shade, "null");
+    REQUIRE(stage >= 1 && stage < 32 && pass_of_stage >= 1 && pass_of_stage <= stage, "bad stage");
+    if (!n_threads) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_light_sort<<<(n_threads + 255) / 256, 256, 0, c->stream>>>(n_threads, pix, path, ray, w, shade, stage, pass_of_stage, n, ppt);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_light_image_gather(clv_ctx *c, uint32_t n, const clv_Path *lp, const clv_Material *mats,
+                                      const int32_t *path_idx, const int32_t *ray_idx, const int32_t *bins,
+                                      uint32_t offset, const float *weights, const float *shades, float *light_image,
+                                      float *sum_weights) {
+    REQUIRE(c && lp && mats && path_idx && ray_idx && bins && weights && shades && light_image && sum_weights, "null");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    k_light_image_gather<<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const Path *)lp, (const Material *)mats, path_idx, ray_idx, bins, offset, weights, shades, (V4 *)light_image, sum_weights);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_light_image_splat(clv_ctx *c, uint32_t n_entries, uint32_t n_pixels, const clv_Path *lp,
+                                     const clv_Material *mats, const int32_t *pix, const int32_t *path_idx,
+                                     const int32_t *ray_idx, const float *weights, const float *shades,
+                                     float *light_image, float *sum_weights) {
+    REQUIRE(c && lp && mats && pix && path_idx && ray_idx && weights && shades && light_image && sum_weights, "null");
+    CK(cudaSetDevice(c->device));
+    if (n_pixels) {
+        k_set_light_image<<<(n_pixels + 255) / 256, 256, 0, c->stream>>>(n_pixels, (V4 *)light_image);
+        LAUNCHED(c);
+    }
+    if (n_entries) {
+        k_light_image_splat<<<(n_entries + 255) / 256, 256, 0, c->stream>>>(n_entries, n_pixels, (const Path *)lp, (const Material *)mats, pix, path_idx, ray_idx, weights, shades, (V4 *)light_image, sum_weights);
+        LAUNCHED(c);
+    }
+    return CLV_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * section 5: fused renderer
+ * ------------------------------------------------------------------------------------------------------------- */
+struct clv_renderer {
+    clv_ctx *ctx;
+    const clv_accel *accel;
+    uint32_t width, height, n_pixels, n_local;
+    int light_count;
+    int mode;
+    /* scene copies */
+    Material *d_materials;
+    Camera *d_camera;
+    Triangle *d_light_triangles;
+    float *d_light_areas;
+    int32_t *d_light_tri_idx;
+    /* work buffers */
+    uint32_t *d_seeds, *d_sample_ids;
+    Path *d_light_paths, *d_camera_paths;
+    WeightAggregator *d_aggs;
+    V4 *d_light_image;
+    Accum *d_accum;
+    float *d_pass_weight;
+    std::vector<uint32_t> sample_ids;
+    unsigned long long passes;
+    /* optional per-kernel timing: events around each of the three kernels of every pass */
+    int timing;
+    std::vector<cudaEvent_t> events; /* 4 per pass: before walks, after walks, after connect, after finalize */
+    double kernel_ms[3];
+    unsigned long long timed_passes;
+};
+
+extern "C" int clv_renderer_destroy(clv_renderer *r) {
+    if (!r) return CLV_OK;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    cudaFree(r->d_materials); cudaFree(r->d_camera); cudaFree(r->d_light_triangles); cudaFree(r->d_light_areas);
+    cudaFree(r->d_light_tri_idx); cudaFree(r->d_seeds); cudaFree(r->d_sample_ids); cudaFree(r->d_light_paths);
+    cudaFree(r->d_camera_paths); cudaFree(r->d_aggs); cudaFree(r->d_light_image); cudaFree(r->d_accum);
+    cudaFree(r->d_pass_weight);
+    for (cudaEvent_t e : r->events) cudaEventDestroy(e);
+    delete r;
+    return CLV_OK;
+}
+
+static int upload_new(clv_ctx *c, void **dst, const void *src, size_t nbytes) {
+    CK(cudaMalloc(dst, nbytes ? nbytes : 16));
+    if (nbytes) CK(cudaMemcpyAsync(*dst, src, nbytes, cudaMemcpyHostToDevice, c->stream));
+    return CLV_OK;
+}
+
+static int load_seeds(clv_renderer *r, const uint32_t *h_seeds) {
+    clv_ctx *c = r->ctx;
+    if (r->sample_ids.empty()) {
+        CK(cudaMemcpyAsync(r->d_seeds, h_seeds, (size_t)r->n_local * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        std::vector<uint32_t> rows((size_t)r->n_local * 2);
+        for (uint32_t i = 0; i < r->n_local; i++) {
+            rows[2 * (size_t)i] = h_seeds[2 * (size_t)r->sample_ids[i]];
+            rows[2 * (size_t)i + 1] = h_seeds[2 * (size_t)r->sample_ids[i] + 1];
+        }
+        CK(cudaMemcpyAsync(r->d_seeds, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return CLV_OK;
+}
+
+extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv_scene_desc *s, const uint32_t *h_seeds,
+                                   const uint32_t *h_sample_ids, uint32_t n_local, clv_renderer **out) {
+    REQUIRE(c && accel && s && h_seeds && out, "null");
+    REQUIRE(s->materials && s->n_materials >= 8 && s->camera && s->light_triangles && s->light_surface_areas &&
+                s->light_triangle_indices && s->n_lights > 0, "incomplete scene description (needs >= 8 materials, >= 1 light)");
+    *out = nullptr;
+    CK(cudaSetDevice(c->device));
+    const Camera *cam = reinterpret_cast<const Camera *>(s->camera);
+    REQUIRE(cam->pixel_width > 0 && cam->pixel_height > 0, "bad camera resolution");
+    uint32_t n_pixels = (uint32_t)cam->pixel_width * (uint32_t)cam->pixel_height;
+    if (!h_sample_ids) n_local = n_pixels;
+    REQUIRE(n_local > 0 && n_local <= n_pixels, "bad n_local");
+    if (h_sample_ids)
+        for (uint32_t i = 0; i < n_local; i++) REQUIRE(h_sample_ids[i] < n_pixels, "sample id out of range");
+
+    clv_renderer *r = new (std::nothrow) clv_renderer();
+    if (!r) return fail(CLV_ERR_NOMEM, "host allocation");
+    r->ctx = c; r->accel = accel;
+    r->width = cam->pixel_width; r->height = cam->pixel_height; r->n_pixels = n_pixels; r->n_local = n_local;
+    r->light_count = s->n_lights;
+    r->mode = CLV_TRAVERSE_ORDERED;
+    r->passes = 0;
+    r->timing = 0;
+    r->kernel_ms[0] = r->kernel_ms[1] = r->kernel_ms[2] = 0.0;
+    r->timed_passes = 0;
+    if (h_sample_ids) r->sample_ids.assign(h_sample_ids, h_sample_ids + n_local);
+    int rc;
+#define TRY(x) do { rc = (x); if (rc != CLV_OK) { clv_renderer_destroy(r); return rc; } } while (0)
+    TRY(upload_new(c, (void **)&r->d_materials, s->materials, (size_t)s->n_materials * sizeof(Material)));
+    TRY(upload_new(c, (void **)&r->d_camera, s->camera, sizeof(Camera)));
+    TRY(upload_new(c, (void **)&r->d_light_triangles, s->light_triangles, (size_t)s->n_lights * sizeof(Triangle)));
+    TRY(upload_new(c, (void **)&r->d_light_areas, s->light_surface_areas, (size_t)s->n_lights * 4));
+    TRY(upload_new(c, (void **)&r->d_light_tri_idx, s->light_triangle_indices, (size_t)s->n_lights * 4));
+    TRY(upload_new(c, (void **)&r->d_sample_ids, h_sample_ids, h_sample_ids ? (size_t)n_local * 4 : 0));
+    auto zalloc = [&](void **p, size_t nbytes) -> int {
+        CK(cudaMalloc(p, nbytes));
+        CK(cudaMemsetAsync(*p, 0, nbytes, c->stream));
+        return CLV_OK;
+    };
+    TRY(zalloc((void **)&r->d_seeds, (size_t)n_local * 8));
+    TRY(zalloc((void **)&r->d_light_paths, (size_t)n_local * sizeof(Path)));
+    TRY(zalloc((void **)&r->d_camera_paths, (size_t)n_local * sizeof(Path)));
+    TRY(zalloc((void **)&r->d_aggs, (size_t)n_pixels * sizeof(WeightAggregator)));
+    TRY(zalloc((void **)&r->d_light_image, (size_t)n_pixels * sizeof(V4)));
+    TRY(zalloc((void **)&r->d_accum, (size_t)n_pixels * sizeof(Accum)));
+    TRY(zalloc((void **)&r->d_pass_weight, 16));
+    TRY(load_seeds(r, h_seeds));
+#undef TRY
+    CK(cudaStreamSynchronize(c->stream));
+    *out = r;
+    return CLV_OK;
+}
+
+extern "C" int clv_renderer_set_traverse_mode(clv_renderer *r, int mode) {
+    REQUIRE(r, "null");
+    REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
+    r->mode = mode;
+    return CLV_OK;
+}
+
+static int launch_pass(clv_renderer *r) {
+    clv_ctx *c = r->ctx;
+    const uint32_t *ids = r->sample_ids.empty() ? nullptr : r->d_sample_ids;
+    uint32_t n = r->n_local;
+    size_t ev0 = r->events.size();
+    if (r->timing) {
+        for (int k = 0; k < 4; k++) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            r->events.push_back(e);
+        }
+        CK(cudaEventRecord(r->events[ev0], c->stream));
+    }
+#define CALL(M, CT) k_fused_walks<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, r->d_light_paths, r->d_camera_paths, r->d_accum, c->d_counters)
+    DISPATCH_MC(r->mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], c->stream));
+    LightSink sink;
+    memset(&sink, 0, sizeof sink);
+    sink.splat_image = r->d_light_image;
+    sink.n_pixels = (int)r->n_pixels;
+#define CALL(M, CT) k_connect_paths<M, true, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_camera_paths, r->d_light_paths, r->accel->view, r->d_materials, r->d_camera, r->d_aggs, nullptr, sink, c->d_counters + COUNTERS_CONNECT)
+    DISPATCH_MC(r->mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 2], c->stream));
+    k_fused_finalize<<<GRID(r->n_pixels), CLV_BLOCK, 0, c->stream>>>(r->n_pixels, r->d_aggs, r->d_camera, r->d_light_image, r->d_accum, r->d_pass_weight);
+    LAUNCHED(c);
+    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 3], c->stream));
+    r->passes++;
+    return CLV_OK;
+}
+
+/* per-kernel device times of the fused pass, from CUDA events on the launch stream */
+extern "C" int clv_renderer_kernel_timing(clv_renderer *r, int enabled) {
+    REQUIRE(r, "null");
+    r->timing = enabled ? 1 : 0;
+    return CLV_OK;
+}
+extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[3], uint64_t *passes_out, int reset) {
+    REQUIRE(r && ms_out && passes_out, "null");
+    CK(cudaSetDevice(r->ctx->device));
+    CK(cudaStreamSynchronize(r->ctx->stream));
+    for (size_t i = 0; i + 3 < r->events.size(); i += 4) {
+        for (int k = 0; k < 3; k++) {
+            float ms = 0.0f;
+            CK(cudaEventElapsedTime(&ms, r->events[i + k], r->events[i + k + 1]));
+            r->kernel_ms[k] += ms;
+        }
+        r->timed_passes++;
+    }
+    for (cudaEvent_t e : r->events) cudaEventDestroy(e);
+    r->events.clear();
+    for (int k = 0; k < 3; k++) ms_out[k] = r->kernel_ms[k];
+    *passes_out = r->timed_passes;
+    if (reset) {
+        r->kernel_ms[0] = r->kernel_ms[1] = r->kernel_ms[2] = 0.0;
+        r->timed_passes = 0;
+    }
+    return CLV_OK;
+}
+
+extern "C" int clv_renderer_run_sample(clv_renderer *r) {
+    REQUIRE(r, "null");
+    CK(cudaSetDevice(r->ctx->device));
+    return launch_pass(r);
+}
+
+extern "C" int clv_renderer_run_sample_e2e(clv_renderer *r, const uint32_t *h_seeds, float *h_accum) {
+    REQUIRE(r, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    if (h_seeds) {
+        int rc = load_seeds(r, h_seeds);
+        if (rc != CLV_OK) return rc;
+    }
+    int rc = launch_pass(r);
+    if (rc != CLV_OK) return rc;
+    if (h_accum) {
+        CK(cudaMemcpyAsync(h_accum, r->d_accum, (size_t)r->n_pixels * sizeof(Accum), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return CLV_OK;
+}
+
+extern "C" int clv_renderer_reset(clv_renderer *r, const uint32_t *h_seeds) {
+    REQUIRE(r, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(r->d_accum, 0, (size_t)r->n_pixels * sizeof(Accum), c->stream));
+    CK(cudaMemsetAsync(r->d_light_image, 0, (size_t)r->n_pixels * sizeof(V4), c->stream));
+    CK(cudaMemsetAsync(r->d_aggs, 0, (size_t)r->n_pixels * sizeof(WeightAggregator), c->stream));
+    CK(cudaMemsetAsync(r->d_pass_weight, 0, 16, c->stream));
+    r->passes = 0;
+    if (h_seeds) return load_seeds(r, h_seeds);
+    return CLV_OK;
+}
+
+extern "C" int clv_renderer_device_ptr(clv_renderer *r, int buffer_id, void **d_ptr, size_t *nbytes) {
+    REQUIRE(r && d_ptr && nbytes, "null");
+    switch (buffer_id) {
+    case CLV_BUF_ACCUM_PACKED: *d_ptr = r->d_accum; *nbytes = (size_t)r->n_pixels * sizeof(Accum); return CLV_OK;
+    case CLV_BUF_SEEDS: *d_ptr = r->d_seeds; *nbytes = (size_t)r->n_local * 8; return CLV_OK;
+    case CLV_BUF_LIGHT_PATHS: *d_ptr = r->d_light_paths; *nbytes = (size_t)r->n_local * sizeof(Path); return CLV_OK;
+    case CLV_BUF_CAMERA_PATHS: *d_ptr = r->d_camera_paths; *nbytes = (size_t)r->n_local * sizeof(Path); return CLV_OK;
+    case CLV_BUF_AGGREGATORS: *d_ptr = r->d_aggs; *nbytes = (size_t)r->n_pixels * sizeof(WeightAggregator); return CLV_OK;
+    case CLV_BUF_PASS_WEIGHT: *d_ptr = r->d_pass_weight; *nbytes = 4; return CLV_OK;
+    default: return fail(CLV_ERR_INVALID, "buffer %d has no device-side representation of its own", buffer_id);
+    }
+}
+
+extern "C" int clv_renderer_read(clv_renderer *r, int buffer_id, void *h_dst, size_t nbytes) {
+    REQUIRE(r && h_dst, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    size_t np = r->n_pixels;
+    if (buffer_id <= CLV_BUF_UNIDIRECTIONAL) {
+        static const size_t per_pixel[4] = {12, 4, 4, 12};
+        REQUIRE(nbytes == np * per_pixel[buffer_id], "size mismatch");
+        std::vector<Accum> acc(np);
+        CK(cudaMemcpyAsync(acc.data(), r->d_accum, np * sizeof(Accum), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float *f = (float *)h_dst;
+        int32_t *iv = (int32_t *)h_dst;
+        for (size_t i = 0; i < np; i++) {
+            switch (buffer_id) {
+            case CLV_BUF_SUMMED_IMAGE: f[3 * i] = acc[i].image[0]; f[3 * i + 1] = acc[i].image[1]; f[3 * i + 2] = acc[i].image[2]; break;
+            case CLV_BUF_SUMMED_SAMPLE_COUNTS: iv[i] = (int32_t)acc[i].count; break;
+            case CLV_BUF_SUMMED_SAMPLE_WEIGHTS: f[i] = acc[i].weight; break;
+            default: f[3 * i] = acc[i].uni[0]; f[3 * i + 1] = acc[i].uni[1]; f[3 * i + 2] = acc[i].uni[2]; break;
+            }
+        }
+        return CLV_OK;
+    }
+    void *d;
+    size_t sz;
+    int rc = clv_renderer_device_ptr(r, buffer_id, &d, &sz);
+    if (rc != CLV_OK) return rc;
+    REQUIRE(nbytes == sz, "size mismatch");
+    CK(cudaMemcpyAsync(h_dst, d, sz, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CLV_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * section 6: parity / measurement hooks
+ * ------------------------------------------------------------------------------------------------------------- */
+extern "C" int clv_traverse(clv_ctx *c, const clv_accel *accel, const clv_Ray *h_rays, uint32_t n, int mode,
+                            int32_t *h_tri, float *h_t, float *h_u, float *h_v) {
+    REQUIRE(c && accel && (n == 0 || (h_rays && h_tri && h_t && h_u && h_v)), "null");
+    REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    Ray *d_rays = nullptr;
+    int32_t *d_tri = nullptr;
+    float *d_f = nullptr;
+    CK(cudaMalloc(&d_rays, (size_t)n * sizeof(Ray)));
+    CK(cudaMalloc(&d_tri, (size_t)n * 4));
+    CK(cudaMalloc(&d_f, (size_t)n * 12));
+    CK(cudaMemcpyAsync(d_rays, h_rays, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, c->stream));
+#define CALL(M, CT) k_traverse<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, d_rays, accel->view, d_tri, d_f, d_f + n, d_f + 2 * (size_t)n, c->d_counters)
+    DISPATCH_MC(mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(h_tri, d_tri, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_t, d_f, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_u, d_f + n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_v, d_f + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_rays); cudaFree(d_tri); cudaFree(d_f);
+    return CLV_OK;
+}
+
+/* device-resident variant for timing: rays and outputs are device pointers (float outputs: t, u, v of n each) */
+extern "C" int clv_traverse_device(clv_ctx *c, const clv_accel *accel, const clv_Ray *d_rays, uint32_t n, int mode,
+                                   int32_t *d_tri, float *d_t, float *d_u, float *d_v) {
+    REQUIRE(c && accel && d_rays && d_tri && d_t && d_u && d_v, "null");
+    REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+#define CALL(M, CT) k_traverse<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, (const Ray *)d_rays, accel->view, d_tri, d_t, d_u, d_v, c->d_counters)
+    DISPATCH_MC(mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+extern "C" int clv_visibility(clv_ctx *c, const clv_accel *accel, const clv_Ray *h_a, const clv_Ray *h_b, uint32_t n,
+                              int mode, int32_t *h_visible) {
+    REQUIRE(c && accel && (n == 0 || (h_a && h_b && h_visible)), "null");
+    REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
+    if (!n) return CLV_OK;
+    CK(cudaSetDevice(c->device));
+    Ray *d_a = nullptr, *d_b = nullptr;
+    int32_t *d_v = nullptr;
+    CK(cudaMalloc(&d_a, (size_t)n * sizeof(Ray)));
+    CK(cudaMalloc(&d_b, (size_t)n * sizeof(Ray)));
+    CK(cudaMalloc(&d_v, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_a, h_a, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_b, h_b, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, c->stream));
+#define CALL(M, CT) k_visibility<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, d_a, d_b, accel->view, d_v, c->d_counters)
+    DISPATCH_MC(mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(h_visible, d_v, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_v);
+    return CLV_OK;
+}
+
+extern "C" int clv_counters_enable(clv_ctx *c, int enabled) {
+    REQUIRE(c, "null");
+    c->counting = enabled ? 1 : 0;
+    return CLV_OK;
+}
+extern "C" int clv_counters_read(clv_ctx *c, uint64_t out[10], int reset) {
+    REQUIRE(c && out, "null");
+    CK(cudaSetDevice(c->device));
+    Counters h[COUNTERS_CLASSES];
+    CK(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < COUNTERS_CLASSES; k++) {
+        uint64_t *o = out + CLV_COUNTER_WORDS * k;
+        o[0] = h[k].rays_ref; o[1] = h[k].rays_traced; o[2] = h[k].node_fetches; o[3] = h[k].tri_fetches;
+        o[4] = h[k].vertices;
+    }
+    if (reset) CK(cudaMemsetAsync(c->d_counters, 0, sizeof h, c->stream));
+    return CLV_OK;
+}
+extern "C" int clv_launch_count(clv_ctx *c, uint64_t *count) {
+    REQUIRE(c && count, "null");
+    *count = c->launches;
+    return CLV_OK;
+}

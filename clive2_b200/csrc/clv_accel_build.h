@@ -1,0 +1,119 @@
+/* clv_accel_build.h — host side of clv_accel_create: reference Box[]/Triangle[] (bvh.py:329-389 encoding) ->
+ * compact traversal layout described at clv_device.cuh `AccelView`.  Plain C++, no CUDA: included by clive_b200.cu
+ * (product) and by tests/hostemu (CPU check of the kernel logic).
+ */
+#ifndef CLV_ACCEL_BUILD_H
+#define CLV_ACCEL_BUILD_H
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "clv_device.cuh"
+
+namespace clv {
+
+struct NodeRec { V4 a, b, c, d; };
+static_assert(sizeof(NodeRec) == 64, "NodeRec");
+
+struct HostAccel {
+    std::vector<NodeRec> nodes;       /* inner nodes; reference inner boxes first (in reference order), then synthetic */
+    std::vector<V4> tris;             /* 3 per triangle, reference order */
+    std::vector<int32_t> camera_tris; /* indices of is_camera triangles */
+    int32_t root_ref;
+};
+
+inline NodeRec pack_node(const Box &l, const Box &r, int32_t lref, int32_t rref) {
+    NodeRec n;
+    n.a = v4(l.min.x, l.min.y, l.min.z, l.max.x);
+    n.b = v4(l.max.y, l.max.z, r.min.x, r.min.y);
+    n.c = v4(r.min.z, r.max.x, r.max.y, r.max.z);
+    float lf, rf;
+    memcpy(&lf, &lref, 4);
+    memcpy(&rf, &rref, 4);
+    n.d = v4(lf, rf, 0.0f, 0.0f);
+    return n;
+}
+
+/* a leaf range as a ref; ranges longer than 15 become a chain of synthetic inner nodes that carry the leaf's own box
+ * on both sides (the slab test of the leaf is simply repeated), first half on the side the reference order visits
+ * first (the right one) */
+inline int32_t leaf_ref(std::vector<NodeRec> &nodes, const Box &bx, int32_t first, int32_t last) {
+    int32_t count = last - first;
+    if (count <= 15) return ~((first << 4) | count);
+    int32_t mid = first + count / 2;
+    size_t me = nodes.size();
+    nodes.push_back(NodeRec());
+    int32_t right = leaf_ref(nodes, bx, first, mid);
+    int32_t left = leaf_ref(nodes, bx, mid, last);
+    nodes[me] = pack_node(bx, bx, left, right);
+    return (int32_t)me;
+}
+
+/* returns NULL on success, else a description of what is wrong with the input */
+inline const char *build_host_accel(const Box *boxes, int32_t n_boxes, const Triangle *tris, int32_t n_tris,
+                                    HostAccel &H) {
+    static thread_local char why[160];
+    if (n_boxes <= 0 || n_tris <= 0) return "empty scene";
+    if (n_tris >= (1 << 27)) return "more than 2^27 triangles";
+    /* validate the encoding of bvh.py:345-349 before trusting indices on the device */
+    for (int32_t b = 0; b < n_boxes; b++) {
+        const Box &bx = boxes[b];
+        if (bx.right == 0) {
+            if (!(bx.left > b && bx.left + 1 < n_boxes)) {
+                snprintf(why, sizeof why, "box %d: bad child index %d", b, bx.left);
+                return why;
+            }
+        } else if (!(bx.left >= 0 && bx.left < bx.right && bx.right <= n_tris)) {
+            snprintf(why, sizeof why, "box %d: bad triangle range [%d,%d)", b, bx.left, bx.right);
+            return why;
+        }
+    }
+    std::vector<int32_t> inner_index(n_boxes, -1);
+    int32_t n_inner = 0;
+    for (int32_t b = 0; b < n_boxes; b++)
+        if (boxes[b].right == 0) inner_index[b] = n_inner++;
+    H.nodes.assign(n_inner, NodeRec());
+    auto ref_of = [&](int32_t b) -> int32_t {
+        const Box &bx = boxes[b];
+        return bx.right == 0 ? inner_index[b] : leaf_ref(H.nodes, bx, bx.left, bx.right);
+    };
+    for (int32_t b = 0; b < n_boxes; b++) {
+        const Box &bx = boxes[b];
+        if (bx.right != 0) continue;
+        int32_t l = bx.left, r = bx.left + 1;
+        int32_t lref = ref_of(l), rref = ref_of(r);
+        H.nodes[inner_index[b]] = pack_node(boxes[l], boxes[r], lref, rref);
+    }
+    H.root_ref = ref_of(0);
+
+    /* reference visiting rank of every triangle: DFS from box 0, right child popped first (trace.metal:158-161) */
+    std::vector<int32_t> rank(n_tris, 0x7fffffff);
+    {
+        std::vector<int32_t> stack;
+        stack.push_back(0);
+        int32_t next = 0;
+        while (!stack.empty()) {
+            int32_t b = stack.back();
+            stack.pop_back();
+            const Box &bx = boxes[b];
+            if (bx.right == 0) { stack.push_back(bx.left); stack.push_back(bx.left + 1); }
+            else for (int32_t i = bx.left; i < bx.right; i++) rank[i] = next++;
+        }
+    }
+    H.tris.resize((size_t)n_tris * 3);
+    H.camera_tris.clear();
+    for (int32_t i = 0; i < n_tris; i++) {
+        const Triangle &t = tris[i];
+        float rk;
+        memcpy(&rk, &rank[i], 4);
+        H.tris[3 * (size_t)i + 0] = v4(t.v0.x, t.v0.y, t.v0.z, rk);
+        H.tris[3 * (size_t)i + 1] = v4(t.v1.x - t.v0.x, t.v1.y - t.v0.y, t.v1.z - t.v0.z, 0.0f);
+        H.tris[3 * (size_t)i + 2] = v4(t.v2.x - t.v0.x, t.v2.y - t.v0.y, t.v2.z - t.v0.z, 0.0f);
+        if (t.is_camera) H.camera_tris.push_back(i);
+    }
+    return nullptr;
+}
+
+} /* namespace clv */
+#endif

@@ -1,0 +1,1051 @@
+/* clv_device.cuh — per-sample device code of the BDPT hot path (sm_100a), shared by every kernel in clv_kernels.cu.
+ *
+ * Everything here is `__host__ __device__`: the product only ever runs the device instantiation
+ * (libclive_b200.so has no host execution path and fails when no GPU is present); tests/hostemu compiles the same
+ * functions for the host so the kernel logic can be diffed against the oracle in a container without a GPU.
+ *
+ * Arithmetic contract: IEEE binary32, one rounding per source operation, NO fused multiply-add
+ * (the translation unit is compiled with -fmad=false), correctly rounded div/sqrt (nvcc defaults), elementary
+ * functions from clv_math.h.  With that contract every buffer written by these kernels equals, bit for bit, what
+ * oracle/trace_ref.c built with -DCLV_SHARED_MATH writes for the same inputs.
+ *
+ * What is restated from the reference (src/trace.metal) and what is new:
+ *   records          trace.metal:7-85            same layouts (include/clive_b200.h)
+ *   RNG              trace.metal:87-93           same integer stream
+ *   slab / triangle  trace.metal:106-142         same operations on a compact layout (child boxes stored in the parent,
+ *                                                v0/e1/e2 per triangle with e1,e2 pre-subtracted in fp32 = same bits)
+ *   traversal        trace.metal:144-176         REFERENCE mode = same visiting order; ORDERED mode = near child first
+ *                                                with a (t, reference-DFS-rank) tie rule, same result
+ *   shadow rays      trace.metal:178-197         target triangle tested first, early exit on the first occluder
+ *   projection rays  trace.metal:569-617         sensor triangles tested first, traversal skipped when they miss
+ *   BSDFs            trace.metal:200-379         same formulas
+ *   random walk      trace.metal:381-532         vertices streamed to the Path record as they are produced
+ *   connection       trace.metal:620-869         per-sample MIS terms staged once (shared memory), per-strategy work
+ *                                                reduced to the connecting edge
+ */
+#ifndef CLV_DEVICE_CUH
+#define CLV_DEVICE_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/clive_b200.h"
+#include "clv_math.h"
+
+#if defined(__CUDACC__)
+#define CLV_HD __host__ __device__ __forceinline__
+#define CLV_HDM __host__ __device__ __forceinline__ /* member functions */
+#else
+#define CLV_HD static inline
+#define CLV_HDM inline
+#endif
+
+#define CLV_PI 3.14159265359f /* trace.metal:4 */
+#define CLV_DELTA 0.0001f     /* trace.metal:5 */
+#define CLV_INF (clv_bits_to_float(0x7f800000u))
+#define CLV_MAX_BOUNCES 6     /* trace.metal:407 */
+#define CLV_STACK 64          /* trace.metal:145 */
+
+namespace clv {
+
+/* ---- vectors ------------------------------------------------------------------------------------------------ */
+struct alignas(16) V4 { float x, y, z, w; };
+struct V3 { float x, y, z; };
+
+CLV_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+CLV_HD V3 xyz(const V4 &a) { return v3(a.x, a.y, a.z); }
+CLV_HD V4 pad0(const V3 &a) { V4 r; r.x = a.x; r.y = a.y; r.z = a.z; r.w = 0.0f; return r; }
+CLV_HD V4 v4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+CLV_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+CLV_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+CLV_HD V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+CLV_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+CLV_HD V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+CLV_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+CLV_HD V3 rcp(V3 a) { return v3(1.0f / a.x, 1.0f / a.y, 1.0f / a.z); }
+CLV_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+CLV_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+CLV_HD float length(V3 a) { return sqrtf(dot(a, a)); }
+CLV_HD V3 normalize(V3 a) { return a / length(a); }
+
+/* ---- records (same bytes as include/clive_b200.h, 16-byte aligned so that copies compile to 128-bit accesses) -- */
+struct alignas(16) Ray {
+    V4 origin, direction, inv_direction, color, normal;
+    int32_t material, triangle;
+    float c_importance, l_importance, tot_importance;
+    int32_t hit_light, from_camera, hit_camera, pixel_idx;
+    int32_t pad[3];
+};
+struct alignas(16) Path {
+    Ray rays[8];
+    int32_t length, from_camera, pad[2];
+};
+struct alignas(16) Box { V4 min, max; int32_t left, right, pad[2]; };
+struct alignas(16) Triangle {
+    V4 v0, v1, v2, n0, n1, n2, normal;
+    int32_t material, is_light, is_camera, pad;
+};
+struct alignas(16) Material { V4 color, emission; int32_t type; float alpha, ior; int32_t pad; };
+struct alignas(16) Camera {
+    V4 center, focal_point, direction, dx, dy;
+    int32_t pixel_width, pixel_height;
+    float phys_width, phys_height, h_fov, v_fov;
+    int32_t pad[2];
+};
+struct alignas(16) WeightAggregator {
+    float weights[3][3];
+    float pad0[3];
+    V4 total_contribution;
+    float contrib_weight_sum;
+    float pad1[3];
+};
+static_assert(sizeof(Ray) == sizeof(clv_Ray) && sizeof(Ray) == 128, "Ray");
+static_assert(sizeof(Path) == sizeof(clv_Path) && sizeof(Path) == 1040, "Path");
+static_assert(sizeof(Box) == sizeof(clv_Box) && sizeof(Box) == 48, "Box");
+static_assert(sizeof(Triangle) == sizeof(clv_Triangle) && sizeof(Triangle) == 128, "Triangle");
+static_assert(sizeof(Material) == sizeof(clv_Material) && sizeof(Material) == 48, "Material");
+static_assert(sizeof(Camera) == sizeof(clv_Camera) && sizeof(Camera) == 112, "Camera");
+static_assert(sizeof(WeightAggregator) == sizeof(clv_WeightAggregator) && sizeof(WeightAggregator) == 80, "WA");
+
+/* read-only 16-byte load through the non-coherent path */
+CLV_HD V4 ld4(const V4 *p) {
+#if defined(__CUDA_ARCH__)
+    float4 f = __ldg(reinterpret_cast<const float4 *>(p));
+    return v4(f.x, f.y, f.z, f.w);
+#else
+    return *p;
+#endif
+}
+CLV_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+CLV_HD float i2f(int i) { return clv_bits_to_float((uint32_t)i); }
+
+/* ---- work counters (instrumented kernel variants only; the timed variants compile all of this out) -------------- */
+struct Counters {
+    unsigned long long rays_ref;     /* traverse_bvh invocations the reference would make */
+    unsigned long long rays_traced;  /* traversals this implementation actually starts */
+    unsigned long long node_fetches; /* 64-byte inner-node records fetched */
+    unsigned long long tri_fetches;  /* 48-byte triangle records fetched */
+    unsigned long long vertices;     /* 128-byte path vertices written (walks) or staged (connection) */
+};
+#define CLV_COUNTER_WORDS 5
+enum { COUNTERS_WALK = 0, COUNTERS_CONNECT = 1, COUNTERS_CLASSES = 2 };
+template <bool COUNT> struct Cnt;
+template <> struct Cnt<false> {
+    CLV_HDM void ray_ref() {} CLV_HDM void ray_traced() {} CLV_HDM void node() {} CLV_HDM void tri() {}
+    CLV_HDM void vertex(int) {}
+};
+template <> struct Cnt<true> {
+    unsigned int rr = 0, rt = 0, nf = 0, tf = 0, vx = 0;
+    CLV_HDM void ray_ref() { rr++; } CLV_HDM void ray_traced() { rt++; } CLV_HDM void node() { nf++; } CLV_HDM void tri() { tf++; }
+    CLV_HDM void vertex(int n) { vx += (unsigned)n; }
+};
+
+/* ---- RNG (trace.metal:87-93) -------------------------------------------------------------------------------- */
+CLV_HD float xorshift_random(uint32_t &seed) {
+    seed ^= seed << 13;
+    seed ^= seed >> 17;
+    seed ^= seed << 5;
+    return (float)seed / 4294967296.0f; /* (float)0xFFFFFFFF rounds to 2^32 */
+}
+
+/* ---- acceleration structure view ------------------------------------------------------------------------------ *
+ * nodes: 4 x V4 per inner node  [lmin.xyz lmax.x] [lmax.yz rmin.xy] [rmin.z rmax.xyz] [lref rref - -]
+ *        a ref >= 0 is an inner node index, a ref < 0 is a leaf: ~ref = (first_triangle << 4) | count, count 1..15
+ * tris : 3 x V4 per triangle in REFERENCE order [v0.xyz rank] [e1.xyz -] [e2.xyz -], e1 = v1 - v0, e2 = v2 - v0 (fp32),
+ *        rank = position of the triangle in the reference's traversal order with no pruning (trace.metal:158-161)
+ */
+struct AccelView {
+    const V4 *nodes;
+    const V4 *tris;
+    const Triangle *ref_triangles; /* shading data (normals, material, flags), reference records */
+    V4 root_min, root_max;
+    int32_t root_ref;
+    int32_t n_camera_tris;
+    const int32_t *camera_tris; /* indices of is_camera triangles */
+};
+
+CLV_HD void slab_test(V3 o, V3 inv, V3 bmin, V3 bmax, bool &hit, float &t_entry) { /* trace.metal:106-115, t = INF */
+    V3 t0s = (bmin - o) * inv;
+    V3 t1s = (bmax - o) * inv;
+    float tminx = fminf(t0s.x, t1s.x), tminy = fminf(t0s.y, t1s.y), tminz = fminf(t0s.z, t1s.z);
+    float tmaxx = fmaxf(t0s.x, t1s.x), tmaxy = fmaxf(t0s.y, t1s.y), tmaxz = fmaxf(t0s.z, t1s.z);
+    float tmin_final = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.0f));
+    float tmax_final = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, CLV_INF));
+    hit = tmin_final <= tmax_final;
+    t_entry = tmin_final;
+}
+
+/* Moeller-Trumbore exactly as trace.metal:117-142 with edge1/edge2 already formed */
+CLV_HD bool tri_test(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float &t_out, float &u, float &v) {
+    V3 h = cross(d, e2);
+    float a = dot(e1, h);
+    float f = 1.0f / a;
+    V3 s = o - v0;
+    u = f * dot(s, h);
+    if (u < 0 || u > 1) return false;
+    V3 q = cross(s, e1);
+    v = f * dot(d, q);
+    if (v < 0 || u + v > 1) return false;
+    float t = f * dot(e2, q);
+    if (t > CLV_DELTA) { t_out = t; return true; }
+    return false;
+}
+
+enum { TRAVERSE_REFERENCE = 0, TRAVERSE_ORDERED = 1 };
+
+/* Closest hit.  Result contract = trace.metal:144-176: the first triangle, in the reference's visiting order, that
+ * attains the minimum t among the triangles whose boxes pass `hit && t_entry < best_t`.
+ *   REFERENCE: visits right child first like the reference (children tested when the parent is expanded, the deferred
+ *              one re-checked against best_t when popped = the same predicate the reference evaluates at pop time).
+ *   ORDERED  : near child first; exact ties in t resolved by the reference rank, boxes kept while t_entry <= best_t so
+ *              tie candidates are still reached.
+ * `stop_below`/`stop_skip`: early exit for predicate rays — as soon as a triangle other than `stop_skip` is accepted
+ * with t < stop_below the search ends (the caller only needs to know that such a hit exists).  Pass -INF to disable.
+ */
+template <int MODE, bool COUNT>
+CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, float &best_t, float &bu, float &bv,
+                        Cnt<COUNT> &cnt, float stop_below, int stop_skip) {
+    int st_ref[CLV_STACK];
+    float st_t[CLV_STACK];
+    int sp = 0;
+    int best_rank = 0x7fffffff;
+    cnt.ray_traced();
+
+    bool hit;
+    float te;
+    slab_test(o, inv, xyz(A.root_min), xyz(A.root_max), hit, te);
+    if (!(hit && te < best_t)) return;
+    int cur = A.root_ref;
+
+    for (;;) {
+        if (cur >= 0) {
+            const V4 *n = A.nodes + 4 * (size_t)cur;
+            V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
+            cnt.node();
+            bool hl, hr;
+            float tl, tr;
+            slab_test(o, inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
+            slab_test(o, inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
+            int lref = f2i(n3.x), rref = f2i(n3.y);
+            if (MODE == TRAVERSE_REFERENCE) {
+                /* reference pushes left then right and pops right first */
+                bool go_r = hr && tr < best_t;
+                if (go_r) {
+                    if (hl && sp < CLV_STACK) { st_ref[sp] = lref; st_t[sp] = tl; sp++; }
+                    cur = rref;
+                    continue;
+                }
+                if (hl && tl < best_t) { cur = lref; continue; }
+            } else {
+                bool go_l = hl && tl <= best_t, go_r = hr && tr <= best_t;
+                if (go_l && go_r) {
+                    bool left_first = tl < tr; /* tie: right first, the reference's order */
+                    int far_ref = left_first ? rref : lref;
+                    float far_t = left_first ? tr : tl;
+                    if (sp < CLV_STACK) { st_ref[sp] = far_ref; st_t[sp] = far_t; sp++; }
+                    cur = left_first ? lref : rref;
+                    continue;
+                }
+                if (go_l) { cur = lref; continue; }
+                if (go_r) { cur = rref; continue; }
+            }
+        } else {
+            int code = ~cur;
+            int first = code >> 4, count = code & 15;
+            for (int i = first; i < first + count; i++) {
+                const V4 *tp = A.tris + 3 * (size_t)i;
+                V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+                cnt.tri();
+                float t, u, v;
+                if (tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v)) {
+                    bool accept;
+                    if (MODE == TRAVERSE_REFERENCE) accept = t < best_t;
+                    else accept = t < best_t || (t == best_t && f2i(a.w) < best_rank);
+                    if (accept) {
+                        best_i = i; best_t = t; bu = u; bv = v;
+                        best_rank = f2i(a.w);
+                        if (i != stop_skip && t < stop_below) return;
+                    }
+                }
+            }
+        }
+        /* pop */
+        for (;;) {
+            if (sp == 0) return;
+            sp--;
+            float t = st_t[sp];
+            bool keep = (MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t);
+            if (keep) { cur = st_ref[sp]; break; }
+        }
+    }
+}
+
+/* direct test of one triangle of the reference numbering */
+CLV_HD bool test_one(const AccelView &A, int tri, V3 o, V3 d, float &t) {
+    const V4 *tp = A.tris + 3 * (size_t)tri;
+    V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+    float u, v;
+    return tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v);
+}
+
+/* visibility_test (trace.metal:178-197): the closest hit from a toward b must be b's triangle. */
+template <int MODE, bool COUNT>
+CLV_HD bool visibility_test(const AccelView &A, V3 a_origin, int a_triangle, V3 b_origin, int b_triangle,
+                            Cnt<COUNT> &cnt) {
+    V3 direction = normalize(b_origin - a_origin);
+    V3 inv = rcp(direction);
+    cnt.ray_ref();
+    float stop = -CLV_INF;
+    if (MODE == TRAVERSE_ORDERED) {
+        /* the traversal evaluates exactly this test for b's triangle; if it fails b can never be the closest hit */
+        if (b_triangle < 0 || b_triangle == a_triangle) return false;
+        float tb;
+        if (!test_one(A, b_triangle, a_origin, direction, tb)) return false;
+        stop = tb; /* any other triangle accepted below tb decides the answer */
+    }
+    int best_i = -1;
+    float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+    closest_hit<MODE, COUNT>(A, a_origin, direction, inv, best_i, best_t, u, v, cnt, stop, b_triangle);
+    if (best_i == -1) return false;
+    if (best_i == a_triangle) return false;
+    return best_i == b_triangle;
+}
+
+/* ---- sampling and BSDFs (trace.metal:200-379) ------------------------------------------------------------------- */
+CLV_HD void orthonormal(V3 n, V3 &x, V3 &y) {
+    V3 v;
+    if (fabsf(n.x) <= fabsf(n.y) && fabsf(n.x) <= fabsf(n.z)) v = v3(1, 0, 0);
+    else if (fabsf(n.y) <= fabsf(n.z)) v = v3(0, 1, 0);
+    else v = v3(0, 0, 1);
+    x = normalize(v - n * dot(v, n));
+    y = normalize(cross(n, x));
+}
+CLV_HD V3 random_hemisphere_cosine(V3 xa, V3 ya, V3 za, float rx, float ry) {
+    float theta = clv_acosf(sqrtf(rx));
+    float phi = 2 * CLV_PI * ry;
+    float st = clv_sinf(theta), ct = clv_cosf(theta), sp = clv_sinf(phi), cp = clv_cosf(phi);
+    return normalize((xa * (st * cp) + ya * (st * sp)) + za * ct);
+}
+CLV_HD V3 random_hemisphere_uniform(V3 xa, V3 ya, V3 za, float rx, float ry) {
+    float z = rx;
+    float rr = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float phi = 2 * CLV_PI * ry;
+    float sp = clv_sinf(phi), cp = clv_cosf(phi);
+    return normalize((xa * (rr * cp) + ya * (rr * sp)) + za * z);
+}
+CLV_HD V3 GGX_sample(V3 n, float rx, float ry, float alpha) {
+    V3 x, y;
+    orthonormal(n, x, y);
+    float theta = 2 * CLV_PI * rx;
+    float phi = clv_atanf(alpha * sqrtf(ry) / sqrtf(1.0f - ry));
+    float sp = clv_sinf(phi), cp = clv_cosf(phi), st = clv_sinf(theta), ct = clv_cosf(theta);
+    return normalize((x * (sp * ct) + y * (sp * st)) + n * cp);
+}
+CLV_HD V3 specular_reflection(V3 i, V3 m) { return normalize(m * (2 * dot(i, m)) - i); }
+CLV_HD V3 GGX_transmit(V3 i, V3 m, float ni, float no) { /* eta, not eta^2, as the reference has it */
+    float cos_i = dot(i, m);
+    float eta = ni / no;
+    float cos_t = sqrtf(1 + eta * (cos_i * cos_i - 1));
+    return normalize(m * (eta * cos_i - cos_t) - i * eta);
+}
+CLV_HD V3 transmit_half(V3 i, V3 o, float ni, float no) { return normalize(o * no + i * ni); }
+CLV_HD float degreve_fresnel(V3 i, V3 m, float ni, float nt) {
+    float cos_i = fabsf(dot(i, m));
+    float eta = ni / nt;
+    float sin_t2 = eta * eta * (1.0f - cos_i * cos_i);
+    if (sin_t2 >= 1.0f) return 1.0f;
+    float cos_t = sqrtf(1.0f - sin_t2);
+    float r_par = (nt * cos_i - ni * cos_t) / (nt * cos_i + ni * cos_t);
+    float r_perp = (ni * cos_i - nt * cos_t) / (ni * cos_i + nt * cos_t);
+    return 0.5f * (r_par * r_par + r_perp * r_perp);
+}
+CLV_HD float GGX_G1(V3 v, V3 m, float alpha) {
+    float mv = dot(m, v);
+    float sin2 = 1.0f - mv * mv;
+    float tan2 = sin2 / (mv * mv);
+    return 2.0f / (1.0f + sqrtf(1.0f + alpha * alpha * tan2));
+}
+CLV_HD float GGX_G(V3 i, V3 o, V3 m, V3 n, float alpha) {
+    if (dot(i, m) * dot(i, n) <= 0.0f) return 0.0f;
+    if (dot(o, m) * dot(o, n) <= 0.0f) return 0.0f;
+    return GGX_G1(i, m, alpha) * GGX_G1(o, m, alpha);
+}
+CLV_HD float GGX_D(V3 m, V3 n, float alpha) {
+    if (alpha == 0.0f) return 1.0f;
+    float alpha2 = alpha * alpha;
+    float c = dot(m, n);
+    float c2 = c * c;
+    float denom = c2 * (alpha2 - 1.0f) + 1.0f;
+    return alpha2 / (CLV_PI * denom * denom);
+}
+CLV_HD float reflect_jacobian(V3 m, V3 o) { return 1.0f / (4.0f * fabsf(dot(m, o))); }
+CLV_HD float transmit_jacobian(V3 i, V3 o, float ni, float no) {
+    V3 h = transmit_half(i, o, ni, no);
+    float ci = dot(i, h), co = dot(o, h);
+    float numerator = no * no * fabsf(co);
+    float s = ni * ci + no * co;
+    return numerator / (s * s);
+}
+CLV_HD float GGX_BRDF_reflect(V3 i, V3 o, V3 m, V3 n, float ni, float no, float alpha) {
+    float D = GGX_D(m, n, alpha), G = GGX_G(i, o, m, n, alpha), F = degreve_fresnel(i, m, ni, no);
+    return (D * G * F) / (4.0f * fabsf(dot(i, m)));
+}
+CLV_HD float GGX_BRDF_transmit(V3 i, V3 o, V3 m, V3 n, float ni, float no, float alpha) {
+    V3 h = transmit_half(i, o, ni, no);
+    float D = GGX_D(m, n, alpha), G = GGX_G(i, o, m, n, alpha), F = degreve_fresnel(i, m, ni, no);
+    float im = dot(i, h), om = dot(o, h), in = dot(i, n), on = dot(o, n);
+    float coeff = (im * om) / (in * on);
+    float num = no * no * D * G * (1.0f - F);
+    float s = ni * im + no * om;
+    return coeff * num / (s * s);
+}
+CLV_HD void diffuse_bounce(V3 wi, V3 n, bool from_camera, float rx, float ry, V3 &wo, float &f, float &c_p, float &l_p) {
+    V3 x, y;
+    orthonormal(n, x, y);
+    wo = random_hemisphere_cosine(x, y, n, rx, ry);
+    f = fabsf(dot(n, wo)) / CLV_PI;
+    float po = fabsf(dot(n, wo)) / CLV_PI, pi_ = fabsf(dot(n, wi)) / CLV_PI;
+    if (from_camera) { c_p = po; l_p = pi_; } else { c_p = pi_; l_p = po; }
+}
+CLV_HD void reflect_bounce(V3 wi, V3 n, V3 m, float ni, float no, float alpha, bool from_camera, V3 &wo, float &f,
+                           float &c_p, float &l_p) {
+    wo = specular_reflection(wi, m);
+    f = GGX_BRDF_reflect(wi, wo, m, n, ni, no, alpha);
+    float pf = degreve_fresnel(wi, m, ni, no);
+    float pm = fabsf(dot(m, n)) * GGX_D(m, n, alpha);
+    float po = pf * pm * reflect_jacobian(m, wo), pi_ = pf * pm * reflect_jacobian(m, wi);
+    if (from_camera) { c_p = po; l_p = pi_; } else { c_p = pi_; l_p = po; }
+}
+CLV_HD void transmit_bounce(V3 wi, V3 n, V3 m, float ni, float no, float alpha, bool from_camera, V3 &wo, float &f,
+                            float &c_p, float &l_p) {
+    wo = GGX_transmit(wi, m, ni, no);
+    f = GGX_BRDF_transmit(wi, wo, m, n, ni, no, alpha);
+    float pf = 1.0f - degreve_fresnel(wi, m, ni, no);
+    float pm = fabsf(dot(m, n)) * GGX_D(m, n, alpha);
+    float fwd = pf * pm * transmit_jacobian(wi, wo, ni, no), rev = pf * pm * transmit_jacobian(wo, wi, no, ni);
+    if (from_camera) { c_p = fwd; l_p = rev; } else { c_p = rev; l_p = fwd; }
+}
+
+/* ---- ray generation --------------------------------------------------------------------------------------------- */
+CLV_HD Ray zero_ray() {
+    Ray r;
+    r.origin = r.direction = r.inv_direction = r.color = r.normal = v4(0, 0, 0, 0);
+    r.material = r.triangle = 0;
+    r.c_importance = r.l_importance = r.tot_importance = 0.0f;
+    r.hit_light = r.from_camera = r.hit_camera = r.pixel_idx = 0;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    return r;
+}
+
+/* generate_camera_rays, trace.metal:1020-1067 */
+CLV_HD Ray make_camera_ray(const Camera &c, int pixel_idx, uint32_t &seed0, uint32_t &seed1) {
+    Ray ray = zero_ray();
+    float x_offset = xorshift_random(seed0);
+    float y_offset = xorshift_random(seed1);
+    int pixel_x = pixel_idx % c.pixel_width;
+    int pixel_y = pixel_idx / c.pixel_width;
+    float x_n = ((float)pixel_x + x_offset - 0.5f * (float)c.pixel_width) / (float)c.pixel_width;
+    float y_n = ((float)pixel_y + y_offset - 0.5f * (float)c.pixel_height) / (float)c.pixel_height;
+    V3 x_vec = (xyz(c.dx) * x_n) * c.phys_width;
+    V3 y_vec = (xyz(c.dy) * y_n) * c.phys_height;
+    V3 origin = (xyz(c.center) + x_vec) + y_vec;
+    V3 direction = normalize(xyz(c.focal_point) - origin);
+    ray.origin = pad0(origin);
+    ray.direction = pad0(direction);
+    ray.normal = pad0(xyz(c.direction));
+    ray.inv_direction = pad0(rcp(direction));
+    ray.color = v4(1.0f, 1.0f, 1.0f, 0.0f);
+    ray.material = 7;
+    ray.triangle = -1;
+    ray.hit_light = -1;
+    ray.hit_camera = -1;
+    ray.from_camera = 1;
+    ray.c_importance = 1.0f / (c.phys_width * c.phys_height);
+    ray.l_importance = 1.0f;
+    ray.tot_importance = ray.c_importance;
+    ray.pixel_idx = pixel_idx;
+    return ray;
+}
+
+/* generate_light_rays, trace.metal:1070-1124 (light_index clamped to count-1: the reference reads out of bounds
+ * when the RNG returns exactly 1.0) */
+CLV_HD Ray make_light_ray(const Triangle *light_triangles, const float *surface_areas,
+                          const int32_t *light_triangle_indices, const Material *materials, int light_count,
+                          uint32_t &seed0, uint32_t &seed1) {
+    Ray ray = zero_ray();
+    ray.hit_light = -1;
+    ray.hit_camera = -1;
+    int light_index = (int)(xorshift_random(seed0) * (float)light_count);
+    if (light_index > light_count - 1) light_index = light_count - 1;
+    const Triangle *lt = light_triangles + light_index;
+    float surface_area = surface_areas[light_index];
+    float u = xorshift_random(seed0);
+    float v = xorshift_random(seed1);
+    if (u + v > 1.0f) { u = 1.0f - u; v = 1.0f - v; }
+    float w = 1.0f - u - v;
+    V3 n = xyz(ld4(&lt->normal));
+    V3 origin = ((xyz(ld4(&lt->v0)) * u + xyz(ld4(&lt->v1)) * v) + xyz(ld4(&lt->v2)) * w) + n * CLV_DELTA;
+    V3 x, y;
+    orthonormal(n, x, y);
+    float rand_x = xorshift_random(seed0);
+    float rand_y = xorshift_random(seed1);
+    V3 direction = random_hemisphere_uniform(x, y, n, rand_x, rand_y);
+    ray.normal = pad0(n);
+    ray.origin = pad0(origin);
+    ray.direction = pad0(direction);
+    ray.inv_direction = pad0(rcp(direction));
+    ray.material = lt->material;
+    ray.color = ld4(&materials[ray.material].emission); /* whole 16-byte slot, like the oracle's struct copy */
+    ray.triangle = light_triangle_indices[light_index];
+    ray.c_importance = 1.0f;
+    ray.l_importance = 1.0f / ((float)light_count * surface_area);
+    ray.tot_importance = ray.l_importance;
+    return ray;
+}
+
+/* ---- random walk: generate_paths, trace.metal:381-532 ----------------------------------------------------------- *
+ * Vertices are written to out_path->rays[i] as they are produced (the reference builds the Path in thread memory and
+ * copies 1040 bytes at the end).  Slots >= length keep whatever they held; nothing downstream reads them.  A path of
+ * length 0 gets a zeroed rays[0], which is what connect_paths' splat-weight code then reads (the reference reads
+ * uninitialised memory there; the oracle reads zeros).
+ */
+template <int MODE, bool COUNT>
+CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, uint32_t &seed0, uint32_t &seed1,
+                        Path *out_path, V4 *out_uni, Cnt<COUNT> &cnt) {
+    const bool from_camera = ray.from_camera != 0;
+    float carry_imp = from_camera ? ray.c_importance : 1.0f / (2.0f * CLV_PI);
+    int length = 0;
+    V4 uni = v4(0, 0, 0, 0);
+    bool uni_found = false;
+    V3 last_stored_color = v3(0, 0, 0);
+
+    for (int i = 0; i < CLV_MAX_BOUNCES; i++) {
+        int best_i = -1;
+        float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+        V3 o = xyz(ray.origin), d = xyz(ray.direction), inv = xyz(ray.inv_direction);
+        cnt.ray_ref();
+        closest_hit<MODE, COUNT>(A, o, d, inv, best_i, best_t, u, v, cnt, -CLV_INF, -1);
+        if (best_i == -1) break;
+
+        const Triangle *tri = A.ref_triangles + best_i;
+        V3 tn = xyz(ld4(&tri->normal));
+        V3 n0 = xyz(ld4(&tri->n0)), n1 = xyz(ld4(&tri->n1)), n2 = xyz(ld4(&tri->n2));
+        int tri_material = tri->material, tri_is_light = tri->is_light, tri_is_camera = tri->is_camera;
+        const Material *mat = materials + tri_material;
+        V3 mat_color = xyz(ld4(&mat->color));
+        int mat_type = mat->type;
+        float alpha = mat->alpha, ior = mat->ior;
+
+        V3 n;
+        float ni, no;
+        V3 sampled_normal = normalize((n0 * (1 - u - v) + n1 * u) + n2 * v);
+        float side = dot(-d, tn);
+        if (side > 0) { n = sampled_normal; ni = 1.0f; no = ior; }
+        else if (side < 0) { n = -sampled_normal; ni = ior; no = 1.0f; }
+        else break;
+
+        Ray nr = zero_ray();
+        if (from_camera) nr.c_importance = carry_imp; else nr.l_importance = carry_imp;
+        nr.origin = pad0(o + d * best_t);
+        nr.material = tri_material;
+        nr.triangle = best_i;
+        nr.hit_light = (tri_is_light && dot(d, tn) < 0.0f) ? best_i : -1;
+        nr.hit_camera = tri_is_camera ? best_i : -1;
+
+        V3 wi = -d;
+        float rand_x_a = xorshift_random(seed0);
+        float rand_y_a = xorshift_random(seed1);
+        float rand_x_b = xorshift_random(seed0);
+        float rand_y_b = xorshift_random(seed1);
+
+        V3 wo = v3(0, 0, 0);
+        float f = 1.0f, c_p = 1.0f, l_p = 1.0f;
+        V3 m = GGX_sample(n, rand_x_a, rand_y_a, alpha);
+        if (dot(wi, m) < 0.0f) break;
+        if (dot(m, n) < 0.0f) break;
+        nr.normal = pad0(n);
+
+        float fresnel = degreve_fresnel(wi, m, ni, no);
+        if (mat_type == 0) {
+            diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
+        } else if (mat_type == 1) {
+            if (rand_x_b <= fresnel) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+            else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+        } else if (mat_type == 2) {
+            if (rand_x_b <= fresnel) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+            else diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
+        } else {
+            reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+        }
+
+        float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
+        V3 rc = xyz(ray.color);
+        if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);
+        else nr.color = pad0(rc * f);
+        nr.direction = pad0(wo);
+        nr.inv_direction = pad0(rcp(wo));
+
+        float next_carry;
+        if (from_camera) {
+            next_carry = c_p;
+            ray.l_importance = l_p;
+            nr.tot_importance = ray.tot_importance * nr.c_importance;
+        } else {
+            next_carry = l_p;
+            ray.c_importance = c_p;
+            nr.tot_importance = ray.tot_importance * nr.l_importance;
+        }
+        if (f == 0.0f) break;
+
+        out_path->rays[i] = ray;
+        cnt.vertex(1);
+        length = i + 1;
+        if (!uni_found && ray.hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
+            V3 c = last_stored_color / ray.tot_importance;
+            uni = v4(c.x, c.y, c.z, 1.0f);
+            uni_found = true;
+        }
+        last_stored_color = xyz(ray.color);
+
+        ray = nr;
+        carry_imp = next_carry;
+    }
+    if (length == 0) out_path->rays[0] = zero_ray();
+    out_path->length = length;
+    out_path->from_camera = from_camera ? 1 : 0;
+    out_path->pad[0] = 0;
+    out_path->pad[1] = 0;
+    *out_uni = uni;
+}
+
+/* ---- connection helpers (trace.metal:539-617) ---------------------------------------------------------------------- */
+CLV_HD float abs_cos(const Ray *r) { return fabsf(dot(xyz(r->direction), xyz(r->normal))); }
+CLV_HD float geometry_from(float cos_a, float cos_b, V3 oa, V3 ob) { /* cosine_geometry_term, :539-544 */
+    float dist = length(ob - oa);
+    return cos_a * cos_b / (dist * dist);
+}
+CLV_HD V3 pixel_center(const Camera &c, int x, int y) { /* :551-562 — the pixel corner, as the reference has it */
+    float x_n = ((float)x - 0.5f * (float)c.pixel_width) / (float)c.pixel_width;
+    float y_n = ((float)y - 0.5f * (float)c.pixel_height) / (float)c.pixel_height;
+    V3 x_vec = xyz(c.dx) * (x_n * c.phys_width);
+    V3 y_vec = xyz(c.dy) * (y_n * c.phys_height);
+    return (xyz(c.center) + x_vec) + y_vec;
+}
+CLV_HD float gaussian_weight(V3 p, V3 q, float sigma) {
+    float dist = length(p - q);
+    return clv_expf(-dist * dist / (2.0f * sigma * sigma));
+}
+
+/* the sensor vertex a light vertex projects to (the fields world_ray_to_camera_ray rewrites, :607-616) */
+struct SensorVertex {
+    V3 origin, direction;
+    int triangle;
+    int pixel_idx;
+};
+
+/* world_ray_to_camera_ray, trace.metal:569-617.  Returns false when the reference leaves pixel_idx at -1. */
+template <int MODE, bool COUNT>
+CLV_HD bool project_to_sensor(const AccelView &A, const Material *materials, const Camera &c, V3 origin, int triangle,
+                              SensorVertex &out, Cnt<COUNT> &cnt) {
+    if (materials[A.ref_triangles[triangle].material].type > 0) return false;
+    V3 direction = normalize(xyz(c.focal_point) - origin);
+    if (dot(direction, xyz(c.direction)) > 0.0f) return false;
+    V3 inv = rcp(direction);
+    cnt.ray_ref();
+    float stop = -CLV_INF;
+    if (MODE == TRAVERSE_ORDERED) {
+        /* the closest hit has to be a sensor triangle: test those first; if none is hit no traversal is needed, and
+         * otherwise any other triangle accepted below the nearest sensor hit decides the answer */
+        float t_sensor = CLV_INF;
+        for (int k = 0; k < A.n_camera_tris; k++) {
+            float t;
+            if (test_one(A, A.camera_tris[k], origin, direction, t)) t_sensor = fminf(t_sensor, t);
+        }
+        if (t_sensor == CLV_INF) return false;
+        stop = t_sensor;
+    }
+    int best_i = -1;
+    float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+    /* stop_skip = -2: every triangle below `stop` ends the search (a sensor triangle cannot be below the nearest one) */
+    closest_hit<MODE, COUNT>(A, origin, direction, inv, best_i, best_t, u, v, cnt, stop, -2);
+    if (best_i == -1) return false;
+    if (!A.ref_triangles[best_i].is_camera) return false;
+
+    V3 camera_point = origin + direction * best_t;
+    float x = dot(camera_point - xyz(c.center), xyz(c.dx));
+    float y = dot(camera_point - xyz(c.center), xyz(c.dy));
+    int pixel_x = (int)roundf((x / c.phys_width + 0.5f) * (float)c.pixel_width);
+    int pixel_y = (int)roundf((y / c.phys_height + 0.5f) * (float)c.pixel_height);
+    out.pixel_idx = pixel_y * c.pixel_width + pixel_x;
+    out.origin = camera_point;
+    out.direction = normalize(xyz(c.focal_point) - camera_point);
+    out.triangle = best_i;
+    return true;
+}
+
+/* per-thread array living in shared memory (device: element k of thread at base[k * stride]) or on the stack (host) */
+struct TArr {
+    float *base;
+    int stride;
+    CLV_HDM float &operator[](int k) const { return base[k * stride]; }
+};
+#define CLV_CONNECT_SCRATCH 58 /* floats per thread, see connect_sample */
+
+/* light-image sink of the t = 1 strategies */
+struct LightSink {
+    /* staged mode (reference arrays, trace.metal:817-823) */
+    int32_t *pixel_indices, *path_indices, *ray_indices;
+    float *weights, *shade;
+    /* splat mode: per-pass light image float4[n_pixels] (xyz = colour, w = sum of weights) */
+    V4 *splat_image;
+    int n_pixels;
+};
+
+CLV_HD void atomic_add(float *p, float v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+#pragma omp atomic
+    *p += v;
+#endif
+}
+
+/* connect_paths, trace.metal:620-869, for one sample.
+ *   slot          : index of this sample in the path arrays
+ *   entry_id      : `id` used to place staged light entries at entry_id + s * total_pixels (:818)
+ *   agg_slot      : index of this sample in the aggregator / `out` arrays (the pixel it belongs to)
+ * Staging (scratch, CLV_CONNECT_SCRATCH floats): for every stored vertex its l_importance, c_importance, |dir.n|,
+ * tot_importance; for every subpath edge its geometry term.  The MIS ratios of trace.metal:709-735 are then formed
+ * from those with the same operations in the same order, so only the connecting edge costs new arithmetic per
+ * strategy (the reference recomputes every edge of the full path for each of the up to 41 strategies).
+ */
+template <int MODE, bool SPLAT, bool COUNT>
+CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, const Path *camera_paths,
+                           const Path *light_paths,
+                           const AccelView &A, const Material *materials, const Camera &c,
+                           WeightAggregator *weight_aggregators, V4 *out, const LightSink &sink, TArr S,
+                           Cnt<COUNT> &cnt) {
+    const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
+    const Ray *cr = cpath->rays, *lr = lpath->rays;
+    const int len_c = cpath->length, len_l = lpath->length;
+    const int total_pixels = c.pixel_width * c.pixel_height;
+
+    /* scratch layout */
+    enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30, C_COS = 36, C_TOT = 42, G_LL = 48,
+           G_CC = 53 };
+    unsigned spec_l = 0, spec_c = 0; /* bit i: vertex i has a specular material */
+    cnt.vertex(len_l + len_c);
+    for (int i = 0; i < len_l; i++) {
+        const Ray *r = lr + i;
+        S[L_LIMP + i] = r->l_importance;
+        S[L_CIMP + i] = r->c_importance;
+        S[L_COS + i] = abs_cos(r);
+        S[L_TOT + i] = r->tot_importance;
+        if (materials[r->material].type > 0) spec_l |= 1u << i;
+    }
+    for (int i = 0; i + 1 < len_l; i++)
+        S[G_LL + i] = geometry_from(S[L_COS + i], S[L_COS + i + 1], xyz(lr[i].origin), xyz(lr[i + 1].origin));
+    for (int j = 0; j < len_c; j++) {
+        const Ray *r = cr + j;
+        S[C_LIMP + j] = r->l_importance;
+        S[C_CIMP + j] = r->c_importance;
+        S[C_COS + j] = abs_cos(r);
+        S[C_TOT + j] = r->tot_importance;
+        if (materials[r->material].type > 0) spec_c |= 1u << j;
+    }
+    for (int j = 0; j + 1 < len_c; j++)
+        S[G_CC + j] = geometry_from(S[C_COS + j], S[C_COS + j + 1], xyz(cr[j].origin), xyz(cr[j + 1].origin));
+    const bool spec_sensor = materials[7].type > 0; /* material of the rewritten sensor vertex (:611) */
+
+    V3 total_contribution = v3(0, 0, 0);
+    float contrib_weight_sum = 0.0f;
+
+    for (int t = 1; t < len_c + 1; t++) {
+        for (int s = 0; s < len_l + 1; s++) {
+            if (t + s < 2) continue;
+
+            /* endpoint data of this strategy */
+            V3 cam_o = v3(0, 0, 0), cam_n = v3(0, 0, 0), lig_o = v3(0, 0, 0), lig_n = v3(0, 0, 0), dir_l_to_c = v3(0, 0, 0);
+            float cam_cos = 0.0f, cam_tot, g_conn = 0.0f;
+            int cam_material;
+            int light_pixel_idx = -1;
+            bool sensor_vertex = false; /* camera endpoint is the rewritten vertex 0 */
+
+            if (s == 0) {
+                const Ray *camera_ray = cr + (t - 1);
+                if (camera_ray->hit_light < 0) continue;
+                cam_tot = S[C_TOT + t - 1];
+                cam_material = camera_ray->material;
+            } else if (t == 1) {
+                const Ray *light_ray = lr + (s - 1);
+                lig_o = xyz(light_ray->origin);
+                lig_n = xyz(light_ray->normal);
+                SensorVertex sv;
+                if (!project_to_sensor<MODE, COUNT>(A, materials, c, lig_o, light_ray->triangle, sv, cnt)) continue;
+                light_pixel_idx = sv.pixel_idx;
+                sensor_vertex = true;
+                cam_o = sv.origin;
+                cam_n = xyz(c.direction);
+                cam_cos = fabsf(dot(sv.direction, cam_n));
+                cam_tot = 1.0f;
+                cam_material = 7;
+                dir_l_to_c = normalize(cam_o - lig_o);
+                g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, cam_o);
+            } else {
+                const Ray *camera_ray = cr + (t - 1);
+                const Ray *light_ray = lr + (s - 1);
+                if ((spec_l >> (s - 1)) & 1u) continue;
+                if ((spec_c >> (t - 1)) & 1u) continue;
+                cam_o = xyz(camera_ray->origin);
+                cam_n = xyz(camera_ray->normal);
+                lig_o = xyz(light_ray->origin);
+                lig_n = xyz(light_ray->normal);
+                dir_l_to_c = normalize(cam_o - lig_o);
+                if (dot(lig_n, dir_l_to_c) < CLV_DELTA) continue;
+                if (dot(cam_n, -dir_l_to_c) < CLV_DELTA) continue;
+                if (!visibility_test<MODE, COUNT>(A, lig_o, light_ray->triangle, cam_o, camera_ray->triangle, cnt)) continue;
+                cam_cos = S[C_COS + t - 1];
+                cam_tot = S[C_TOT + t - 1];
+                cam_material = camera_ray->material;
+                g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, cam_o);
+            }
+
+            /* full-path accessors: vertex i < s is light vertex i, otherwise camera vertex t+s-i-1 (:546-549) */
+            const int k = s + t; /* number of vertices */
+            auto limp = [&](int i) { return i < s ? S[L_LIMP + i] : S[C_LIMP + (k - i - 1)]; };
+            auto cimp = [&](int i) { return i < s ? S[L_CIMP + i] : S[C_CIMP + (k - i - 1)]; };
+            /* geometry term of the edge between full-path vertices i and i+1 */
+            auto edge = [&](int i) {
+                if (i + 1 < s) return S[G_LL + i];
+                if (i == s - 1) return g_conn;
+                return S[G_CC + (k - i - 2)];
+            };
+            auto ratio = [&](int i) { /* p_ratios[i], :709-735 */
+                float num, denom;
+                if (i == 0) { num = limp(0); denom = cimp(0) * edge(0); }
+                else if (i == k - 1) { num = limp(i) * edge(i - 1); denom = cimp(i); }
+                else { num = limp(i) * edge(i - 1); denom = cimp(i) * edge(i); }
+                return num / denom;
+            };
+            auto specular = [&](int i) {
+                if (i < s) return ((spec_l >> i) & 1u) != 0;
+                int j = k - i - 1;
+                if (j == 0 && sensor_vertex) return spec_sensor;
+                return ((spec_c >> j) & 1u) != 0;
+            };
+
+            float prior_light_importance = (s == 0) ? 1.0f : S[L_TOT + s - 1];
+            float p_s = cam_tot * prior_light_importance;
+
+            /* p_values[0..k] (:737-766); p_values[k] is forced to zero, p_values[k+1] is never read */
+            float pv[14];
+#pragma unroll
+            for (int i = 0; i < 14; i++) pv[i] = 0.0f;
+            {
+                float p_i = p_s;
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    if (i >= s && i < k - 1) { /* p_values[i+1] for i+1 <= k-1 */
+                        p_i = ratio(i) * p_i;
+                        pv[i + 1] = p_i;
+                    }
+                }
+                p_i = p_s;
+#pragma unroll
+                for (int i = 11; i >= 0; i--) {
+                    if (i <= s - 1) {
+                        p_i = p_i / ratio(i);
+                        pv[i] = p_i;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 13; i++)
+                if (i == s) pv[i] = p_s;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                if (i < k && specular(i)) { pv[i] = 0.0f; pv[i + 1] = 0.0f; }
+            }
+            float p_at_s = 0.0f, sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 13; i++) {
+                if (i == k) pv[i] = 0.0f;
+                if (i <= k) sum += pv[i];
+                if (i == s) p_at_s = pv[i];
+            }
+
+            float w;
+            if (p_at_s > 0.0f && sum > 0.0f) w = p_at_s / sum;
+            else continue;
+
+            V3 color;
+            float g = 1.0f, new_light_f = 1.0f;
+            if (s == 0) {
+                V3 prior_color = xyz(cr[t - 2].color);
+                V3 emission = xyz(ld4(&materials[cam_material].emission));
+                color = prior_color * emission;
+            } else if (t == 1) {
+                const Ray *light_ray = lr + (s - 1);
+                int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
+                V3 prior_color = xyz(lr[prior_light_ind].color);
+                if (s > 1) new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
+                color = (prior_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+                g = g_conn; /* cosine_geometry_term(light_ray, camera_ray) */
+            } else {
+                const Ray *light_ray = lr + (s - 1);
+                V3 prior_camera_color = xyz(cr[t - 2].color);
+                float new_camera_f = fabsf(dot(-dir_l_to_c, cam_n)) / CLV_PI;
+                V3 camera_color = (prior_camera_color * new_camera_f) * xyz(ld4(&materials[cam_material].color));
+                V3 light_color;
+                if (s == 1) {
+                    light_color = xyz(ld4(&materials[light_ray->material].emission));
+                } else {
+                    V3 prior_light_color = xyz(lr[s - 2].color);
+                    new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
+                    light_color = (prior_light_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+                }
+                color = camera_color * light_color;
+                g = g_conn; /* cosine_geometry_term(camera_ray, light_ray): symmetric, same bits */
+            }
+            if (t != 1) {
+                total_contribution = total_contribution + (color * (w * g)) / p_s;
+                contrib_weight_sum += w;
+            } else {
+                float shade = new_light_f * g / p_s;
+                if (SPLAT) {
+                    /* light_image_gather (:937-964) applied on the spot: weights * shades * prior.color * mat.color */
+                    if (light_pixel_idx >= 0 && light_pixel_idx < sink.n_pixels) {
+                        const Ray *light_ray = lr + (s - 1);
+                        int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
+                        V3 contrib = (xyz(lr[prior_light_ind].color) * (w * shade)) *
+                                     xyz(ld4(&materials[light_ray->material].color));
+                        float *px = &sink.splat_image[light_pixel_idx].x;
+                        atomic_add(px + 0, contrib.x);
+                        atomic_add(px + 1, contrib.y);
+                        atomic_add(px + 2, contrib.z);
+                        atomic_add(px + 3, w);
+                    }
+                } else {
+                    size_t e = (size_t)entry_id + (size_t)s * (size_t)total_pixels;
+                    sink.pixel_indices[e] = light_pixel_idx;
+                    sink.path_indices[e] = (int32_t)entry_id;
+                    sink.ray_indices[e] = s - 1;
+                    sink.weights[e] = w;
+                    sink.shade[e] = shade;
+                }
+            }
+        }
+    }
+
+    /* 3x3 splat weights (:827-864) */
+    WeightAggregator agg;
+    for (int i = 0; i < 3; i++) { agg.pad0[i] = 0.0f; agg.pad1[i] = 0.0f; }
+    const int pixel_idx = cr[0].pixel_idx;
+    const V3 sensor_origin = xyz(cr[0].origin);
+    float weight_sum = 0.0f;
+    float ppw = c.phys_width / (float)c.pixel_width;
+    float pph = c.phys_height / (float)c.pixel_height;
+    float sigma = 0.5f * sqrtf(ppw * ppw + pph * pph);
+    float wts[3][3];
+#pragma unroll
+    for (int i = -1; i < 2; i++) {
+#pragma unroll
+        for (int j = -1; j < 2; j++) {
+            wts[i + 1][j + 1] = 0.0f;
+            int x = (pixel_idx % c.pixel_width) + i;
+            int y = (pixel_idx / c.pixel_width) + j;
+            if (x < 0 || x >= c.pixel_width || y < 0 || y >= c.pixel_height) continue;
+            float weight = gaussian_weight(pixel_center(c, x, y), sensor_origin, sigma);
+            wts[i + 1][j + 1] = weight;
+            weight_sum += weight;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) agg.weights[i][j] = (weight_sum != 0.0f) ? wts[i][j] / weight_sum : wts[i][j];
+    agg.total_contribution = pad0(total_contribution);
+    agg.contrib_weight_sum = contrib_weight_sum;
+    if (out) out[agg_slot] = v4(total_contribution.x, total_contribution.y, total_contribution.z, 1.0f);
+    weight_aggregators[agg_slot] = agg;
+}
+
+/* adaptive_finalize_samples for one pixel, trace.metal:981-1018, with general sample bins */
+CLV_HD void finalize_pixel(uint32_t id, const WeightAggregator *aggs, const Camera &camera, const uint32_t *bin_offsets,
+                           V3 &total_sample, float &weight_sum, uint32_t &count) {
+    total_sample = v3(0, 0, 0);
+    weight_sum = 0.0f;
+    int px = (int)(id % (uint32_t)camera.pixel_width), py = (int)(id / (uint32_t)camera.pixel_width);
+    for (int i = -1; i < 2; i++) {
+        for (int j = -1; j < 2; j++) {
+            int sx = px + i, sy = py + j;
+            if (sx < 0 || sx >= camera.pixel_width || sy < 0 || sy >= camera.pixel_height) continue;
+            int sample_index = sy * camera.pixel_width + sx;
+            uint32_t k0 = bin_offsets ? bin_offsets[sample_index] : (uint32_t)sample_index;
+            uint32_t k1 = bin_offsets ? bin_offsets[sample_index + 1] : (uint32_t)sample_index + 1;
+            for (uint32_t k = k0; k < k1; k++) {
+                const WeightAggregator *wa = aggs + k;
+                float weight = wa->weights[1 - i][1 - j];
+                total_sample = total_sample + xyz(wa->total_contribution) * weight;
+                weight_sum += weight * wa->contrib_weight_sum;
+            }
+        }
+    }
+    count = bin_offsets ? bin_offsets[id + 1] - bin_offsets[id] : 1u;
+}
+
+CLV_HD float nan_to_num0(float x) { return (x != x || fabsf(x) == CLV_INF) ? 0.0f : x; } /* renderer.py:271,278 */
+
+/* ---- fused per-pass pieces (Renderer.run_sample without host round trips) --------------------------------------- */
+struct Accum { float image[3], weight, uni[3], count; }; /* CLV_BUF_ACCUM_PACKED, 32 bytes per pixel */
+static_assert(sizeof(Accum) == 32, "Accum");
+
+/* stages 1-4 of renderer.py:281-285 for one sample: both ray generators and both random walks, RNG streams consumed in
+ * the reference's order (light gen, camera gen, light walk, camera walk), then the unidirectional part of
+ * process_images (renderer.py:273-278).  `gid` = global sample id = pixel; this pixel's accumulator is touched by
+ * exactly one sample per pass, so the read-modify-write needs no atomics. */
+template <int MODE, bool COUNT>
+CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light_triangles, const float *surface_areas,
+                              const int32_t *light_triangle_indices, int light_count, const Material *materials,
+                              const Camera &c, const AccelView &A, uint32_t &seed0, uint32_t &seed1, Path *light_paths,
+                              Path *camera_paths, Accum *accum, Cnt<COUNT> &cnt) {
+    Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
+    Ray cray = make_camera_ray(c, (int)gid, seed0, seed1);
+    V4 uni;
+    random_walk<MODE, COUNT>(lray, A, materials, seed0, seed1, light_paths + slot, &uni, cnt);
+    random_walk<MODE, COUNT>(cray, A, materials, seed0, seed1, camera_paths + slot, &uni, cnt);
+    Accum *a = accum + gid;
+    a->uni[0] += nan_to_num0(uni.x);
+    a->uni[1] += nan_to_num0(uni.y);
+    a->uni[2] += nan_to_num0(uni.z);
+    a->count += 1.0f;
+}
+
+/* stages 6-8 for one pixel: adaptive_finalize_samples with identity bins, the light image the connect kernel
+ * splatted this pass (cleared here for the next one), and process_images' accumulation (renderer.py:253-271).
+ * Returns this pixel's sample weight of the pass. */
+CLV_HD float fused_finalize_pixel(uint32_t id, const WeightAggregator *aggs, const Camera &c, V4 *light_image,
+                                  Accum *accum) {
+    V3 fin;
+    float wsum;
+    uint32_t count;
+    finalize_pixel(id, aggs, c, nullptr, fin, wsum, count);
+    V4 li = light_image[id];
+    light_image[id] = v4(0.0f, 0.0f, 0.0f, 0.0f);
+    Accum *a = accum + id;
+    a->image[0] += nan_to_num0(li.x + fin.x);
+    a->image[1] += nan_to_num0(li.y + fin.y);
+    a->image[2] += nan_to_num0(li.z + fin.z);
+    float wpass = wsum + li.w;
+    a->weight += wpass;
+    return wpass;
+}
+
+} /* namespace clv */
+#endif /* CLV_DEVICE_CUH */

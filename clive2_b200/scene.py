@@ -51,14 +51,14 @@ def _mesh_soup(spec):
 
 
 def build_scene_arrays(pixel_width=1280, pixel_height=720, cam_center=ZERO_VECTOR, cam_direction=UNIT_Z,
-                       file_specs=None, materials=None, bvh_builder="auto"):
+                       file_specs=None, materials=None, bvh_builder="auto", sort_kind="stable"):
     camera = Camera(center=cam_center, direction=cam_direction, pixel_width=pixel_width, pixel_height=pixel_height,
                     phys_width=pixel_width / pixel_height, phys_height=1)
     # sensor triangles first, then the enclosure: this order fixes the soup order the BVH build starts from
     soup = FastTreeBox.from_triangle_objects(camera_geometry(camera) + triangles_for_box())
     for spec in file_specs or ():
         soup = soup + _mesh_soup(spec)
-    boxes, triangles = build_flat_bvh(soup, builder=bvh_builder)
+    boxes, triangles = build_flat_bvh(soup, builder=bvh_builder, sort_kind=sort_kind)
 
     is_light = triangles["is_light"] != 0
     light_idx = np.flatnonzero(is_light).astype(np.int32)

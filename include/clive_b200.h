@@ -194,9 +194,10 @@ CLV_API int clv_renderer_create(clv_ctx *ctx, const clv_accel *accel, const clv_
 CLV_API int clv_renderer_destroy(clv_renderer *r);
 /* one sample pass (= Renderer.run_sample, renderer.py:281-291), asynchronous, accumulates on the device */
 CLV_API int clv_renderer_run_sample(clv_renderer *r);
-/* end-to-end variant: uploads this pass's seed rows from host memory first and downloads the per-pass checksum
- * (sum of sample weights over the frame) afterwards */
-CLV_API int clv_renderer_run_sample_e2e(clv_renderer *r, const uint32_t *h_seeds_pinned, float *h_checksum_pinned);
+/* end-to-end variant with HOST buffers: uploads a fresh seed buffer uint32[W*H][2] for this pass (NULL = keep the
+ * device-resident streams), runs the pass, then downloads the packed accumulators float[H][W][8] (NULL = skip) and
+ * waits.  Page-locked memory from clv_host_alloc makes both copies asynchronous DMA. */
+CLV_API int clv_renderer_run_sample_e2e(clv_renderer *r, const uint32_t *h_seeds, float *h_accum_packed);
 CLV_API int clv_renderer_reset(clv_renderer *r, const uint32_t *h_seeds); /* zero accumulators, reload seeds */
 
 typedef enum clv_buffer_id {
@@ -205,13 +206,16 @@ typedef enum clv_buffer_id {
     CLV_BUF_SUMMED_SAMPLE_WEIGHTS = 2, /* float[H][W]      renderer.py:43  */
     CLV_BUF_UNIDIRECTIONAL = 3,        /* float[H][W][3]   renderer.py:45  */
     CLV_BUF_SEEDS = 4,                 /* uint32[W*H][2]                   */
-    CLV_BUF_ACCUM_PACKED = 5           /* float[H][W][8]: image3, weight, uni3, count — the multi-GPU reduce payload */
+    CLV_BUF_ACCUM_PACKED = 5,          /* float[H][W][8]: image3, weight, uni3, count — the accumulators as stored
+                                          on the device, and the multi-GPU reduce payload */
+    CLV_BUF_LIGHT_PATHS = 6,           /* Path[n_local]  (last pass)  renderer.py:79 */
+    CLV_BUF_CAMERA_PATHS = 7,          /* Path[n_local]  (last pass)  renderer.py:58 */
+    CLV_BUF_AGGREGATORS = 8,           /* WeightAggregator[W*H] (last pass, indexed by pixel) */
+    CLV_BUF_PASS_WEIGHT = 9            /* float: running sum over passes and pixels of the per-pass sample weights */
 } clv_buffer_id;
 CLV_API int clv_renderer_read(clv_renderer *r, int buffer_id, void *h_dst, size_t nbytes); /* synchronises */
-/* device pointer + size of a buffer, e.g. to hand the packed accumulators to a collective */
+/* device pointer + size of a buffer (ids >= 4), e.g. to hand the packed accumulators to a collective in place */
 CLV_API int clv_renderer_device_ptr(clv_renderer *r, int buffer_id, void **d_ptr, size_t *nbytes);
-/* replace the accumulators by a reduced packed buffer (after the collective) */
-CLV_API int clv_renderer_unpack_accumulators(clv_renderer *r);
 
 /* ---- 6. parity and measurement hooks ------------------------------------------------------------------------------ */
 typedef enum clv_traverse_mode {
@@ -221,14 +225,27 @@ typedef enum clv_traverse_mode {
 /* closest hit for n host rays; outputs are host arrays of n elements (triangle index in the REFERENCE numbering) */
 CLV_API int clv_traverse(clv_ctx *ctx, const clv_accel *accel, const clv_Ray *h_rays, uint32_t n, int mode,
                          int32_t *h_tri, float *h_t, float *h_u, float *h_v);
+/* the same kernel on device-resident rays/outputs, asynchronous (for timing the traversal alone) */
+CLV_API int clv_traverse_device(clv_ctx *ctx, const clv_accel *accel, const clv_Ray *d_rays, uint32_t n, int mode,
+                                int32_t *d_tri, float *d_t, float *d_u, float *d_v);
 /* visibility_test (trace.metal:178-197) for n host vertex pairs a -> b */
 CLV_API int clv_visibility(clv_ctx *ctx, const clv_accel *accel, const clv_Ray *h_a, const clv_Ray *h_b, uint32_t n,
-                           int32_t *h_visible);
+                           int mode, int32_t *h_visible);
+/* traversal flavour used by the stage-level entry points of section 4 (process-wide; default ORDERED) and by one
+ * fused renderer (default ORDERED).  REFERENCE_ORDER visits boxes exactly like trace.metal:144-176. */
+CLV_API int clv_set_stage_traverse_mode(int mode);
+CLV_API int clv_renderer_set_traverse_mode(clv_renderer *r, int mode);
 /* work counters accumulated by kernels launched while counting is enabled (instrumented variants; the timed kernels
- * carry no counter code): [0] rays (= traverse_bvh invocations of the reference), [1] node records fetched,
- * [2] triangle records fetched */
+ * carry no counter code).  Two classes of five words: out[0..4] random-walk / traversal kernels, out[5..9] connection
+ * kernels; per class: rays = traverse_bvh invocations the reference would make, traversals actually started,
+ * 64-byte node records fetched, 48-byte triangle records fetched, 128-byte path vertices written / staged */
 CLV_API int clv_counters_enable(clv_ctx *ctx, int enabled);
-CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[3], int reset);
+CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
+/* per-kernel device time of the fused pass: CUDA events recorded on the launch stream around each of its three
+ * kernels (walks, connect, finalize) while enabled; `kernel_times` waits, returns the accumulated milliseconds and the
+ * number of passes they cover */
+CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
+CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[3], uint64_t *passes_out, int reset);
 /* number of kernel launches issued on this context so far */
 CLV_API int clv_launch_count(clv_ctx *ctx, uint64_t *count);
 

@@ -1,0 +1,228 @@
+/* hostemu.cpp — TEST INFRASTRUCTURE.  Compiles the per-sample kernel bodies of clive2_b200/csrc/clv_device.cuh for the
+ * HOST (g++, no CUDA) so their logic can be diffed against oracle/trace_ref.c in a container without a GPU.
+ *
+ * Nothing in clive2_b200/ loads this library; the product's only execution path is the CUDA one in
+ * libclive_b200.so.  The `-m gpu` tests repeat the same comparisons on the real kernels.
+ * Build: tests/hostemu/__init__.py (g++ -O2 -fopenmp -ffp-contract=off: same arithmetic contract as -fmad=false).
+ */
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../clive2_b200/csrc/clv_accel_build.h"
+
+using namespace clv;
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+struct EmuAccel {
+    HostAccel h;
+    std::vector<Triangle> ref;
+    AccelView view;
+};
+
+EXPORT EmuAccel *emu_accel_create(const Box *boxes, int32_t n_boxes, const Triangle *tris, int32_t n_tris) {
+    EmuAccel *a = new EmuAccel();
+    if (build_host_accel(boxes, n_boxes, tris, n_tris, a->h)) { delete a; return nullptr; }
+    a->ref.assign(tris, tris + n_tris);
+    a->view.nodes = &a->h.nodes.data()->a;
+    a->view.tris = a->h.tris.data();
+    a->view.ref_triangles = a->ref.data();
+    a->view.root_min = boxes[0].min;
+    a->view.root_max = boxes[0].max;
+    a->view.root_ref = a->h.root_ref;
+    a->view.n_camera_tris = (int32_t)a->h.camera_tris.size();
+    a->view.camera_tris = a->h.camera_tris.data();
+    return a;
+}
+EXPORT void emu_accel_destroy(EmuAccel *a) { delete a; }
+EXPORT void emu_accel_info(EmuAccel *a, int64_t out[3]) {
+    out[0] = (int64_t)a->h.nodes.size(); out[1] = (int64_t)a->h.tris.size() / 3; out[2] = a->h.root_ref;
+}
+
+static unsigned long long g_cnt[5];
+EXPORT void emu_counters(unsigned long long out[5], int reset) {
+    for (int i = 0; i < 5; i++) out[i] = g_cnt[i];
+    if (reset) memset(g_cnt, 0, sizeof g_cnt);
+}
+static void merge(const Cnt<true> &c) {
+#pragma omp critical(emu_cnt)
+    { g_cnt[0] += c.rr; g_cnt[1] += c.rt; g_cnt[2] += c.nf; g_cnt[3] += c.tf; g_cnt[4] += c.vx; }
+}
+
+EXPORT void emu_generate_light_rays(uint32_t n, const Triangle *lt, const float *areas, const int32_t *lti,
+                                    const Material *mats, uint32_t *rnd, Ray *out, const int32_t *counts) {
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < (int64_t)n; id++) {
+        uint32_t s0 = rnd[2 * id], s1 = rnd[2 * id + 1];
+        out[id] = make_light_ray(lt, areas, lti, mats, counts[0], s0, s1);
+        rnd[2 * id] = s0; rnd[2 * id + 1] = s1;
+    }
+}
+EXPORT void emu_generate_camera_rays(uint32_t n, const Camera *cam, uint32_t *rnd, const uint32_t *indices, Ray *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < (int64_t)n; id++) {
+        uint32_t s0 = rnd[2 * id], s1 = rnd[2 * id + 1];
+        out[id] = make_camera_ray(cam[0], (int)indices[id], s0, s1);
+        rnd[2 * id] = s0; rnd[2 * id + 1] = s1;
+    }
+}
+
+template <int MODE>
+static void gen_paths(uint32_t n, const Ray *rays, const EmuAccel *a, const Material *mats, uint32_t *rnd, V4 *out,
+                      Path *paths, V4 *debug) {
+#pragma omp parallel
+    {
+        Cnt<true> cnt;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t id = 0; id < (int64_t)n; id++) {
+            uint32_t s0 = rnd[2 * id], s1 = rnd[2 * id + 1];
+            V4 uni;
+            random_walk<MODE, true>(rays[id], a->view, mats, s0, s1, paths + id, &uni, cnt);
+            out[id] = uni;
+            if (debug) debug[id] = v4(100.0f, 100.0f, 100.0f, 100.0f);
+            rnd[2 * id] = s0; rnd[2 * id + 1] = s1;
+        }
+        merge(cnt);
+    }
+}
+EXPORT void emu_generate_paths(uint32_t n, const Ray *rays, const EmuAccel *a, const Material *mats, uint32_t *rnd,
+                               V4 *out, Path *paths, V4 *debug, int mode) {
+    if (mode == TRAVERSE_REFERENCE) gen_paths<TRAVERSE_REFERENCE>(n, rays, a, mats, rnd, out, paths, debug);
+    else gen_paths<TRAVERSE_ORDERED>(n, rays, a, mats, rnd, out, paths, debug);
+}
+
+template <int MODE, bool SPLAT>
+static void connect(uint32_t n, const Path *cp, const Path *lp, const EmuAccel *a, const Material *mats,
+                    const Camera *cam, WeightAggregator *aggs, V4 *out, LightSink sink) {
+#pragma omp parallel
+    {
+        Cnt<true> cnt;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t id = 0; id < (int64_t)n; id++) {
+            float scratch[CLV_CONNECT_SCRATCH];
+            TArr S;
+            S.base = scratch; S.stride = 1;
+            connect_sample<MODE, SPLAT, true>((uint32_t)id, (uint32_t)id, (uint32_t)id, cp, lp, a->view, mats, cam[0],
+                                              aggs, out, sink, S, cnt);
+        }
+        merge(cnt);
+    }
+}
+EXPORT void emu_connect_paths(uint32_t n, const Path *cp, const Path *lp, const EmuAccel *a, const Material *mats,
+                              const Camera *cam, WeightAggregator *aggs, V4 *out, int32_t *pix, int32_t *path,
+                              int32_t *ray, float *w, float *shade, V4 *splat_image, int mode) {
+    LightSink sink;
+    memset(&sink, 0, sizeof sink);
+    sink.pixel_indices = pix; sink.path_indices = path; sink.ray_indices = ray; sink.weights = w; sink.shade = shade;
+    sink.splat_image = splat_image;
+    sink.n_pixels = cam[0].pixel_width * cam[0].pixel_height;
+    bool splat = splat_image != nullptr;
+    if (mode == TRAVERSE_REFERENCE) {
+        if (splat) connect<TRAVERSE_REFERENCE, true>(n, cp, lp, a, mats, cam, aggs, out, sink);
+        else connect<TRAVERSE_REFERENCE, false>(n, cp, lp, a, mats, cam, aggs, out, sink);
+    } else {
+        if (splat) connect<TRAVERSE_ORDERED, true>(n, cp, lp, a, mats, cam, aggs, out, sink);
+        else connect<TRAVERSE_ORDERED, false>(n, cp, lp, a, mats, cam, aggs, out, sink);
+    }
+}
+
+EXPORT void emu_adaptive_finalize_samples(uint32_t n, const WeightAggregator *aggs, const Camera *cam, V4 *out,
+                                          uint32_t *counts, const uint32_t *bins, float *weights) {
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < (int64_t)n; id++) {
+        V3 total;
+        float wsum;
+        uint32_t count;
+        finalize_pixel((uint32_t)id, aggs, cam[0], bins, total, wsum, count);
+        counts[id] = count;
+        out[id] = v4(total.x, total.y, total.z, 1.0f);
+        weights[id] = wsum;
+    }
+}
+
+template <int MODE>
+static void traverse(uint32_t n, const Ray *rays, const EmuAccel *a, int32_t *tri, float *t, float *u, float *v) {
+#pragma omp parallel
+    {
+        Cnt<true> cnt;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t id = 0; id < (int64_t)n; id++) {
+            int best_i = -1;
+            float best_t = CLV_INF, bu = 0.0f, bv = 0.0f;
+            cnt.ray_ref();
+            closest_hit<MODE, true>(a->view, xyz(rays[id].origin), xyz(rays[id].direction), xyz(rays[id].inv_direction),
+                                    best_i, best_t, bu, bv, cnt, -CLV_INF, -1);
+            tri[id] = best_i; t[id] = best_t; u[id] = bu; v[id] = bv;
+        }
+        merge(cnt);
+    }
+}
+EXPORT void emu_traverse(uint32_t n, const Ray *rays, const EmuAccel *a, int32_t *tri, float *t, float *u, float *v,
+                         int mode) {
+    if (mode == TRAVERSE_REFERENCE) traverse<TRAVERSE_REFERENCE>(n, rays, a, tri, t, u, v);
+    else traverse<TRAVERSE_ORDERED>(n, rays, a, tri, t, u, v);
+}
+
+EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAccel *a, int32_t *visible, int mode) {
+#pragma omp parallel
+    {
+        Cnt<true> cnt;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t id = 0; id < (int64_t)n; id++) {
+            bool vis;
+            if (mode == TRAVERSE_REFERENCE)
+                vis = visibility_test<TRAVERSE_REFERENCE, true>(a->view, xyz(ra[id].origin), ra[id].triangle,
+                                                               xyz(rb[id].origin), rb[id].triangle, cnt);
+            else
+                vis = visibility_test<TRAVERSE_ORDERED, true>(a->view, xyz(ra[id].origin), ra[id].triangle,
+                                                             xyz(rb[id].origin), rb[id].triangle, cnt);
+            visible[id] = vis ? 1 : 0;
+        }
+        merge(cnt);
+    }
+}
+
+/* one fused pass exactly as clv_renderer_run_sample launches it: walks -> connect (splat) -> finalize+accumulate */
+EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
+                           const int32_t *lti, int light_count, const Material *mats, const Camera *cam,
+                           const EmuAccel *a, uint32_t *seeds, Path *light_paths, Path *camera_paths,
+                           WeightAggregator *aggs, V4 *light_image, Accum *accum, int mode) {
+    uint32_t n_pixels = (uint32_t)(cam[0].pixel_width * cam[0].pixel_height);
+#pragma omp parallel
+    {
+        Cnt<true> cnt;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t id = 0; id < (int64_t)n_local; id++) {
+            uint32_t gid = sample_ids ? sample_ids[id] : (uint32_t)id;
+            uint32_t s0 = seeds[2 * id], s1 = seeds[2 * id + 1];
+            if (mode == TRAVERSE_REFERENCE)
+                fused_walk_sample<TRAVERSE_REFERENCE, true>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0],
+                                                            a->view, s0, s1, light_paths, camera_paths, accum, cnt);
+            else
+                fused_walk_sample<TRAVERSE_ORDERED, true>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0],
+                                                          a->view, s0, s1, light_paths, camera_paths, accum, cnt);
+            seeds[2 * id] = s0; seeds[2 * id + 1] = s1;
+        }
+        LightSink sink;
+        memset(&sink, 0, sizeof sink);
+        sink.splat_image = light_image;
+        sink.n_pixels = (int)n_pixels;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t id = 0; id < (int64_t)n_local; id++) {
+            uint32_t gid = sample_ids ? sample_ids[id] : (uint32_t)id;
+            float scratch[CLV_CONNECT_SCRATCH];
+            TArr S;
+            S.base = scratch; S.stride = 1;
+            if (mode == TRAVERSE_REFERENCE)
+                connect_sample<TRAVERSE_REFERENCE, true, true>((uint32_t)id, (uint32_t)id, gid, camera_paths, light_paths,
+                                                               a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
+            else
+                connect_sample<TRAVERSE_ORDERED, true, true>((uint32_t)id, (uint32_t)id, gid, camera_paths, light_paths,
+                                                             a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
+        }
+#pragma omp for schedule(static)
+        for (int64_t id = 0; id < (int64_t)n_pixels; id++) fused_finalize_pixel((uint32_t)id, aggs, cam[0], light_image, accum);
+        merge(cnt);
+    }
+}

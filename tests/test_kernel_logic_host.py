@@ -1,0 +1,219 @@
+"""Kernel SOURCE vs oracle, on the CPU: clv_device.cuh compiled for the host by tests/hostemu (test infrastructure)
+must reproduce the shared-math oracle bit for bit, stage by stage.  The `-m gpu` tests repeat this on the device."""
+import numpy as np
+import pytest
+
+from clive2_b200 import struct_types as T
+from oracle.oracle import Oracle, OracleRenderer
+from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, oracle_stages, random_rays,
+                          rel_rmse, seeds_for)
+from tests.hostemu import MODE_ORDERED, MODE_REFERENCE, HostEmu
+
+SCENES = [("empty", 40, 40), ("bench-spheres", 48, 32)]
+
+
+@pytest.fixture(scope="module")
+def O():
+    return Oracle(shared_math=True)
+
+
+@pytest.fixture(scope="module")
+def E():
+    return HostEmu()
+
+
+def emu_stages(E, acc, a, B, mode):
+    b = B.batch
+    E.generate_light_rays(b, a.light_triangles, a.light_surface_areas, a.light_triangle_indices, a.materials, B.rand,
+                          B.light_rays, a.light_counts)
+    E.generate_camera_rays(b, a.camera, B.rand, B.indices, B.camera_rays)
+    E.generate_paths(b, B.light_rays, acc, a.materials, B.rand, B.out_light, B.light_paths, B.debug, mode)
+    E.generate_paths(b, B.camera_rays, acc, a.materials, B.rand, B.out_camera, B.camera_paths, B.debug, mode)
+    E.connect_paths(b, B.camera_paths, B.light_paths, acc, a.materials, a.camera, B.aggs, B.out_samples, B.pix, B.pth,
+                    B.ry, B.w, B.sh, None, mode)
+    E.adaptive_finalize_samples(b, B.aggs, a.camera, B.finalized, B.sample_counts, B.bins_identity, B.sample_weights)
+    return B
+
+
+@pytest.mark.parametrize("preset,w,h", SCENES)
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_ORDERED])
+def test_stage_buffers_bit_exact(O, E, preset, w, h, mode):
+    a = arrays(preset, w, h)
+    seeds = seeds_for(w * h)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+    finally:
+        E.accel_destroy(acc)
+    assert_bits_equal(R.rand, S.rand, "RNG state")
+    assert_bits_equal(R.light_rays, S.light_rays, "light rays")
+    assert_bits_equal(R.camera_rays, S.camera_rays, "camera rays")
+    assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+    assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+    assert_bits_equal(R.out_camera, S.out_camera, "unidirectional estimate")
+    for name in ("pix", "pth", "ry", "w", "sh"):
+        assert_bits_equal(getattr(R, name), getattr(S, name), "light entries " + name)
+    assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+    assert_bits_equal(R.out_samples, S.out_samples, "out_samples")
+    assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    assert_bits_equal(R.sample_weights, S.sample_weights, "sample weights")
+    assert np.array_equal(R.sample_counts, S.sample_counts)
+
+
+@pytest.mark.parametrize("preset,w,h", SCENES)
+def test_traversal_modes_agree_with_oracle(O, E, preset, w, h):
+    a = arrays(preset, w, h)
+    rays = random_rays(60000, [-9, -1.9, -9], [9, 9, 9], seed=3)
+    tri, t, u, v = O.traverse(rays, a.boxes, a.triangles)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            tri2, t2, u2, v2 = E.traverse(rays, acc, mode)
+            assert np.array_equal(tri, tri2), (mode, int((tri != tri2).sum()))
+            hit = tri >= 0
+            assert np.array_equal(t[hit].view(np.uint32), t2[hit].view(np.uint32))
+            assert np.array_equal(u[hit].view(np.uint32), u2[hit].view(np.uint32))
+            assert np.array_equal(v[hit].view(np.uint32), v2[hit].view(np.uint32))
+        assert (tri >= 0).mean() > 0.99  # closed box: (almost) every ray hits something
+    finally:
+        E.accel_destroy(acc)
+
+
+def test_ordered_traversal_does_less_work(E):
+    a = arrays("bench-spheres", 48, 32)
+    rays = random_rays(20000, [-9, -1.9, -9], [9, 9, 9], seed=4)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        E.counters()
+        E.traverse(rays, acc, MODE_REFERENCE)
+        ref = E.counters()
+        E.traverse(rays, acc, MODE_ORDERED)
+        ordd = E.counters()
+    finally:
+        E.accel_destroy(acc)
+    assert ordd["node_fetches"] < ref["node_fetches"] and ordd["tri_fetches"] < ref["tri_fetches"]
+
+
+def test_visibility_matches_oracle(O, E):
+    a = arrays("bench-spheres", 48, 32)
+    rays = random_rays(20000, [-9, -1.9, -9], [9, 9, 9], seed=5)
+    tri, t, _, _ = O.traverse(rays, a.boxes, a.triangles)
+    ok = tri >= 0
+    # vertex pairs: a = ray origin (off-surface, triangle -1), b = hit point on triangle tri (visible by construction)
+    # and b' = hit point of ANOTHER ray (mostly occluded or visible by chance)
+    A = rays[ok].copy()
+    B = np.zeros(len(A), T.Ray)
+    B["origin"][:, :3] = A["origin"][:, :3] + A["direction"][:, :3] * t[ok][:, None]
+    B["triangle"] = tri[ok]
+    B2 = np.roll(B, 7)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for b in (B, B2):
+            ref = O.visibility(A, b, a.boxes, a.triangles)
+            for mode in (MODE_REFERENCE, MODE_ORDERED):
+                assert np.array_equal(ref, E.visibility(A, b, acc, mode)), mode
+        assert O.visibility(A, B, a.boxes, a.triangles).mean() > 0.9
+        assert 0.02 < O.visibility(A, B2, a.boxes, a.triangles).mean() < 0.98
+    finally:
+        E.accel_destroy(acc)
+
+
+def test_single_leaf_scene_and_long_leaf(O, E):
+    """Edge cases of the BVH encoding: the root is a leaf; a leaf longer than the 15 triangles a leaf ref encodes."""
+    rng = np.random.default_rng(11)
+    for n_tris in (3, 40):
+        tris = np.zeros(n_tris, T.Triangle)
+        base = rng.uniform(-1, 1, (n_tris, 3)).astype(np.float32)
+        tris["v0"][:, :3] = base
+        tris["v1"][:, :3] = base + rng.normal(0, 0.5, (n_tris, 3)).astype(np.float32)
+        tris["v2"][:, :3] = base + rng.normal(0, 0.5, (n_tris, 3)).astype(np.float32)
+        boxes = np.zeros(1, T.Box)
+        allv = np.concatenate([tris["v0"][:, :3], tris["v1"][:, :3], tris["v2"][:, :3]])
+        boxes["min"][0, :3] = allv.min(0)
+        boxes["max"][0, :3] = allv.max(0)
+        boxes["left"], boxes["right"] = 0, n_tris
+        rays = random_rays(5000, [-3, -3, -3], [3, 3, 3], seed=n_tris)
+        tri, t, u, v = O.traverse(rays, boxes, tris)
+        acc = E.accel(boxes, tris)
+        try:
+            for mode in (MODE_REFERENCE, MODE_ORDERED):
+                tri2, t2, _, _ = E.traverse(rays, acc, mode)
+                assert np.array_equal(tri, tri2)
+                assert np.array_equal(t[tri >= 0].view(np.uint32), t2[tri >= 0].view(np.uint32))
+        finally:
+            E.accel_destroy(acc)
+        assert 0 < (tri >= 0).sum() < len(rays)
+
+
+def test_bad_bvh_arrays_are_rejected(E):
+    boxes = np.zeros(2, T.Box)
+    boxes["left"][0], boxes["right"][0] = 5, 0  # child index out of range
+    with pytest.raises(ValueError):
+        E.accel(boxes, np.zeros(1, T.Triangle))
+
+
+def test_fused_pass_matches_oracle_renderer(E):
+    """clv_renderer_run_sample's three kernels vs the reference's eight stages (oracle): everything that does not go
+    through the atomically splatted light image is bit exact; the image agrees to float-summation-order tolerance."""
+    w = h = 40
+    a = arrays("empty", w, h)
+    seeds = seeds_for(w * h)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    b = w * h
+    s = seeds.copy()
+    lp, cp = np.zeros(b, T.Path), np.zeros(b, T.Path)
+    aggs = np.zeros(b, T.WeightAggregator)
+    light_image = np.zeros((b, 4), np.float32)
+    accum = np.zeros((b, 8), np.float32)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for _ in range(3):
+            ref.run_sample()
+            E.fused_pass(a, acc, s, lp, cp, aggs, light_image, accum)
+    finally:
+        E.accel_destroy(acc)
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), s, "RNG state after 3 passes")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), accum[:, 4:7].copy(), "unidirectional image")
+    assert np.array_equal(ref.summed_sample_counts.reshape(b), accum[:, 7].astype(np.int32))
+    assert (light_image == 0).all()  # cleared for the next pass
+    np.testing.assert_allclose(accum[:, 3], ref.summed_sample_weights.reshape(b), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(accum[:, 0:3], ref.summed_image.reshape(b, 3), rtol=2e-4, atol=1e-6)
+    est_ref = np.nan_to_num(ref.summed_image / ref.summed_sample_weights).reshape(b, 3)
+    est = np.nan_to_num(accum[:, 0:3] / accum[:, 3:4])
+    assert rel_rmse(est, est_ref) < 1e-4
+
+
+def test_sharded_fused_pass_sums_to_full_render(E):
+    """Two shards (sample ids split in 8-pixel stripes) keep the global RNG streams; their accumulators add up to the
+    single-renderer result (float summation order aside)."""
+    w = h = 32
+    a = arrays("empty", w, h)
+    b = w * h
+    seeds = seeds_for(b)
+    acc = E.accel(a.boxes, a.triangles)
+
+    def render(ids):
+        n = b if ids is None else len(ids)
+        s = (seeds if ids is None else seeds[ids]).copy()
+        lp, cp = np.zeros(n, T.Path), np.zeros(n, T.Path)
+        aggs = np.zeros(b, T.WeightAggregator)
+        li = np.zeros((b, 4), np.float32)
+        accum = np.zeros((b, 8), np.float32)
+        for _ in range(2):
+            E.fused_pass(a, acc, s, lp, cp, aggs, li, accum, sample_ids=ids)
+        return accum, s
+
+    try:
+        full, s_full = render(None)
+        ids = np.arange(b, dtype=np.uint32)
+        stripe = (ids // 8) % 2
+        parts = [render(np.ascontiguousarray(ids[stripe == r])) for r in (0, 1)]
+    finally:
+        E.accel_destroy(acc)
+    total = parts[0][0] + parts[1][0]
+    assert np.array_equal(total[:, 7], full[:, 7])                      # counts
+    assert_bits_equal(total[:, 4:7].copy(), full[:, 4:7].copy(), "unidirectional")  # one owner per pixel
+    np.testing.assert_allclose(total[:, 0:4], full[:, 0:4], rtol=2e-4, atol=1e-6)
+    for r in (0, 1):
+        assert_bits_equal(parts[r][1], s_full[stripe == r], "shard RNG streams")
