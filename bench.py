@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the BDPT hot path (one "step" = one sample pass = Renderer.run_sample over a full frame).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` is whole-job Msamples/s with everything resident in HBM (CUDA events on the
+launch stream, max over ranks); `e2e` is the same metric through `Renderer.run_sample_e2e` with HOST buffers (seed
+upload + accumulator download inside the timed region); `roofline` is for the dominant kernel of the pass;
+`cpu_baseline` is the CPU transcription of the reference (oracle/, glibc build) timed on this box's host cores.
+`--impl reference` times that CPU transcription as the reference arm (the reference's Metal kernels cannot run on
+Linux and its Python needs `metalcompute`).
+
+Multi-GPU (torchrun, one rank per GPU): every rank renders full-frame passes with its own RNG streams (the work
+shards by sample pass, no data-path collective), and ONE NCCL reduce of the packed float accumulators closes the timed
+region.  Per-GPU work is fixed => "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+CONFIGS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "c1": dict(preset="empty", width=256, height=256,
+               workload="C1: Cornell box (preset 'empty', 16 triangles), 256x256, diffuse, max path length 6+6"),
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
+    "c2": dict(preset="bench-spheres", width=512, height=512,
+               workload="C2: Cornell box + two icospheres (2 x 20480 triangles), rough-dielectric (GGX transmission) "
+                        "and coated-diffuse (GGX specular) materials, 512x512"),
+    # BASELINE.json configs[2]
+    "c3": dict(preset="bench-terrain-1m", width=1024, height=1024,
+               workload="C3: Cornell enclosure + procedural terrain mesh (1 002 528 triangles), 1024x1024"),
+}
+SEED = 20240928
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed regions run."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower() == "active":
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_arrays(cfg, width=None, height=None):
+    from clive2_b200 import scene
+    return scene.preset_arrays(cfg["preset"], width or cfg["width"], height or cfg["height"])
+
+
+def seeds_for(batch, rank):
+    s = np.random.RandomState(SEED + 7919 * rank).randint(0, 2 ** 32, size=(batch, 2), dtype=np.uint32)
+    s[s == 0] = 1
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU transcription (oracle) legs
+# ---------------------------------------------------------------------------------------------------------------------
+def oracle_passes(arrays, seeds, n_passes):
+    """Seconds per pass of the C transcription (glibc build, all host threads) over `n_passes` passes."""
+    from oracle.oracle import OracleRenderer
+    r = OracleRenderer(arrays, seeds, shared_math=False)
+    times = []
+    for _ in range(n_passes):
+        t0 = time.perf_counter()
+        r.run_sample()
+        times.append(time.perf_counter() - t0)
+    threads = r.oracle.num_threads
+    r.close()
+    return times, threads
+
+
+def cpu_baseline(cfg, budget_s=20.0):
+    arrays = build_arrays(cfg)
+    batch = cfg["width"] * cfg["height"]
+    seeds = seeds_for(batch, 0)
+    t1, threads = oracle_passes(arrays, seeds, 1)
+    n_more = int(max(1, min(6, (budget_s - t1[0]) // max(t1[0], 1e-3))))
+    tn, _ = oracle_passes(arrays, seeds, n_more)
+    per_pass = min(statistics.median(tn), t1[0])
+    return {"value": batch / per_pass / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": f"{n_more} full passes of the same workload ({batch} samples each) after 1 warm-up pass; "
+                      f"oracle/trace_ref.c (gcc -O3 -fopenmp, glibc libm), {per_pass:.3f} s/pass"}
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    width, height = cfg["width"], cfg["height"]
+    arrays = build_arrays(cfg)
+    probe, threads = oracle_passes(arrays, seeds_for(width * height, 0), 1)
+    shrink = 1
+    while probe[0] / (shrink * shrink) * (args.steps + args.warmup) > 240.0 and min(width, height) // (2 * shrink) >= 64:
+        shrink *= 2
+    if shrink > 1:
+        width, height = width // shrink, height // shrink
+        arrays = build_arrays(cfg, width, height)
+    batch = width * height
+    from oracle.oracle import OracleRenderer
+    r = OracleRenderer(arrays, seeds_for(batch, 0), shared_math=False)
+    for _ in range(args.warmup):
+        r.run_sample()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.run_sample()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt / 1e6
+    sample = (f"each step = one full pass of the {width}x{height} frame ({batch} samples)"
+              + (f", frame reduced {shrink}x per axis from {cfg['width']}x{cfg['height']} to bound the run" if shrink > 1 else ""))
+    line = {
+        "impl": "reference", "metric": "bdpt_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "width": width, "height": height, "samples_per_step": batch,
+                   "what": "CPU transcription of the reference's trace.metal + renderer.py pass (oracle/trace_ref.c, "
+                           "glibc build, OpenMP over all host threads); the reference's Metal kernels cannot run on Linux"},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from clive2_b200 import runtime, scene
+    from clive2_b200.renderer import Renderer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; clive2_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    width, height = cfg["width"], cfg["height"]
+    batch = width * height
+    t_scene = time.perf_counter()
+    arrays = build_arrays(cfg)
+    t_scene = time.perf_counter() - t_scene
+    dev = runtime.Device(local_rank)
+    t_up = time.perf_counter()
+    sc = scene.scene_from_arrays(arrays, dev)
+    seeds = seeds_for(batch, rank)
+    r = Renderer(sc, seeds=seeds)
+    dev.synchronize()
+    t_up = time.perf_counter() - t_up
+    accel_stats = dev.accel(sc.boxes, sc.triangles).stats()
+    K, W = args.steps, args.warmup
+
+    # ---- 1. instrumented run: work counters of exactly the passes that will be timed (same seeds => same work) ----
+    dev.counters_enable(True)
+    for _ in range(W):
+        r.run_sample()
+    dev.counters(reset=True)
+    for _ in range(K):
+        r.run_sample()
+    counters = dev.counters(reset=True, per_class=True)
+    dev.counters_enable(False)
+    r._fr.reset(seeds)
+
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- 2. device-resident timed run -------------------------------------------------------------------------------
+    for _ in range(W):
+        r.run_sample()
+    dev.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    r._fr.kernel_timing(True)
+    launches0 = dev.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        r.run_sample()
+    if world > 1:
+        dev.synchronize()
+        acc = torch.as_tensor(r.accumulator_buffer(), device=torch.device("cuda", local_rank))
+        dist.reduce(acc, dst=0)
+        torch.cuda.synchronize()
+    e1.record(stream)
+    dev.synchronize()
+    torch.cuda.synchronize()
+    launches = dev.launch_count - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        dist.barrier()
+    kernel_ms, timed_passes = r._fr.kernel_times(reset=True)
+    r._fr.kernel_timing(False)
+
+    # ---- 3. end-to-end timed run: host seeds in, host accumulators out, every step ----------------------------------
+    r._fr.reset(seeds)
+    h_seeds = runtime.PinnedArray((batch, 2), np.uint32)
+    h_accum = runtime.PinnedArray((height, width, 8), np.float32)
+    h_seeds.array[:] = seeds
+    for _ in range(W):
+        r.run_sample_e2e(h_seeds, h_accum)
+    dev.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        # a fresh host-side RNG state per step (cheap in-place update so that the upload is real work every step)
+        h_seeds.array[:, 0] ^= np.uint32(k + 1)
+        r.run_sample_e2e(h_seeds, h_accum)
+    dev.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(np.nan_to_num(h_accum.array[..., 3]).sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        samples = batch * K * world
+        value = samples / (elapsed_ms * 1e-3) / 1e6
+        e2e_value = samples / e2e_s / 1e6
+        tot = {k: counters["walk"][k] + counters["connect"][k] for k in counters["walk"]}
+        rays_ref_per_pass = tot["rays_ref"] / K
+        # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+        peak, peak_src = measured_peaks()
+        dom = max(("walks", "connect"), key=lambda k: kernel_ms[k])
+        c = counters["walk" if dom == "walks" else "connect"]
+        per_pass = {k: v / K for k, v in c.items()}
+        if dom == "connect":
+            # node 64 B + triangle 48 B records fetched, path vertices staged (128 B each), aggregator written (80 B)
+            alg_bytes = per_pass["node_fetches"] * 64 + per_pass["tri_fetches"] * 48 + per_pass["vertices"] * 128 + batch * 80
+        else:
+            # + shading record of every hit (80 B of the reference Triangle), vertices written, seeds and accumulator RMW
+            alg_bytes = (per_pass["node_fetches"] * 64 + per_pass["tri_fetches"] * 48 + per_pass["rays_ref"] * 80
+                         + per_pass["vertices"] * 128 + batch * (16 + 64))
+        dom_ms = kernel_ms[dom] / max(timed_passes, 1)
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_connect_paths" if dom == "connect" else "k_fused_walks",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms,
+                    "kernel_ms_per_pass": {k: v / max(timed_passes, 1) for k, v in kernel_ms.items()},
+                    "note": "algorithmic bytes = node (64 B) and triangle (48 B) records the kernel fetches (device "
+                            "counters of an instrumented run of the same passes) + path vertices (128 B) + per-sample "
+                            "records; the geometry of this configuration is cache resident, so DRAM traffic is far "
+                            "below this figure (see profiles/)"}
+        traffic_file = os.path.join(REPO, "profiles", "dram_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(roofline["kernel"])
+            except Exception:
+                pass
+        line = {
+            "metric": "bdpt_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "width": width, "height": height, "samples_per_step_per_gpu": batch,
+                       "triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)),
+                       "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"per-pass working set {2 * 1040 * batch / 1e6:.0f} MB of path records "
+                             f"(> 126 MB L2) is rewritten every step; no explicit flush" if 2 * 1040 * batch > 126e6
+                             else "working set below L2 size; steps run back to back without flush",
+                       "accel_bytes": accel_stats["node_bytes"] + accel_stats["triangle_bytes"],
+                       "scene_build_s": t_scene, "scene_upload_s": t_up},
+            "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,
+            "mrays_traced_per_s": tot["rays_traced"] * world / (elapsed_ms * 1e-3) / 1e6,
+            "rays_per_sample": rays_ref_per_pass / batch,
+            "rays_definition": "mrays_per_s counts traverse_bvh invocations the reference makes for the same paths "
+                               "(SURVEY.md 8d); mrays_traced_per_s counts traversals this implementation starts "
+                               "(connection rays whose target test fails first are skipped)",
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * 8,
+                    "d2h_bytes_per_step": batch * 32, "ms_per_step": e2e_s / K * 1e3, "checksum": checksum,
+                    "api": "Renderer.run_sample_e2e -> clv_renderer_run_sample_e2e (pinned host seeds in, packed "
+                           "accumulators out)"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+
+    h_seeds.release()
+    h_accum.release()
+    r.release()
+    sc.release()
+    dev.release()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    args.steps = max(args.steps, 1)
+    cfg = CONFIGS[args.config]
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+    if args.gpus > 1 and world == 1:
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

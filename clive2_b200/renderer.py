@@ -100,6 +100,17 @@ class Renderer:
             self.process_images()
         self.samples += 1
 
+    def run_sample_e2e(self, host_seeds, host_accum):
+        """One pass end to end with HOST buffers (fused mode): upload `host_seeds` (uint32 (W*H,2), a fresh RNG state
+        for this pass; None keeps the device-resident streams), run the pass, download the packed accumulators
+        float32 (H,W,8) into `host_accum` and wait.  Both arguments are `runtime.PinnedArray`s (or None)."""
+        if not self.fused:
+            raise ValueError("run_sample_e2e is a fused-renderer call")
+        self._fr.run_sample_e2e(None if host_seeds is None else host_seeds.ptr,
+                                None if host_accum is None else host_accum.ptr)
+        self._cache = None
+        self.samples += 1
+
     # ================================================================================================================
     # staged path: renderer.py:47-84 buffers and :113-278 stages
     # ================================================================================================================
