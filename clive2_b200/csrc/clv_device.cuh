@@ -211,6 +211,10 @@ enum { TRAVERSE_REFERENCE = 0, TRAVERSE_ORDERED = 1 };
 template <int MODE, bool COUNT>
 CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, float &best_t, float &bu, float &bv,
                         Cnt<COUNT> &cnt, float stop_below, int stop_skip) {
+    /* Control flow is "while-while" with a single back edge per loop and no `continue`: lanes of a warp that sit at
+     * inner nodes step together until every lane has reached a leaf (or finished), then all leaves are processed
+     * together.  (A loop with several back edges lets the lanes drift apart for good: the first version of this
+     * function ran its slab tests with 5 of 32 lanes active, profiles/r01_c2_ncu_v1.md.) */
     int st_ref[CLV_STACK];
     float st_t[CLV_STACK];
     int sp = 0;
@@ -222,9 +226,11 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
     slab_test(o, inv, xyz(A.root_min), xyz(A.root_max), hit, te);
     if (!(hit && te < best_t)) return;
     int cur = A.root_ref;
+    bool have = true; /* `cur` holds a node that still has to be processed */
 
-    for (;;) {
-        if (cur >= 0) {
+    while (have) {
+        /* ---- phase 1: walk down inner nodes ------------------------------------------------------------------ */
+        while (have && cur >= 0) {
             const V4 *n = A.nodes + 4 * (size_t)cur;
             V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
             cnt.node();
@@ -233,31 +239,41 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
             slab_test(o, inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
             slab_test(o, inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
             int lref = f2i(n3.x), rref = f2i(n3.y);
+            bool go_l, go_r, push;
+            int push_ref;
+            float push_t;
             if (MODE == TRAVERSE_REFERENCE) {
-                /* reference pushes left then right and pops right first */
-                bool go_r = hr && tr < best_t;
-                if (go_r) {
-                    if (hl && sp < CLV_STACK) { st_ref[sp] = lref; st_t[sp] = tl; sp++; }
-                    cur = rref;
-                    continue;
-                }
-                if (hl && tl < best_t) { cur = lref; continue; }
+                /* the reference pushes left then right and pops right first; the deferred left child is re-checked
+                 * against best_t when popped = the predicate the reference evaluates at pop time */
+                go_r = hr && tr < best_t;
+                go_l = hl && tl < best_t;
+                push = go_r && hl;
+                push_ref = lref;
+                push_t = tl;
+                cur = go_r ? rref : lref;
+                have = go_r || go_l;
             } else {
-                bool go_l = hl && tl <= best_t, go_r = hr && tr <= best_t;
-                if (go_l && go_r) {
-                    bool left_first = tl < tr; /* tie: right first, the reference's order */
-                    int far_ref = left_first ? rref : lref;
-                    float far_t = left_first ? tr : tl;
-                    if (sp < CLV_STACK) { st_ref[sp] = far_ref; st_t[sp] = far_t; sp++; }
-                    cur = left_first ? lref : rref;
-                    continue;
-                }
-                if (go_l) { cur = lref; continue; }
-                if (go_r) { cur = rref; continue; }
+                go_l = hl && tl <= best_t;
+                go_r = hr && tr <= best_t;
+                bool left_first = tl < tr; /* tie: right first, the reference's order */
+                push = go_l && go_r;
+                push_ref = left_first ? rref : lref;
+                push_t = left_first ? tr : tl;
+                cur = (go_l && (left_first || !go_r)) ? lref : rref;
+                have = go_l || go_r;
             }
-        } else {
+            if (push && sp < CLV_STACK) { st_ref[sp] = push_ref; st_t[sp] = push_t; sp++; }
+            while (!have && sp > 0) {
+                sp--;
+                float t = st_t[sp];
+                if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+            }
+        }
+        /* ---- phase 2: one leaf ----------------------------------------------------------------------------------- */
+        if (have) {
             int code = ~cur;
             int first = code >> 4, count = code & 15;
+            bool stop = false;
             for (int i = first; i < first + count; i++) {
                 const V4 *tp = A.tris + 3 * (size_t)i;
                 V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
@@ -270,18 +286,17 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
                     if (accept) {
                         best_i = i; best_t = t; bu = u; bv = v;
                         best_rank = f2i(a.w);
-                        if (i != stop_skip && t < stop_below) return;
+                        stop = stop || (i != stop_skip && t < stop_below);
                     }
                 }
             }
-        }
-        /* pop */
-        for (;;) {
-            if (sp == 0) return;
-            sp--;
-            float t = st_t[sp];
-            bool keep = (MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t);
-            if (keep) { cur = st_ref[sp]; break; }
+            have = false;
+            if (stop) sp = 0; /* early exit of a predicate ray: nothing left to look at */
+            while (!have && sp > 0) {
+                sp--;
+                float t = st_t[sp];
+                if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+            }
         }
     }
 }
@@ -1018,8 +1033,13 @@ CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light
     Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
     Ray cray = make_camera_ray(c, (int)gid, seed0, seed1);
     V4 uni;
-    random_walk<MODE, COUNT>(lray, A, materials, seed0, seed1, light_paths + slot, &uni, cnt);
-    random_walk<MODE, COUNT>(cray, A, materials, seed0, seed1, camera_paths + slot, &uni, cnt);
+    /* one copy of the walk code for both subpaths (two inlined copies made instruction fetch the top stall reason) */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int which = 0; which < 2; which++)
+        random_walk<MODE, COUNT>(which ? cray : lray, A, materials, seed0, seed1,
+                                 (which ? camera_paths : light_paths) + slot, &uni, cnt);
     Accum *a = accum + gid;
     a->uni[0] += nan_to_num0(uni.x);
     a->uni[1] += nan_to_num0(uni.y);
