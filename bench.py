@@ -298,28 +298,37 @@ def run_ours(args, cfg, rank, local_rank, world):
         e2e_value = samples / e2e_s / 1e6
         tot = {k: counters["walk"][k] + counters["connect"][k] for k in counters["walk"]}
         rays_ref_per_pass = tot["rays_ref"] / K
-        # ---- roofline of the dominant kernel ------------------------------------------------------------------------
         peak, peak_src = measured_peaks()
-        dom = max(("walks", "connect"), key=lambda k: kernel_ms[k])
-        c = counters["walk" if dom == "walks" else "connect"]
-        per_pass = {k: v / K for k, v in c.items()}
-        if dom == "connect":
-            # node 64 B + triangle 48 B records fetched, path vertices staged (128 B each), aggregator written (80 B)
-            alg_bytes = per_pass["node_fetches"] * 64 + per_pass["tri_fetches"] * 48 + per_pass["vertices"] * 128 + batch * 80
-        else:
-            # + shading record of every hit (80 B of the reference Triangle), vertices written, seeds and accumulator RMW
-            alg_bytes = (per_pass["node_fetches"] * 64 + per_pass["tri_fetches"] * 48 + per_pass["rays_ref"] * 80
-                         + per_pass["vertices"] * 128 + batch * (16 + 64))
+        # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
+        dom = max(kernel_ms, key=lambda k: kernel_ms[k])
+        cw, cc = ({k: v / K for k, v in counters[x].items()} for x in ("walk", "connect"))
+        alg = {
+            # node (64 B) + triangle (48 B) records fetched + the hit triangle's shading record (80 B of the reference
+            # Triangle) + path vertices written (128 B) + seeds RMW (16 B) + accumulator RMW (64 B)
+            "k_fused_walks": cw["node_fetches"] * 64 + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * 128
+                             + batch * (16 + 64),
+            # node + triangle records fetched + per task: 4 B task word, two vertex origins and triangle ids (2 x 20 B)
+            "k_connect_rays": cc["node_fetches"] * 64 + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 40),
+            # path vertices staged (128 B each), visibility bits + projection record (8 + 48 B), aggregator written (80 B)
+            "k_connect_finish": cc["vertices"] * 128 + batch * (8 + 48 + 80),
+            # vertex origins/normals/materials of both subpaths (~48 B per vertex), task words + projection record written
+            "k_connect_enumerate": cc["vertices"] * 48 + cc["rays_ref"] * 4 + batch * (48 + 8),
+            # 9 aggregators read (80 B), light image RMW (32 B), accumulator RMW (64 B) per pixel
+            "k_fused_finalize": batch * (9 * 80 + 32 + 64),
+        }
+        alg_bytes = alg[dom]
         dom_ms = kernel_ms[dom] / max(timed_passes, 1)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_connect_paths" if dom == "connect" else "k_fused_walks",
+        roofline = {"bound": "hbm", "kernel": dom,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms,
                     "kernel_ms_per_pass": {k: v / max(timed_passes, 1) for k, v in kernel_ms.items()},
+                    "algorithmic_gbs_per_kernel": {k: alg[k] / (kernel_ms[k] / max(timed_passes, 1) * 1e-3) / 1e9
+                                                   for k in kernel_ms if kernel_ms[k] > 0},
                     "note": "algorithmic bytes = node (64 B) and triangle (48 B) records the kernel fetches (device "
-                            "counters of an instrumented run of the same passes) + path vertices (128 B) + per-sample "
-                            "records; the geometry of this configuration is cache resident, so DRAM traffic is far "
-                            "below this figure (see profiles/)"}
+                            "counters of an instrumented run of the same passes) + the per-sample / per-ray records it "
+                            "reads and writes (DESIGN.md §7); BVH records of this configuration are cache resident, so "
+                            "DRAM traffic (`traffic`, from ncu) is far below the algorithmic figure"}
         traffic_file = os.path.join(REPO, "profiles", "dram_traffic.json")
         if os.path.exists(traffic_file):
             try:

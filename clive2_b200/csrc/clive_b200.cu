@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -58,6 +59,10 @@ struct clv_ctx {
     int counting;
     unsigned long long launches;
     int sm_count;
+    int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
+    /* scratch of the stage-level clv_connect_paths (grown on demand) */
+    void *cs_mem;
+    uint32_t cs_capacity;
 };
 
 extern "C" int clv_device_count(int *count) {
@@ -90,6 +95,9 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     c->counting = 0;
     c->launches = 0;
     c->sm_count = prop.multiProcessorCount;
+    c->refill_below = getenv("CLV_REFILL_BELOW") ? atoi(getenv("CLV_REFILL_BELOW")) : 24;
+    c->cs_mem = nullptr;
+    c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_counters, COUNTERS_CLASSES * sizeof(Counters)));
     CK(cudaMemsetAsync(c->d_counters, 0, COUNTERS_CLASSES * sizeof(Counters), c->stream));
@@ -102,6 +110,7 @@ extern "C" int clv_ctx_destroy(clv_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_counters);
+    cudaFree(c->cs_mem);
     cudaStreamDestroy(c->stream);
     delete c;
     return CLV_OK;
@@ -342,23 +351,136 @@ __global__ void k_reset_light_indices(uint32_t n, int32_t *pix, int32_t *path, i
     pix[id] = -1; path[id] = 0; ray[id] = 0; w[id] = 0.0f; shade[id] = 0.0f;
 }
 
-template <int MODE, bool SPLAT, bool COUNT>
+/* connect_paths (trace.metal:620-869) as three kernels:
+ *   k_connect_enumerate  one thread per sample: cheap rejections, sensor pre-test, append the surviving strategies as
+ *                        32-bit tasks (sample << 6 | strategy) to one dense list (one atomicAdd per warp)
+ *   k_connect_rays       the occlusion queries of the list.  Small register footprint, no shared memory => high
+ *                        occupancy and the whole L1 for BVH nodes.  Each warp owns a chunk of the list; lanes take the
+ *                        next task of the chunk as soon as their ray is decided (ballot-based refill, no atomics), one
+ *                        traversal round per loop iteration, so lanes stay busy whatever the lengths of their rays
+ *   k_connect_finish     one thread per sample: stage MIS terms in shared memory, evaluate the surviving strategies
+ *                        in the reference's order, splat weights, aggregator
+ */
+#define CLV_RAY_CHUNK 256 /* tasks per warp in k_connect_rays */
+#define CLV_WARPS_PER_BLOCK (CLV_BLOCK / 32)
+
+struct ConnectScratch { /* device buffers shared by the three kernels */
+    uint32_t *tasks;      /* [n * 36] */
+    uint32_t *task_count; /* [1] */
+    unsigned int *vis;    /* [n][2]: visibility bits of strategies 0..41 */
+    float *sensor;        /* [n][CLV_SENSOR_WORDS] */
+};
+
+template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(CLV_BLOCK)
-k_connect_paths(uint32_t n, const uint32_t *sample_ids, const Path *camera_paths, const Path *light_paths, AccelView A,
-                const Material *materials, const Camera *camera, WeightAggregator *aggs, V4 *out, LightSink sink,
-                Counters *counters) {
-    __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_paths, AccelView A, const Material *materials,
+                    const Camera *camera, ConnectScratch cs, Counters *counters) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     Cnt<COUNT> cnt;
+    unsigned long long cand = 0ull;
     if (id < n) {
         Camera c = camera[0];
-        TArr S;
+        TArr Sens;
+        Sens.base = cs.sensor + (size_t)id * CLV_SENSOR_WORDS;
+        Sens.stride = 1;
+        cand = connect_enumerate<MODE, COUNT>(id, camera_paths, light_paths, A, materials, c, Sens, cnt);
+        cs.vis[2 * (size_t)id] = 0u;
+        cs.vis[2 * (size_t)id + 1] = 0u;
+    }
+    const int mine = __popcll(cand);
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cs.task_count, (uint32_t)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t pos = base + (uint32_t)(incl - mine);
+    while (cand) {
+        int q = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        cs.tasks[pos++] = (id << 6) | (uint32_t)q;
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, const Camera *camera, ConnectScratch cs,
+               Counters *counters, int refill_below) {
+    const uint32_t count = *cs.task_count;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint64_t first = (uint64_t)warp * CLV_RAY_CHUNK;
+    if (first >= count) return; /* whole warp */
+    const int total = (int)min((uint64_t)CLV_RAY_CHUNK, (uint64_t)count - first);
+    const uint32_t *tasks = cs.tasks + first;
+    Cnt<COUNT> cnt;
+    Camera c = camera[0];
+    OccRay ray;
+    int stack[CLV_STACK];
+    bool have = false;
+    uint32_t task = 0;
+    int next = 0; /* warp-uniform: first task of the chunk not handed out yet */
+    for (;;) {
+        const unsigned holding = __ballot_sync(0xffffffffu, have);
+        if (next < total && __popc(holding) < refill_below) {
+            const unsigned idle = ~holding;
+            const int my = next + __popc(idle & ((1u << lane) - 1u));
+            if (!have && my < total) {
+                task = tasks[my];
+                const uint32_t slot = task >> 6;
+                const int q = (int)(task & 63u);
+                TArr Sens;
+                Sens.base = cs.sensor + (size_t)slot * CLV_SENSOR_WORDS;
+                Sens.stride = 1;
+                int st = connect_ray_begin<MODE, COUNT>(q, camera_paths[slot].rays, light_paths[slot].rays, Sens, A, c, ray, cnt);
+                have = st == OCC_RUNNING;
+                if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
+            }
+            next += __popc(idle);
+        } else if (holding == 0u) {
+            break;
+        }
+        if (have) {
+            int st = occ_round<COUNT>(A, ray, stack, cnt);
+            if (st != OCC_RUNNING) {
+                have = false;
+                const uint32_t slot = task >> 6;
+                const int q = (int)(task & 63u);
+                if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
+            }
+        }
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+template <bool SPLAT, bool COUNT>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_paths, const Path *light_paths,
+                 const Material *materials, const Camera *camera, ConnectScratch cs, WeightAggregator *aggs, V4 *out,
+                 LightSink sink, Counters *counters) {
+    __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    Cnt<COUNT> cnt;
+    if (id == 0) *cs.task_count = 0u; /* every ray of this pass is done (stream order): reset the list for the next */
+    if (id < n) {
+        Camera c = camera[0];
+        TArr S, Sens;
         S.base = scratch + threadIdx.x;
         S.stride = CLV_BLOCK;
-        /* staged ABI: slot == id.  Fused renderer: paths are per local slot, aggregators/out are per pixel */
+        Sens.base = cs.sensor + (size_t)id * CLV_SENSOR_WORDS;
+        Sens.stride = 1;
+        ConnectCtx X;
+        unsigned long long valid0;
+        connect_stage<COUNT>(id, camera_paths, light_paths, materials, S, Sens, X, valid0, cnt);
+        unsigned long long visible = (unsigned long long)cs.vis[2 * (size_t)id] | ((unsigned long long)cs.vis[2 * (size_t)id + 1] << 32);
+        /* staged ABI: aggregator slot == id.  Fused renderer: aggregators are per pixel */
         uint32_t agg_slot = sample_ids ? sample_ids[id] : id;
-        connect_sample<MODE, SPLAT, COUNT>(id, id, agg_slot, camera_paths, light_paths, A, materials, c, aggs, out, sink,
-                                           S, cnt);
+        connect_finish<SPLAT>(X, valid0 | visible, id, agg_slot, materials, c, aggs, out, sink);
     }
     flush_counters<COUNT>(cnt, counters);
 }
@@ -518,6 +640,23 @@ k_visibility(uint32_t n, const Ray *a, const Ray *b, AccelView A, int32_t *visib
     flush_counters<COUNT>(cnt, counters);
 }
 
+/* ---- host side of the connection stage --------------------------------------------------------------------------- */
+static size_t connect_scratch_bytes(uint32_t n) {
+    return 64 + (size_t)n * (36 * 4 + 2 * 4 + CLV_SENSOR_WORDS * 4);
+}
+static ConnectScratch connect_scratch_at(void *mem, uint32_t n) {
+    ConnectScratch cs;
+    char *p = (char *)mem;
+    cs.task_count = (uint32_t *)p;
+    p += 64;
+    cs.tasks = (uint32_t *)p;
+    p += (size_t)n * 36 * 4;
+    cs.vis = (unsigned int *)p;
+    p += (size_t)n * 2 * 4;
+    cs.sensor = (float *)p;
+    return cs;
+}
+
 /* ---------------------------------------------------------------------------------------------------------------
  * section 4: stage-level entry points (reference argument order)
  * ------------------------------------------------------------------------------------------------------------- */
@@ -536,6 +675,35 @@ static int g_stage_mode = CLV_TRAVERSE_ORDERED;
 extern "C" int clv_set_stage_traverse_mode(int mode) {
     REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
     g_stage_mode = mode;
+    return CLV_OK;
+}
+
+/* enumerate -> rays -> finish on the context's stream */
+static int launch_connect(clv_ctx *c, int mode, bool splat, uint32_t n, const uint32_t *sample_ids, const Path *cp,
+                          const Path *lp, const AccelView &view, const Material *mats, const Camera *cam,
+                          ConnectScratch cs, WeightAggregator *aggs, V4 *out, const LightSink &sink,
+                          cudaEvent_t *mid_events /* NULL or 2 events: after enumerate, after rays */) {
+    Counters *ctr = c->d_counters + COUNTERS_CONNECT;
+#define CALL(M, CT) k_connect_enumerate<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, cp, lp, view, mats, cam, cs, ctr)
+    DISPATCH_MC(mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    if (mid_events) CK(cudaEventRecord(mid_events[0], c->stream));
+    const uint64_t warps = ((uint64_t)n * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
+    const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
+#define CALL(M, CT) k_connect_rays<M, CT><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(cp, lp, view, cam, cs, ctr, c->refill_below)
+    DISPATCH_MC(mode, c->counting, CALL);
+#undef CALL
+    LAUNCHED(c);
+    if (mid_events) CK(cudaEventRecord(mid_events[1], c->stream));
+    if (splat) {
+        if (c->counting) k_connect_finish<true, true><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+        else k_connect_finish<true, false><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+    } else {
+        if (c->counting) k_connect_finish<false, true><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+        else k_connect_finish<false, false><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+    }
+    LAUNCHED(c);
     return CLV_OK;
 }
 
@@ -591,11 +759,18 @@ extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, con
     LightSink sink;
     memset(&sink, 0, sizeof sink);
     sink.pixel_indices = pix; sink.path_indices = path; sink.ray_indices = ray; sink.weights = w; sink.shade = shade;
-#define CALL(M, CT) k_connect_paths<M, false, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, nullptr, (const Path *)cp, (const Path *)lp, accel->view, (const Material *)mats, (const Camera *)cam, (WeightAggregator *)aggs, (V4 *)out, sink, c->d_counters + COUNTERS_CONNECT)
-    DISPATCH_MC(g_stage_mode, c->counting, CALL);
-#undef CALL
-    LAUNCHED(c);
-    return CLV_OK;
+    if (c->cs_capacity < n) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->cs_mem) CK(cudaFree(c->cs_mem));
+        c->cs_mem = nullptr;
+        c->cs_capacity = 0;
+        CK(cudaMalloc(&c->cs_mem, connect_scratch_bytes(n)));
+        c->cs_capacity = n;
+    }
+    ConnectScratch cs = connect_scratch_at(c->cs_mem, n);
+    CK(cudaMemsetAsync(cs.task_count, 0, 64, c->stream));
+    return launch_connect(c, g_stage_mode, false, n, nullptr, (const Path *)cp, (const Path *)lp, accel->view,
+                          (const Material *)mats, (const Camera *)cam, cs, (WeightAggregator *)aggs, (V4 *)out, sink, nullptr);
 }
 
 extern "C" int clv_adaptive_finalize_samples(clv_ctx *c, uint32_t n, const clv_WeightAggregator *aggs,
@@ -652,6 +827,8 @@ extern "C" int clv_light_image_splat(clv_ctx *c, uint32_t n_entries, uint32_t n_
 /* ---------------------------------------------------------------------------------------------------------------
  * section 5: fused renderer
  * ------------------------------------------------------------------------------------------------------------- */
+#define CLV_PASS_KERNELS 5 /* walks, connect-enumerate, connect-rays, connect-finish, finalize */
+#define CLV_PASS_EVENTS (CLV_PASS_KERNELS + 1)
 struct clv_renderer {
     clv_ctx *ctx;
     const clv_accel *accel;
@@ -671,12 +848,13 @@ struct clv_renderer {
     V4 *d_light_image;
     Accum *d_accum;
     float *d_pass_weight;
+    void *d_connect_scratch;
     std::vector<uint32_t> sample_ids;
     unsigned long long passes;
     /* optional per-kernel timing: events around each of the three kernels of every pass */
     int timing;
-    std::vector<cudaEvent_t> events; /* 4 per pass: before walks, after walks, after connect, after finalize */
-    double kernel_ms[3];
+    std::vector<cudaEvent_t> events; /* CLV_PASS_EVENTS per pass: before walks, after each of the five kernels */
+    double kernel_ms[CLV_PASS_KERNELS];
     unsigned long long timed_passes;
 };
 
@@ -688,6 +866,7 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     cudaFree(r->d_light_tri_idx); cudaFree(r->d_seeds); cudaFree(r->d_sample_ids); cudaFree(r->d_light_paths);
     cudaFree(r->d_camera_paths); cudaFree(r->d_aggs); cudaFree(r->d_light_image); cudaFree(r->d_accum);
     cudaFree(r->d_pass_weight);
+    cudaFree(r->d_connect_scratch);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     delete r;
     return CLV_OK;
@@ -738,7 +917,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     r->mode = CLV_TRAVERSE_ORDERED;
     r->passes = 0;
     r->timing = 0;
-    r->kernel_ms[0] = r->kernel_ms[1] = r->kernel_ms[2] = 0.0;
+    for (int k = 0; k < CLV_PASS_KERNELS; k++) r->kernel_ms[k] = 0.0;
     r->timed_passes = 0;
     if (h_sample_ids) r->sample_ids.assign(h_sample_ids, h_sample_ids + n_local);
     int rc;
@@ -761,6 +940,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     TRY(zalloc((void **)&r->d_light_image, (size_t)n_pixels * sizeof(V4)));
     TRY(zalloc((void **)&r->d_accum, (size_t)n_pixels * sizeof(Accum)));
     TRY(zalloc((void **)&r->d_pass_weight, 16));
+    TRY(zalloc((void **)&r->d_connect_scratch, connect_scratch_bytes(n_local)));
     TRY(load_seeds(r, h_seeds));
 #undef TRY
     CK(cudaStreamSynchronize(c->stream));
@@ -781,7 +961,7 @@ static int launch_pass(clv_renderer *r) {
     uint32_t n = r->n_local;
     size_t ev0 = r->events.size();
     if (r->timing) {
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < CLV_PASS_EVENTS; k++) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             r->events.push_back(e);
@@ -797,14 +977,16 @@ static int launch_pass(clv_renderer *r) {
     memset(&sink, 0, sizeof sink);
     sink.splat_image = r->d_light_image;
     sink.n_pixels = (int)r->n_pixels;
-#define CALL(M, CT) k_connect_paths<M, true, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_camera_paths, r->d_light_paths, r->accel->view, r->d_materials, r->d_camera, r->d_aggs, nullptr, sink, c->d_counters + COUNTERS_CONNECT)
-    DISPATCH_MC(r->mode, c->counting, CALL);
-#undef CALL
-    LAUNCHED(c);
-    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 2], c->stream));
+    {
+        int rc = launch_connect(c, r->mode, true, n, ids, r->d_camera_paths, r->d_light_paths, r->accel->view, r->d_materials,
+                                r->d_camera, connect_scratch_at(r->d_connect_scratch, n), r->d_aggs, nullptr, sink,
+                                r->timing ? &r->events[ev0 + 2] : nullptr);
+        if (rc != CLV_OK) return rc;
+    }
+    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 4], c->stream));
     k_fused_finalize<<<GRID(r->n_pixels), CLV_BLOCK, 0, c->stream>>>(r->n_pixels, r->d_aggs, r->d_camera, r->d_light_image, r->d_accum, r->d_pass_weight);
     LAUNCHED(c);
-    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 3], c->stream));
+    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 5], c->stream));
     r->passes++;
     return CLV_OK;
 }
@@ -815,12 +997,12 @@ extern "C" int clv_renderer_kernel_timing(clv_renderer *r, int enabled) {
     r->timing = enabled ? 1 : 0;
     return CLV_OK;
 }
-extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[3], uint64_t *passes_out, int reset) {
+extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_t *passes_out, int reset) {
     REQUIRE(r && ms_out && passes_out, "null");
     CK(cudaSetDevice(r->ctx->device));
     CK(cudaStreamSynchronize(r->ctx->stream));
-    for (size_t i = 0; i + 3 < r->events.size(); i += 4) {
-        for (int k = 0; k < 3; k++) {
+    for (size_t i = 0; i + CLV_PASS_KERNELS < r->events.size(); i += CLV_PASS_EVENTS) {
+        for (int k = 0; k < CLV_PASS_KERNELS; k++) {
             float ms = 0.0f;
             CK(cudaEventElapsedTime(&ms, r->events[i + k], r->events[i + k + 1]));
             r->kernel_ms[k] += ms;
@@ -829,10 +1011,10 @@ extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[3], uint
     }
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     r->events.clear();
-    for (int k = 0; k < 3; k++) ms_out[k] = r->kernel_ms[k];
+    for (int k = 0; k < CLV_PASS_KERNELS; k++) ms_out[k] = r->kernel_ms[k];
     *passes_out = r->timed_passes;
     if (reset) {
-        r->kernel_ms[0] = r->kernel_ms[1] = r->kernel_ms[2] = 0.0;
+        for (int k = 0; k < CLV_PASS_KERNELS; k++) r->kernel_ms[k] = 0.0;
         r->timed_passes = 0;
     }
     return CLV_OK;

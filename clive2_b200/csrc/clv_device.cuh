@@ -301,11 +301,83 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
     }
 }
 
-/* direct test of one triangle of the reference numbering */
-CLV_HD bool test_one(const AccelView &A, int tri, V3 o, V3 d, float &t) {
+/* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
+ * Both predicates of connect_paths ask whether ONE known triangle is the closest hit of a ray: visibility_test
+ * (trace.metal:178-197: closest hit must be b's triangle) and world_ray_to_camera_ray (:569-617: closest hit must be a
+ * sensor triangle).  Intersecting that triangle first gives its (t, rank); the answer is then "no other triangle has a
+ * lexicographically smaller (t, rank)", an any-hit search bounded by t from the start.  Unlike the closest-hit search
+ * the bound never shrinks, so the stack holds node refs only and a box is pruned when it is pushed.
+ * The search is resumable (one round = walk down to the next leaf, test it, pop) so that a warp can keep all lanes
+ * busy by handing a finished lane the next ray of its task list (k_connect_paths). */
+struct OccRay { /* scalars only, so that they live in registers; the node stack is a separate local array */
+    V3 o, d, inv;
+    float t_bound;
+    int rank_bound, skip;
+    int cur, sp;
+};
+enum { OCC_RUNNING = 0, OCC_CLEAR = 1, OCC_BLOCKED = 2 };
+
+template <bool COUNT>
+CLV_HD int occ_begin(const AccelView &A, OccRay &r, Cnt<COUNT> &cnt) {
+    cnt.ray_traced();
+    bool hit;
+    float te;
+    slab_test(r.o, r.inv, xyz(A.root_min), xyz(A.root_max), hit, te);
+    /* a ray that misses the scene box finds nothing in the reference either: its target is then not "the closest hit" */
+    if (!hit) return OCC_BLOCKED;
+    r.cur = A.root_ref;
+    r.sp = 0;
+    return OCC_RUNNING;
+}
+
+template <bool COUNT>
+CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt) {
+    int cur = r.cur, sp = r.sp;
+    int status = OCC_RUNNING;
+    while (status == OCC_RUNNING && cur >= 0) {
+        const V4 *n = A.nodes + 4 * (size_t)cur;
+        V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
+        cnt.node();
+        bool hl, hr;
+        float tl, tr;
+        slab_test(r.o, r.inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
+        slab_test(r.o, r.inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
+        int lref = f2i(n3.x), rref = f2i(n3.y);
+        bool go_l = hl && tl <= r.t_bound, go_r = hr && tr <= r.t_bound;
+        bool left_first = tl < tr;
+        if (go_l && go_r && sp < CLV_STACK) stack[sp++] = left_first ? rref : lref;
+        if (go_l || go_r) cur = (go_l && (left_first || !go_r)) ? lref : rref;
+        else if (sp > 0) cur = stack[--sp];
+        else status = OCC_CLEAR;
+    }
+    if (status == OCC_RUNNING) {
+        int code = ~cur;
+        int first = code >> 4, count = code & 15;
+        for (int i = first; i < first + count; i++) {
+            const V4 *tp = A.tris + 3 * (size_t)i;
+            V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+            cnt.tri();
+            float t, u, v;
+            if (i != r.skip && tri_test(r.o, r.d, xyz(a), xyz(b), xyz(c), t, u, v) &&
+                (t < r.t_bound || (t == r.t_bound && f2i(a.w) < r.rank_bound)))
+                status = OCC_BLOCKED;
+        }
+        if (status == OCC_RUNNING) {
+            if (sp > 0) cur = stack[--sp];
+            else status = OCC_CLEAR;
+        }
+    }
+    r.cur = cur;
+    r.sp = sp;
+    return status;
+}
+
+/* direct test of one triangle of the reference numbering; also returns its reference rank */
+CLV_HD bool test_one(const AccelView &A, int tri, V3 o, V3 d, float &t, int &rank) {
     const V4 *tp = A.tris + 3 * (size_t)tri;
     V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
     float u, v;
+    rank = f2i(a.w);
     return tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v);
 }
 
@@ -316,17 +388,19 @@ CLV_HD bool visibility_test(const AccelView &A, V3 a_origin, int a_triangle, V3 
     V3 direction = normalize(b_origin - a_origin);
     V3 inv = rcp(direction);
     cnt.ray_ref();
-    float stop = -CLV_INF;
     if (MODE == TRAVERSE_ORDERED) {
-        /* the traversal evaluates exactly this test for b's triangle; if it fails b can never be the closest hit */
         if (b_triangle < 0 || b_triangle == a_triangle) return false;
-        float tb;
-        if (!test_one(A, b_triangle, a_origin, direction, tb)) return false;
-        stop = tb; /* any other triangle accepted below tb decides the answer */
+        OccRay r;
+        r.o = a_origin; r.d = direction; r.inv = inv; r.skip = b_triangle;
+        if (!test_one(A, b_triangle, a_origin, direction, r.t_bound, r.rank_bound)) return false;
+        int stack[CLV_STACK];
+        int st = occ_begin<COUNT>(A, r, cnt);
+        while (st == OCC_RUNNING) st = occ_round<COUNT>(A, r, stack, cnt);
+        return st == OCC_CLEAR;
     }
     int best_i = -1;
     float best_t = CLV_INF, u = 0.0f, v = 0.0f;
-    closest_hit<MODE, COUNT>(A, a_origin, direction, inv, best_i, best_t, u, v, cnt, stop, b_triangle);
+    closest_hit<MODE, COUNT>(A, a_origin, direction, inv, best_i, best_t, u, v, cnt, -CLV_INF, -1);
     if (best_i == -1) return false;
     if (best_i == a_triangle) return false;
     return best_i == b_triangle;
@@ -657,60 +731,19 @@ CLV_HD float gaussian_weight(V3 p, V3 q, float sigma) {
     return clv_expf(-dist * dist / (2.0f * sigma * sigma));
 }
 
-/* the sensor vertex a light vertex projects to (the fields world_ray_to_camera_ray rewrites, :607-616) */
-struct SensorVertex {
-    V3 origin, direction;
-    int triangle;
-    int pixel_idx;
-};
-
-/* world_ray_to_camera_ray, trace.metal:569-617.  Returns false when the reference leaves pixel_idx at -1. */
-template <int MODE, bool COUNT>
-CLV_HD bool project_to_sensor(const AccelView &A, const Material *materials, const Camera &c, V3 origin, int triangle,
-                              SensorVertex &out, Cnt<COUNT> &cnt) {
-    if (materials[A.ref_triangles[triangle].material].type > 0) return false;
-    V3 direction = normalize(xyz(c.focal_point) - origin);
-    if (dot(direction, xyz(c.direction)) > 0.0f) return false;
-    V3 inv = rcp(direction);
-    cnt.ray_ref();
-    float stop = -CLV_INF;
-    if (MODE == TRAVERSE_ORDERED) {
-        /* the closest hit has to be a sensor triangle: test those first; if none is hit no traversal is needed, and
-         * otherwise any other triangle accepted below the nearest sensor hit decides the answer */
-        float t_sensor = CLV_INF;
-        for (int k = 0; k < A.n_camera_tris; k++) {
-            float t;
-            if (test_one(A, A.camera_tris[k], origin, direction, t)) t_sensor = fminf(t_sensor, t);
-        }
-        if (t_sensor == CLV_INF) return false;
-        stop = t_sensor;
-    }
-    int best_i = -1;
-    float best_t = CLV_INF, u = 0.0f, v = 0.0f;
-    /* stop_skip = -2: every triangle below `stop` ends the search (a sensor triangle cannot be below the nearest one) */
-    closest_hit<MODE, COUNT>(A, origin, direction, inv, best_i, best_t, u, v, cnt, stop, -2);
-    if (best_i == -1) return false;
-    if (!A.ref_triangles[best_i].is_camera) return false;
-
-    V3 camera_point = origin + direction * best_t;
-    float x = dot(camera_point - xyz(c.center), xyz(c.dx));
-    float y = dot(camera_point - xyz(c.center), xyz(c.dy));
-    int pixel_x = (int)roundf((x / c.phys_width + 0.5f) * (float)c.pixel_width);
-    int pixel_y = (int)roundf((y / c.phys_height + 0.5f) * (float)c.pixel_height);
-    out.pixel_idx = pixel_y * c.pixel_width + pixel_x;
-    out.origin = camera_point;
-    out.direction = normalize(xyz(c.focal_point) - camera_point);
-    out.triangle = best_i;
-    return true;
-}
-
 /* per-thread array living in shared memory (device: element k of thread at base[k * stride]) or on the stack (host) */
 struct TArr {
     float *base;
     int stride;
     CLV_HDM float &operator[](int k) const { return base[k * stride]; }
 };
-#define CLV_CONNECT_SCRATCH 58 /* floats per thread, see connect_sample */
+/* scratch layout of one sample in the connection stage (floats) */
+enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30, C_COS = 36, C_TOT = 42, G_LL = 48, G_CC = 53 };
+#define CLV_CONNECT_SCRATCH 58
+/* per-sample record of the t = 1 projections (12 words): [s-1] = t of the nearest sensor-triangle hit of light vertex
+ * s-1, [6 + s-1] = index of that triangle (int bits) */
+enum { T_SENSOR = 0, CAM_TRI = 6 };
+#define CLV_SENSOR_WORDS 12
 
 /* light-image sink of the t = 1 strategies */
 struct LightSink {
@@ -731,229 +764,354 @@ CLV_HD void atomic_add(float *p, float v) {
 #endif
 }
 
-/* connect_paths, trace.metal:620-869, for one sample.
- *   slot          : index of this sample in the path arrays
- *   entry_id      : `id` used to place staged light entries at entry_id + s * total_pixels (:818)
- *   agg_slot      : index of this sample in the aggregator / `out` arrays (the pixel it belongs to)
- * Staging (scratch, CLV_CONNECT_SCRATCH floats): for every stored vertex its l_importance, c_importance, |dir.n|,
- * tot_importance; for every subpath edge its geometry term.  The MIS ratios of trace.metal:709-735 are then formed
- * from those with the same operations in the same order, so only the connecting edge costs new arithmetic per
- * strategy (the reference recomputes every edge of the full path for each of the up to 41 strategies).
+/* ---- connect_paths, trace.metal:620-869, in three phases per sample ---------------------------------------------------
+ *   enumerate  the (s,t) strategies that need a predicate ray (t = 1 projections, regular joins) after the reference's
+ *              cheap rejections (:577-586, :676-688)
+ *   rays       one occlusion query per candidate strategy -> a visibility bit per strategy
+ *   stage      the per-vertex MIS ingredients, once per sample (l/c importance, |dir.n|, tot importance, subpath edge
+ *              geometry terms), and the s = 0 strategies, which need no ray (:662-666)
+ *   finish     for the surviving strategies IN THE REFERENCE'S ORDER (t outer, s inner): MIS weight (:709-776) from the
+ *              staged terms with the same operations in the same order, contribution (:778-823), then the 3x3 splat
+ *              weights (:827-864)
+ * The reference interleaves the three per strategy and recomputes every edge of the full path for each of its up to 41
+ * strategies.  Splitting them makes the ray phase a dense list of independent rays (any lane of the warp can take any
+ * ray) and the finish phase a loop over survivors only.
+ * Strategy index q = (t-1)*7 + s, t = 1..6, s = 0..6; ascending q is the reference's loop order.
  */
-template <int MODE, bool SPLAT, bool COUNT>
-CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, const Path *camera_paths,
-                           const Path *light_paths,
-                           const AccelView &A, const Material *materials, const Camera &c,
-                           WeightAggregator *weight_aggregators, V4 *out, const LightSink &sink, TArr S,
-                           Cnt<COUNT> &cnt) {
+struct ConnectCtx {
+    const Ray *cr, *lr;
+    int len_c, len_l;
+    unsigned spec_l, spec_c; /* bit i: vertex i has a specular material */
+    bool spec_sensor;        /* material of the rewritten sensor vertex (:611) is specular */
+    TArr S;                  /* staged MIS terms, CLV_CONNECT_SCRATCH floats */
+    TArr Sens;               /* projection record, CLV_SENSOR_WORDS words */
+};
+
+/* nearest sensor triangle hit by a ray (lexicographic (t, rank) minimum over the is_camera triangles) */
+CLV_HD bool sensor_hit(const AccelView &A, V3 origin, V3 direction, float &t_best, int &rank_best, int &tri_best) {
+    t_best = CLV_INF;
+    rank_best = 0x7fffffff;
+    tri_best = -1;
+    for (int k = 0; k < A.n_camera_tris; k++) {
+        float t;
+        int rank, tri = A.camera_tris[k];
+        if (test_one(A, tri, origin, direction, t, rank) && (t < t_best || (t == t_best && rank < rank_best))) {
+            t_best = t; rank_best = rank; tri_best = tri;
+        }
+    }
+    return tri_best >= 0;
+}
+
+/* phase 1a: stage the MIS terms of one sample and find the s = 0 strategies (camera subpath ends on an emitter) */
+template <bool COUNT>
+CLV_HD void connect_stage(uint32_t slot, const Path *camera_paths, const Path *light_paths, const Material *materials,
+                          TArr S, TArr Sens, ConnectCtx &X, unsigned long long &valid0, Cnt<COUNT> &cnt) {
     const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
     const Ray *cr = cpath->rays, *lr = lpath->rays;
     const int len_c = cpath->length, len_l = lpath->length;
-    const int total_pixels = c.pixel_width * c.pixel_height;
-
-    /* scratch layout */
-    enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30, C_COS = 36, C_TOT = 42, G_LL = 48,
-           G_CC = 53 };
-    unsigned spec_l = 0, spec_c = 0; /* bit i: vertex i has a specular material */
+    X.cr = cr; X.lr = lr; X.len_c = len_c; X.len_l = len_l; X.S = S; X.Sens = Sens;
+    unsigned spec_l = 0, spec_c = 0;
     cnt.vertex(len_l + len_c);
     for (int i = 0; i < len_l; i++) {
         const Ray *r = lr + i;
         S[L_LIMP + i] = r->l_importance;
         S[L_CIMP + i] = r->c_importance;
-        S[L_COS + i] = abs_cos(r);
+        S[L_COS + i] = fabsf(dot(xyz(r->direction), xyz(r->normal)));
         S[L_TOT + i] = r->tot_importance;
         if (materials[r->material].type > 0) spec_l |= 1u << i;
     }
     for (int i = 0; i + 1 < len_l; i++)
         S[G_LL + i] = geometry_from(S[L_COS + i], S[L_COS + i + 1], xyz(lr[i].origin), xyz(lr[i + 1].origin));
+    valid0 = 0ull;
     for (int j = 0; j < len_c; j++) {
         const Ray *r = cr + j;
         S[C_LIMP + j] = r->l_importance;
         S[C_CIMP + j] = r->c_importance;
-        S[C_COS + j] = abs_cos(r);
+        S[C_COS + j] = fabsf(dot(xyz(r->direction), xyz(r->normal)));
         S[C_TOT + j] = r->tot_importance;
         if (materials[r->material].type > 0) spec_c |= 1u << j;
+        if (j >= 1 && r->hit_light >= 0) valid0 |= 1ull << (j * 7); /* t = j + 1, s = 0 (t + s >= 2) */
     }
     for (int j = 0; j + 1 < len_c; j++)
         S[G_CC + j] = geometry_from(S[C_COS + j], S[C_COS + j + 1], xyz(cr[j].origin), xyz(cr[j + 1].origin));
-    const bool spec_sensor = materials[7].type > 0; /* material of the rewritten sensor vertex (:611) */
+    X.spec_l = spec_l; X.spec_c = spec_c;
+    X.spec_sensor = materials[7].type > 0;
+}
 
+/* phase 1b: the strategies that need a predicate ray, after the reference's cheap rejections */
+template <int MODE, bool COUNT>
+CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_paths, const Path *light_paths,
+                                            const AccelView &A, const Material *materials, const Camera &c, TArr Sens,
+                                            Cnt<COUNT> &cnt) {
+    const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
+    const Ray *cr = cpath->rays, *lr = lpath->rays;
+    const int len_c = cpath->length, len_l = lpath->length;
+    unsigned long long cand = 0ull;
+    unsigned spec_c = 0;
+    for (int j = 0; j < len_c; j++)
+        if (materials[cr[j].material].type > 0) spec_c |= 1u << j;
+    for (int s = 1; s < len_l + 1; s++) {
+        const Ray *light_ray = lr + (s - 1);
+        V3 lig_o = xyz(light_ray->origin);
+        /* t = 1: world_ray_to_camera_ray up to its traversal (:577-586) */
+        if (len_c >= 1 && !(materials[A.ref_triangles[light_ray->triangle].material].type > 0)) {
+            V3 direction = normalize(xyz(c.focal_point) - lig_o);
+            if (!(dot(direction, xyz(c.direction)) > 0.0f)) {
+                cnt.ray_ref();
+                bool ok = true;
+                if (MODE == TRAVERSE_ORDERED) {
+                    /* the closest hit has to be a sensor triangle: if the ray misses all of them no traversal can
+                     * make the strategy valid */
+                    float ts;
+                    int rank, tri;
+                    ok = sensor_hit(A, lig_o, direction, ts, rank, tri);
+                    if (ok) { Sens[T_SENSOR + s - 1] = ts; Sens[CAM_TRI + s - 1] = i2f(tri); }
+                }
+                if (ok) cand |= 1ull << s;
+            }
+        }
+        /* t >= 2: regular joins up to visibility_test (:676-688) */
+        if (materials[light_ray->material].type > 0) continue;
+        V3 lig_n = xyz(light_ray->normal);
+        for (int t = 2; t < len_c + 1; t++) {
+            if ((spec_c >> (t - 1)) & 1u) continue;
+            V3 dir_l_to_c = normalize(xyz(cr[t - 1].origin) - lig_o);
+            if (dot(lig_n, dir_l_to_c) < CLV_DELTA) continue;
+            if (dot(xyz(cr[t - 1].normal), -dir_l_to_c) < CLV_DELTA) continue;
+            cnt.ray_ref();
+            cand |= 1ull << ((t - 1) * 7 + s);
+        }
+    }
+    return cand;
+}
+
+/* Start the predicate ray of strategy q of the sample whose paths are (cr, lr) and whose scratch is S (which may belong
+ * to another lane of the warp).  Returns OCC_RUNNING with `ray` set up, or the final status. */
+template <int MODE, bool COUNT>
+CLV_HD int connect_ray_begin(int q, const Ray *cr, const Ray *lr, TArr Sens, const AccelView &A, const Camera &c, OccRay &ray,
+                             Cnt<COUNT> &cnt) {
+    const int t = q / 7 + 1, s = q % 7;
+    const Ray *light_ray = lr + (s - 1);
+    V3 lig_o = xyz(light_ray->origin);
+    if (t == 1) {
+        V3 direction = normalize(xyz(c.focal_point) - lig_o);
+        if (MODE == TRAVERSE_ORDERED) {
+            int tri = f2i(Sens[CAM_TRI + s - 1]);
+            ray.o = lig_o; ray.d = direction; ray.inv = rcp(direction);
+            ray.t_bound = Sens[T_SENSOR + s - 1];
+            ray.rank_bound = f2i(ld4(A.tris + 3 * (size_t)tri).w);
+            ray.skip = tri;
+            return occ_begin<COUNT>(A, ray, cnt);
+        }
+        int best_i = -1;
+        float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+        closest_hit<MODE, COUNT>(A, lig_o, direction, rcp(direction), best_i, best_t, u, v, cnt, -CLV_INF, -1);
+        if (best_i == -1 || !A.ref_triangles[best_i].is_camera) return OCC_BLOCKED;
+        Sens[T_SENSOR + s - 1] = best_t;
+        Sens[CAM_TRI + s - 1] = i2f(best_i);
+        return OCC_CLEAR;
+    }
+    const Ray *camera_ray = cr + (t - 1);
+    V3 cam_o = xyz(camera_ray->origin);
+    int a_triangle = light_ray->triangle, b_triangle = camera_ray->triangle;
+    if (MODE == TRAVERSE_ORDERED) {
+        V3 direction = normalize(cam_o - lig_o);
+        if (b_triangle < 0 || b_triangle == a_triangle) return OCC_BLOCKED;
+        ray.o = lig_o; ray.d = direction; ray.inv = rcp(direction); ray.skip = b_triangle;
+        if (!test_one(A, b_triangle, lig_o, direction, ray.t_bound, ray.rank_bound)) return OCC_BLOCKED;
+        return occ_begin<COUNT>(A, ray, cnt);
+    }
+    /* reference-order flavour: visibility_test (:178-197) as written, one closest-hit search */
+    V3 direction = normalize(cam_o - lig_o);
+    int best_i = -1;
+    float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+    closest_hit<MODE, COUNT>(A, lig_o, direction, rcp(direction), best_i, best_t, u, v, cnt, -CLV_INF, -1);
+    if (best_i == -1 || best_i == a_triangle) return OCC_BLOCKED;
+    return best_i == b_triangle ? OCC_CLEAR : OCC_BLOCKED;
+}
+
+/* finish: MIS + contributions of the surviving strategies, splat weights, aggregator */
+template <bool SPLAT>
+CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
+                           const Material *materials, const Camera &c, WeightAggregator *weight_aggregators, V4 *out,
+                           const LightSink &sink) {
+    const Ray *cr = X.cr, *lr = X.lr;
+    TArr S = X.S;
+    const unsigned spec_l = X.spec_l, spec_c = X.spec_c;
+    const int total_pixels = c.pixel_width * c.pixel_height;
     V3 total_contribution = v3(0, 0, 0);
     float contrib_weight_sum = 0.0f;
 
-    for (int t = 1; t < len_c + 1; t++) {
-        for (int s = 0; s < len_l + 1; s++) {
-            if (t + s < 2) continue;
+    while (survivors) {
+        int q;
+#if defined(__CUDA_ARCH__)
+        q = __ffsll((long long)survivors) - 1;
+#else
+        q = __builtin_ctzll(survivors);
+#endif
+        survivors &= survivors - 1;
+        const int t = q / 7 + 1, s = q % 7;
 
-            /* endpoint data of this strategy */
-            V3 cam_o = v3(0, 0, 0), cam_n = v3(0, 0, 0), lig_o = v3(0, 0, 0), lig_n = v3(0, 0, 0), dir_l_to_c = v3(0, 0, 0);
-            float cam_cos = 0.0f, cam_tot, g_conn = 0.0f;
-            int cam_material;
-            int light_pixel_idx = -1;
-            bool sensor_vertex = false; /* camera endpoint is the rewritten vertex 0 */
+        V3 cam_n = v3(0, 0, 0), lig_o = v3(0, 0, 0), lig_n = v3(0, 0, 0), dir_l_to_c = v3(0, 0, 0);
+        float cam_tot, g_conn = 0.0f;
+        int cam_material;
+        int light_pixel_idx = -1;
+        bool sensor_vertex = false; /* camera endpoint is the rewritten vertex 0 (:607-616) */
 
-            if (s == 0) {
-                const Ray *camera_ray = cr + (t - 1);
-                if (camera_ray->hit_light < 0) continue;
-                cam_tot = S[C_TOT + t - 1];
-                cam_material = camera_ray->material;
-            } else if (t == 1) {
-                const Ray *light_ray = lr + (s - 1);
-                lig_o = xyz(light_ray->origin);
-                lig_n = xyz(light_ray->normal);
-                SensorVertex sv;
-                if (!project_to_sensor<MODE, COUNT>(A, materials, c, lig_o, light_ray->triangle, sv, cnt)) continue;
-                light_pixel_idx = sv.pixel_idx;
-                sensor_vertex = true;
-                cam_o = sv.origin;
-                cam_n = xyz(c.direction);
-                cam_cos = fabsf(dot(sv.direction, cam_n));
-                cam_tot = 1.0f;
-                cam_material = 7;
-                dir_l_to_c = normalize(cam_o - lig_o);
-                g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, cam_o);
-            } else {
-                const Ray *camera_ray = cr + (t - 1);
-                const Ray *light_ray = lr + (s - 1);
-                if ((spec_l >> (s - 1)) & 1u) continue;
-                if ((spec_c >> (t - 1)) & 1u) continue;
-                cam_o = xyz(camera_ray->origin);
-                cam_n = xyz(camera_ray->normal);
-                lig_o = xyz(light_ray->origin);
-                lig_n = xyz(light_ray->normal);
-                dir_l_to_c = normalize(cam_o - lig_o);
-                if (dot(lig_n, dir_l_to_c) < CLV_DELTA) continue;
-                if (dot(cam_n, -dir_l_to_c) < CLV_DELTA) continue;
-                if (!visibility_test<MODE, COUNT>(A, lig_o, light_ray->triangle, cam_o, camera_ray->triangle, cnt)) continue;
-                cam_cos = S[C_COS + t - 1];
-                cam_tot = S[C_TOT + t - 1];
-                cam_material = camera_ray->material;
-                g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, cam_o);
-            }
+        if (s == 0) {
+            cam_tot = S[C_TOT + t - 1];
+            cam_material = cr[t - 1].material;
+        } else if (t == 1) {
+            const Ray *light_ray = lr + (s - 1);
+            lig_o = xyz(light_ray->origin);
+            lig_n = xyz(light_ray->normal);
+            V3 direction = normalize(xyz(c.focal_point) - lig_o);
+            V3 camera_point = lig_o + direction * X.Sens[T_SENSOR + s - 1];
+            float x = dot(camera_point - xyz(c.center), xyz(c.dx));
+            float y = dot(camera_point - xyz(c.center), xyz(c.dy));
+            int pixel_x = (int)roundf((x / c.phys_width + 0.5f) * (float)c.pixel_width);
+            int pixel_y = (int)roundf((y / c.phys_height + 0.5f) * (float)c.pixel_height);
+            light_pixel_idx = pixel_y * c.pixel_width + pixel_x;
+            sensor_vertex = true;
+            cam_n = xyz(c.direction);
+            float cam_cos = fabsf(dot(normalize(xyz(c.focal_point) - camera_point), cam_n));
+            cam_tot = 1.0f;
+            cam_material = 7;
+            dir_l_to_c = normalize(camera_point - lig_o);
+            g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, camera_point);
+        } else {
+            const Ray *camera_ray = cr + (t - 1);
+            const Ray *light_ray = lr + (s - 1);
+            V3 cam_o = xyz(camera_ray->origin);
+            cam_n = xyz(camera_ray->normal);
+            lig_o = xyz(light_ray->origin);
+            lig_n = xyz(light_ray->normal);
+            dir_l_to_c = normalize(cam_o - lig_o);
+            cam_tot = S[C_TOT + t - 1];
+            cam_material = camera_ray->material;
+            g_conn = geometry_from(S[L_COS + s - 1], S[C_COS + t - 1], lig_o, cam_o);
+        }
 
-            /* full-path accessors: vertex i < s is light vertex i, otherwise camera vertex t+s-i-1 (:546-549) */
-            const int k = s + t; /* number of vertices */
-            auto limp = [&](int i) { return i < s ? S[L_LIMP + i] : S[C_LIMP + (k - i - 1)]; };
-            auto cimp = [&](int i) { return i < s ? S[L_CIMP + i] : S[C_CIMP + (k - i - 1)]; };
-            /* geometry term of the edge between full-path vertices i and i+1 */
-            auto edge = [&](int i) {
-                if (i + 1 < s) return S[G_LL + i];
-                if (i == s - 1) return g_conn;
-                return S[G_CC + (k - i - 2)];
-            };
-            auto ratio = [&](int i) { /* p_ratios[i], :709-735 */
-                float num, denom;
-                if (i == 0) { num = limp(0); denom = cimp(0) * edge(0); }
-                else if (i == k - 1) { num = limp(i) * edge(i - 1); denom = cimp(i); }
-                else { num = limp(i) * edge(i - 1); denom = cimp(i) * edge(i); }
-                return num / denom;
-            };
-            auto specular = [&](int i) {
-                if (i < s) return ((spec_l >> i) & 1u) != 0;
-                int j = k - i - 1;
-                if (j == 0 && sensor_vertex) return spec_sensor;
-                return ((spec_c >> j) & 1u) != 0;
-            };
+        /* full-path accessors: vertex i < s is light vertex i, otherwise camera vertex t+s-i-1 (:546-549) */
+        const int k = s + t; /* number of vertices */
+        auto limp = [&](int i) { return i < s ? S[L_LIMP + i] : S[C_LIMP + (k - i - 1)]; };
+        auto cimp = [&](int i) { return i < s ? S[L_CIMP + i] : S[C_CIMP + (k - i - 1)]; };
+        auto edge = [&](int i) { /* geometry term of the edge between full-path vertices i and i+1 */
+            if (i + 1 < s) return S[G_LL + i];
+            if (i == s - 1) return g_conn;
+            return S[G_CC + (k - i - 2)];
+        };
+        auto ratio = [&](int i) { /* p_ratios[i], :709-735 */
+            float num, denom;
+            if (i == 0) { num = limp(0); denom = cimp(0) * edge(0); }
+            else if (i == k - 1) { num = limp(i) * edge(i - 1); denom = cimp(i); }
+            else { num = limp(i) * edge(i - 1); denom = cimp(i) * edge(i); }
+            return num / denom;
+        };
+        auto specular = [&](int i) {
+            if (i < s) return ((spec_l >> i) & 1u) != 0;
+            int j = k - i - 1;
+            if (j == 0 && sensor_vertex) return X.spec_sensor;
+            return ((spec_c >> j) & 1u) != 0;
+        };
 
-            float prior_light_importance = (s == 0) ? 1.0f : S[L_TOT + s - 1];
-            float p_s = cam_tot * prior_light_importance;
+        float prior_light_importance = (s == 0) ? 1.0f : S[L_TOT + s - 1];
+        float p_s = cam_tot * prior_light_importance;
 
-            /* p_values[0..k] (:737-766); p_values[k] is forced to zero, p_values[k+1] is never read */
-            float pv[14];
+        /* p_values[0..k] (:737-766); p_values[k] is forced to zero, p_values[k+1] is never read */
+        float pv[14];
 #pragma unroll
-            for (int i = 0; i < 14; i++) pv[i] = 0.0f;
-            {
-                float p_i = p_s;
-#pragma unroll
-                for (int i = 0; i < 12; i++) {
-                    if (i >= s && i < k - 1) { /* p_values[i+1] for i+1 <= k-1 */
-                        p_i = ratio(i) * p_i;
-                        pv[i + 1] = p_i;
-                    }
-                }
-                p_i = p_s;
-#pragma unroll
-                for (int i = 11; i >= 0; i--) {
-                    if (i <= s - 1) {
-                        p_i = p_i / ratio(i);
-                        pv[i] = p_i;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 13; i++)
-                if (i == s) pv[i] = p_s;
+        for (int i = 0; i < 14; i++) pv[i] = 0.0f;
+        {
+            float p_i = p_s;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                if (i < k && specular(i)) { pv[i] = 0.0f; pv[i + 1] = 0.0f; }
+                if (i >= s && i < k - 1) {
+                    p_i = ratio(i) * p_i;
+                    pv[i + 1] = p_i;
+                }
             }
-            float p_at_s = 0.0f, sum = 0.0f;
+            p_i = p_s;
 #pragma unroll
-            for (int i = 0; i < 13; i++) {
-                if (i == k) pv[i] = 0.0f;
-                if (i <= k) sum += pv[i];
-                if (i == s) p_at_s = pv[i];
-            }
-
-            float w;
-            if (p_at_s > 0.0f && sum > 0.0f) w = p_at_s / sum;
-            else continue;
-
-            V3 color;
-            float g = 1.0f, new_light_f = 1.0f;
-            if (s == 0) {
-                V3 prior_color = xyz(cr[t - 2].color);
-                V3 emission = xyz(ld4(&materials[cam_material].emission));
-                color = prior_color * emission;
-            } else if (t == 1) {
-                const Ray *light_ray = lr + (s - 1);
-                int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
-                V3 prior_color = xyz(lr[prior_light_ind].color);
-                if (s > 1) new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
-                color = (prior_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
-                g = g_conn; /* cosine_geometry_term(light_ray, camera_ray) */
-            } else {
-                const Ray *light_ray = lr + (s - 1);
-                V3 prior_camera_color = xyz(cr[t - 2].color);
-                float new_camera_f = fabsf(dot(-dir_l_to_c, cam_n)) / CLV_PI;
-                V3 camera_color = (prior_camera_color * new_camera_f) * xyz(ld4(&materials[cam_material].color));
-                V3 light_color;
-                if (s == 1) {
-                    light_color = xyz(ld4(&materials[light_ray->material].emission));
-                } else {
-                    V3 prior_light_color = xyz(lr[s - 2].color);
-                    new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
-                    light_color = (prior_light_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+            for (int i = 11; i >= 0; i--) {
+                if (i <= s - 1) {
+                    p_i = p_i / ratio(i);
+                    pv[i] = p_i;
                 }
-                color = camera_color * light_color;
-                g = g_conn; /* cosine_geometry_term(camera_ray, light_ray): symmetric, same bits */
             }
-            if (t != 1) {
-                total_contribution = total_contribution + (color * (w * g)) / p_s;
-                contrib_weight_sum += w;
+        }
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+            if (i == s) pv[i] = p_s;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if (i < k && specular(i)) { pv[i] = 0.0f; pv[i + 1] = 0.0f; }
+        }
+        float p_at_s = 0.0f, sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 13; i++) {
+            if (i == k) pv[i] = 0.0f;
+            if (i <= k) sum += pv[i];
+            if (i == s) p_at_s = pv[i];
+        }
+
+        if (!(p_at_s > 0.0f && sum > 0.0f)) continue;
+        float w = p_at_s / sum;
+
+        V3 color;
+        float g = 1.0f, new_light_f = 1.0f;
+        if (s == 0) {
+            V3 prior_color = xyz(cr[t - 2].color);
+            V3 emission = xyz(ld4(&materials[cam_material].emission));
+            color = prior_color * emission;
+        } else if (t == 1) {
+            const Ray *light_ray = lr + (s - 1);
+            int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
+            V3 prior_color = xyz(lr[prior_light_ind].color);
+            if (s > 1) new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
+            color = (prior_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+            g = g_conn; /* cosine_geometry_term(light_ray, camera_ray) */
+        } else {
+            const Ray *light_ray = lr + (s - 1);
+            V3 prior_camera_color = xyz(cr[t - 2].color);
+            float new_camera_f = fabsf(dot(-dir_l_to_c, cam_n)) / CLV_PI;
+            V3 camera_color = (prior_camera_color * new_camera_f) * xyz(ld4(&materials[cam_material].color));
+            V3 light_color;
+            if (s == 1) {
+                light_color = xyz(ld4(&materials[light_ray->material].emission));
             } else {
-                float shade = new_light_f * g / p_s;
-                if (SPLAT) {
-                    /* light_image_gather (:937-964) applied on the spot: weights * shades * prior.color * mat.color */
-                    if (light_pixel_idx >= 0 && light_pixel_idx < sink.n_pixels) {
-                        const Ray *light_ray = lr + (s - 1);
-                        int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
-                        V3 contrib = (xyz(lr[prior_light_ind].color) * (w * shade)) *
-                                     xyz(ld4(&materials[light_ray->material].color));
-                        float *px = &sink.splat_image[light_pixel_idx].x;
-                        atomic_add(px + 0, contrib.x);
-                        atomic_add(px + 1, contrib.y);
-                        atomic_add(px + 2, contrib.z);
-                        atomic_add(px + 3, w);
-                    }
-                } else {
-                    size_t e = (size_t)entry_id + (size_t)s * (size_t)total_pixels;
-                    sink.pixel_indices[e] = light_pixel_idx;
-                    sink.path_indices[e] = (int32_t)entry_id;
-                    sink.ray_indices[e] = s - 1;
-                    sink.weights[e] = w;
-                    sink.shade[e] = shade;
+                V3 prior_light_color = xyz(lr[s - 2].color);
+                new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
+                light_color = (prior_light_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+            }
+            color = camera_color * light_color;
+            g = g_conn; /* cosine_geometry_term(camera_ray, light_ray): symmetric, same bits */
+        }
+        if (t != 1) {
+            total_contribution = total_contribution + (color * (w * g)) / p_s;
+            contrib_weight_sum += w;
+        } else {
+            float shade = new_light_f * g / p_s;
+            if (SPLAT) {
+                /* light_image_gather (:937-964) applied on the spot: weights * shades * prior.color * mat.color */
+                if (light_pixel_idx >= 0 && light_pixel_idx < sink.n_pixels) {
+                    const Ray *light_ray = lr + (s - 1);
+                    int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
+                    V3 contrib = (xyz(lr[prior_light_ind].color) * (w * shade)) *
+                                 xyz(ld4(&materials[light_ray->material].color));
+                    float *px = &sink.splat_image[light_pixel_idx].x;
+                    atomic_add(px + 0, contrib.x);
+                    atomic_add(px + 1, contrib.y);
+                    atomic_add(px + 2, contrib.z);
+                    atomic_add(px + 3, w);
                 }
+            } else {
+                size_t e = (size_t)entry_id + (size_t)s * (size_t)total_pixels;
+                sink.pixel_indices[e] = light_pixel_idx;
+                sink.path_indices[e] = (int32_t)entry_id;
+                sink.ray_indices[e] = s - 1;
+                sink.weights[e] = w;
+                sink.shade[e] = shade;
             }
         }
     }
@@ -989,6 +1147,38 @@ CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, 
     agg.contrib_weight_sum = contrib_weight_sum;
     if (out) out[agg_slot] = v4(total_contribution.x, total_contribution.y, total_contribution.z, 1.0f);
     weight_aggregators[agg_slot] = agg;
+}
+
+/* the three phases for one sample, rays traced one after the other by the calling thread (host build; also the shape
+ * of the computation the warp-cooperative kernel distributes) */
+template <int MODE, bool SPLAT, bool COUNT>
+CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, const Path *camera_paths,
+                           const Path *light_paths, const AccelView &A, const Material *materials, const Camera &c,
+                           WeightAggregator *weight_aggregators, V4 *out, const LightSink &sink, TArr S,
+                           Cnt<COUNT> &cnt) {
+    ConnectCtx X;
+    unsigned long long valid0;
+    float sens_words[CLV_SENSOR_WORDS];
+    TArr Sens;
+    Sens.base = sens_words;
+    Sens.stride = 1;
+    connect_stage<COUNT>(slot, camera_paths, light_paths, materials, S, Sens, X, valid0, cnt);
+    unsigned long long cand = connect_enumerate<MODE, COUNT>(slot, camera_paths, light_paths, A, materials, c, Sens, cnt);
+    unsigned long long visible = 0ull, m = cand;
+    while (m) {
+#if defined(__CUDA_ARCH__)
+        int q = __ffsll((long long)m) - 1;
+#else
+        int q = __builtin_ctzll(m);
+#endif
+        m &= m - 1;
+        OccRay ray;
+        int stack[CLV_STACK];
+        int st = connect_ray_begin<MODE, COUNT>(q, X.cr, X.lr, Sens, A, c, ray, cnt);
+        while (st == OCC_RUNNING) st = occ_round<COUNT>(A, ray, stack, cnt);
+        if (st == OCC_CLEAR) visible |= 1ull << q;
+    }
+    connect_finish<SPLAT>(X, valid0 | visible, entry_id, agg_slot, materials, c, weight_aggregators, out, sink);
 }
 
 /* adaptive_finalize_samples for one pixel, trace.metal:981-1018, with general sample bins */

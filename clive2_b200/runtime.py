@@ -474,6 +474,8 @@ _DISPATCH = {
 # ---------------------------------------------------------------------------------------------------------------
 class FusedRenderer:
     """Thin owner of a `clv_renderer`: one call per sample pass, accumulators resident on the device."""
+    #: kernels of one pass, in launch order
+    KERNELS = ("k_fused_walks", "k_connect_enumerate", "k_connect_rays", "k_connect_finish", "k_fused_finalize")
 
     def __init__(self, device, accel, arrays, seeds, sample_ids=None):
         self.device, self.accel = device, accel
@@ -507,10 +509,10 @@ class FusedRenderer:
         _check(self.device.lib.clv_renderer_kernel_timing(self.handle, int(bool(enabled))))
 
     def kernel_times(self, reset=True):
-        """(ms per kernel summed over the timed passes: walks, connect, finalize; number of passes)."""
-        ms, n = (C.c_double * 3)(), C.c_uint64()
+        """(ms per kernel summed over the timed passes, number of passes)."""
+        ms, n = (C.c_double * 5)(), C.c_uint64()
         _check(self.device.lib.clv_renderer_kernel_times(self.handle, ms, C.byref(n), int(bool(reset))))
-        return {"walks": ms[0], "connect": ms[1], "finalize": ms[2]}, int(n.value)
+        return dict(zip(self.KERNELS, ms)), int(n.value)
 
     def reset(self, seeds=None):
         s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32).reshape(self.n_pixels, 2)

@@ -192,7 +192,8 @@ CLV_API int clv_renderer_create(clv_ctx *ctx, const clv_accel *accel, const clv_
                                 const uint32_t *h_seeds, const uint32_t *h_sample_ids, uint32_t n_local,
                                 clv_renderer **out);
 CLV_API int clv_renderer_destroy(clv_renderer *r);
-/* one sample pass (= Renderer.run_sample, renderer.py:281-291), asynchronous, accumulates on the device */
+/* one sample pass (= Renderer.run_sample, renderer.py:281-291): five kernels on the context's stream, asynchronous,
+ * accumulates on the device */
 CLV_API int clv_renderer_run_sample(clv_renderer *r);
 /* end-to-end variant with HOST buffers: uploads a fresh seed buffer uint32[W*H][2] for this pass (NULL = keep the
  * device-resident streams), runs the pass, then downloads the packed accumulators float[H][W][8] (NULL = skip) and
@@ -241,11 +242,11 @@ CLV_API int clv_renderer_set_traverse_mode(clv_renderer *r, int mode);
  * 64-byte node records fetched, 48-byte triangle records fetched, 128-byte path vertices written / staged */
 CLV_API int clv_counters_enable(clv_ctx *ctx, int enabled);
 CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
-/* per-kernel device time of the fused pass: CUDA events recorded on the launch stream around each of its three
- * kernels (walks, connect, finalize) while enabled; `kernel_times` waits, returns the accumulated milliseconds and the
- * number of passes they cover */
+/* per-kernel device time of the fused pass: CUDA events recorded on the launch stream around each of its five
+ * kernels (walks, connect-enumerate, connect-rays, connect-finish, finalize) while enabled; `kernel_times` waits,
+ * returns the accumulated milliseconds and the number of passes they cover */
 CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
-CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[3], uint64_t *passes_out, int reset);
+CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_t *passes_out, int reset);
 /* number of kernel launches issued on this context so far */
 CLV_API int clv_launch_count(clv_ctx *ctx, uint64_t *count);
 

@@ -296,7 +296,7 @@ def test_full_size_properties(dev):
     for _ in range(4):
         r.run_sample()
     dev.synchronize()
-    assert dev.launch_count - n0 == 12  # three kernels per pass
+    assert dev.launch_count - n0 == 4 * len(runtime.FusedRenderer.KERNELS)  # five kernels per pass
     assert (r.summed_sample_counts == 4).all()
     img = r.summed_image
     assert np.isfinite(img).all() and (img >= 0).all()
