@@ -575,8 +575,11 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 /* ---- fused per-pass kernels (Renderer.run_sample without host round trips) ---------------------------------------- */
 /* stages 1-4: both ray generators and both random walks of one sample, RNG streams in the reference's order
  * (light gen, camera gen, light walk, camera walk; renderer.py:281-285) */
+#ifndef CLV_WALK_MIN_BLOCKS
+#define CLV_WALK_MIN_BLOCKS 6
+#endif
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(CLV_BLOCK)
+__global__ void __launch_bounds__(CLV_BLOCK, CLV_WALK_MIN_BLOCKS)
 k_fused_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
               const int32_t *light_triangle_indices, int light_count, const Material *materials, const Camera *camera,
               AccelView A, uint32_t *seeds, Path *light_paths, Path *camera_paths, Accum *accum, Counters *counters) {

@@ -615,9 +615,15 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
     V3 last_stored_color = v3(0, 0, 0);
 
     for (int i = 0; i < CLV_MAX_BOUNCES; i++) {
+        /* The vertex goes to its slot BEFORE the bounce is known to succeed (slot i only counts once length > i; the
+         * one field the bounce still changes is patched below).  That ends the live range of the 32-word record here
+         * instead of across the traversal, which is what bounds this kernel's registers and therefore its occupancy. */
+        out_path->rays[i] = ray;
+        const V3 o = xyz(ray.origin), d = xyz(ray.direction), inv = xyz(ray.inv_direction), rc = xyz(ray.color);
+        const float ray_tot = ray.tot_importance;
+        const int ray_hit_light = ray.hit_light;
         int best_i = -1;
         float best_t = CLV_INF, u = 0.0f, v = 0.0f;
-        V3 o = xyz(ray.origin), d = xyz(ray.direction), inv = xyz(ray.inv_direction);
         cnt.ray_ref();
         closest_hit<MODE, COUNT>(A, o, d, inv, best_i, best_t, u, v, cnt, -CLV_INF, -1);
         if (best_i == -1) break;
@@ -674,7 +680,6 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         }
 
         float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
-        V3 rc = xyz(ray.color);
         if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);
         else nr.color = pad0(rc * f);
         nr.direction = pad0(wo);
@@ -683,24 +688,24 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         float next_carry;
         if (from_camera) {
             next_carry = c_p;
-            ray.l_importance = l_p;
-            nr.tot_importance = ray.tot_importance * nr.c_importance;
+            nr.tot_importance = ray_tot * nr.c_importance;
         } else {
             next_carry = l_p;
-            ray.c_importance = c_p;
-            nr.tot_importance = ray.tot_importance * nr.l_importance;
+            nr.tot_importance = ray_tot * nr.l_importance;
         }
         if (f == 0.0f) break;
 
-        out_path->rays[i] = ray;
+        /* path.rays[i] = ray with the reverse-direction pdf the bounce produced (:499-507, :512) */
+        if (from_camera) out_path->rays[i].l_importance = l_p;
+        else out_path->rays[i].c_importance = c_p;
         cnt.vertex(1);
         length = i + 1;
-        if (!uni_found && ray.hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
-            V3 c = last_stored_color / ray.tot_importance;
+        if (!uni_found && ray_hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
+            V3 c = last_stored_color / ray_tot;
             uni = v4(c.x, c.y, c.z, 1.0f);
             uni_found = true;
         }
-        last_stored_color = xyz(ray.color);
+        last_stored_color = rc;
 
         ray = nr;
         carry_imp = next_carry;
