@@ -38,6 +38,8 @@ def stale():
 
 def build(force=False, verbose=False):
     if not force and not stale():
+        from . import native_bvh
+        native_bvh.build_library()
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
@@ -46,6 +48,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
+    from . import native_bvh
+    native_bvh.build_library(force=force)  # host-only BVH builder (g++), next to the CUDA library
     return LIB
 
 

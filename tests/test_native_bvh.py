@@ -1,0 +1,65 @@
+"""Native BVH builder against the numpy specification and against the REFERENCE's own builder
+output on tie-free input (tests/golden/bvh_random_soup.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from clive2_b200 import bvh, meshgen, native_bvh, scene
+from clive2_b200.load import fast_load
+from tests.common import GOLDEN
+
+
+def _same(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+
+
+def test_matches_reference_builder_on_tie_free_soup():
+    g = np.load(os.path.join(GOLDEN, "bvh_random_soup.npz"))
+    soup = fast_load(g["mesh_vertices"], g["mesh_faces"], material=2)
+    boxes, tris = native_bvh.build(soup)
+    assert _same(boxes, g["boxes"]) and _same(tris, g["triangles"])
+
+
+@pytest.mark.parametrize("quads,dtype", [(12, np.float64), (40, np.float64), (40, np.float32)])
+def test_matches_numpy_specification(quads, dtype):
+    v, f = meshgen.terrain(quads, quads, jitter=0.0)  # regular grid: full of centroid ties -> exercises the stable order
+    soup = fast_load(v.astype(dtype), f, material=3)
+    b0, t0 = bvh.np_flatten_bvh(bvh.construct_BVH(soup))
+    b1, t1 = native_bvh.build(soup)
+    assert _same(b0, b1) and _same(t0, t1)
+
+
+@pytest.mark.parametrize("preset", ["empty", "bench-spheres"])
+def test_presets_identical_with_either_builder(preset):
+    a0 = scene.preset_arrays(preset, 32, 32, bvh_builder="numpy")
+    a1 = scene.preset_arrays(preset, 32, 32, bvh_builder="native")
+    assert _same(a0.boxes, a1.boxes) and _same(a0.triangles, a1.triangles)
+    assert np.array_equal(a0.light_triangle_indices, a1.light_triangle_indices)
+
+
+def test_tree_invariants_on_a_larger_mesh():
+    v, f = meshgen.terrain(150, 150)
+    soup = fast_load(v, f, material=3)
+    boxes, order = native_bvh.build_order(soup.mins, soup.maxes)
+    assert np.array_equal(np.sort(order), np.arange(len(f)))
+    inner = boxes["right"] == 0
+    leaves = boxes[~inner]
+    assert (leaves["right"] - leaves["left"]).max() <= 8 and (leaves["right"] - leaves["left"]).min() >= 1
+    assert np.array_equal(np.sort(leaves["left"])[1:], np.sort(leaves["right"])[:-1])  # ranges tile [0, n)
+    kids = boxes["left"][inner]
+    assert (kids > np.flatnonzero(inner)).all() and (kids + 1 < len(boxes)).all()
+    # every child box lies inside its parent's
+    for k in (0, 1):
+        c = boxes[kids + k]
+        assert (c["min"][:, :3] >= boxes["min"][inner][:, :3]).all() and (c["max"][:, :3] <= boxes["max"][inner][:, :3]).all()
+
+
+def test_single_triangle_and_small_inputs():
+    for n in (1, 5, 9):
+        rng = np.random.default_rng(n)
+        lo = rng.uniform(-1, 1, (n, 3))
+        hi = lo + rng.uniform(0.01, 0.5, (n, 3))
+        boxes, order = native_bvh.build_order(lo, hi)
+        assert sorted(order.tolist()) == list(range(n))
+        assert len(boxes) == (1 if n <= 8 else 3)
