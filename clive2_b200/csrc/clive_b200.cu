@@ -375,6 +375,7 @@ template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(CLV_BLOCK)
 k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_paths, AccelView A, const Material *materials,
                     const Camera *camera, ConnectScratch cs, Counters *counters) {
+    __shared__ float cam_scratch[CLV_ENUM_SCRATCH * CLV_BLOCK];
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     Cnt<COUNT> cnt;
@@ -384,7 +385,10 @@ k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_path
         TArr Sens;
         Sens.base = cs.sensor + (size_t)id * CLV_SENSOR_WORDS;
         Sens.stride = 1;
-        cand = connect_enumerate<MODE, COUNT>(id, camera_paths, light_paths, A, materials, c, Sens, cnt);
+        TArr Cam;
+        Cam.base = cam_scratch + threadIdx.x;
+        Cam.stride = CLV_BLOCK;
+        cand = connect_enumerate<MODE, COUNT>(id, camera_paths, light_paths, A, materials, c, Sens, Cam, cnt);
         cs.vis[2 * (size_t)id] = 0u;
         cs.vis[2 * (size_t)id + 1] = 0u;
     }

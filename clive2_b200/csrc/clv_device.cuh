@@ -749,6 +749,7 @@ enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30,
  * s-1, [6 + s-1] = index of that triangle (int bits) */
 enum { T_SENSOR = 0, CAM_TRI = 6 };
 #define CLV_SENSOR_WORDS 12
+#define CLV_ENUM_SCRATCH 36 /* origin + normal of up to 6 camera vertices, staged by connect_enumerate */
 
 /* light-image sink of the t = 1 strategies */
 struct LightSink {
@@ -847,14 +848,20 @@ CLV_HD void connect_stage(uint32_t slot, const Path *camera_paths, const Path *l
 template <int MODE, bool COUNT>
 CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_paths, const Path *light_paths,
                                             const AccelView &A, const Material *materials, const Camera &c, TArr Sens,
-                                            Cnt<COUNT> &cnt) {
+                                            TArr Cam /* CLV_ENUM_SCRATCH floats */, Cnt<COUNT> &cnt) {
     const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
     const Ray *cr = cpath->rays, *lr = lpath->rays;
     const int len_c = cpath->length, len_l = lpath->length;
     unsigned long long cand = 0ull;
     unsigned spec_c = 0;
-    for (int j = 0; j < len_c; j++)
+    /* camera vertices are needed once per light vertex: read each from global memory once (the per-thread working set
+     * of path records is far larger than L1, so re-reads went to L2/DRAM: 1.26 GB per launch at C2 before this) */
+    for (int j = 0; j < len_c; j++) {
         if (materials[cr[j].material].type > 0) spec_c |= 1u << j;
+        V4 o = cr[j].origin, nn = cr[j].normal;
+        Cam[6 * j + 0] = o.x; Cam[6 * j + 1] = o.y; Cam[6 * j + 2] = o.z;
+        Cam[6 * j + 3] = nn.x; Cam[6 * j + 4] = nn.y; Cam[6 * j + 5] = nn.z;
+    }
     for (int s = 1; s < len_l + 1; s++) {
         const Ray *light_ray = lr + (s - 1);
         V3 lig_o = xyz(light_ray->origin);
@@ -880,9 +887,10 @@ CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_pa
         V3 lig_n = xyz(light_ray->normal);
         for (int t = 2; t < len_c + 1; t++) {
             if ((spec_c >> (t - 1)) & 1u) continue;
-            V3 dir_l_to_c = normalize(xyz(cr[t - 1].origin) - lig_o);
+            const int j = t - 1;
+            V3 dir_l_to_c = normalize(v3(Cam[6 * j + 0], Cam[6 * j + 1], Cam[6 * j + 2]) - lig_o);
             if (dot(lig_n, dir_l_to_c) < CLV_DELTA) continue;
-            if (dot(xyz(cr[t - 1].normal), -dir_l_to_c) < CLV_DELTA) continue;
+            if (dot(v3(Cam[6 * j + 3], Cam[6 * j + 4], Cam[6 * j + 5]), -dir_l_to_c) < CLV_DELTA) continue;
             cnt.ray_ref();
             cand |= 1ull << ((t - 1) * 7 + s);
         }
@@ -1168,7 +1176,11 @@ CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, 
     Sens.base = sens_words;
     Sens.stride = 1;
     connect_stage<COUNT>(slot, camera_paths, light_paths, materials, S, Sens, X, valid0, cnt);
-    unsigned long long cand = connect_enumerate<MODE, COUNT>(slot, camera_paths, light_paths, A, materials, c, Sens, cnt);
+    float cam_words[CLV_ENUM_SCRATCH];
+    TArr Cam;
+    Cam.base = cam_words;
+    Cam.stride = 1;
+    unsigned long long cand = connect_enumerate<MODE, COUNT>(slot, camera_paths, light_paths, A, materials, c, Sens, Cam, cnt);
     unsigned long long visible = 0ull, m = cand;
     while (m) {
 #if defined(__CUDA_ARCH__)
