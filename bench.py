@@ -40,6 +40,8 @@ CONFIGS = {
     "c3": dict(preset="bench-terrain-1m", width=1024, height=1024,
                workload="C3: Cornell enclosure + procedural terrain mesh (1 002 528 triangles), 1024x1024"),
 }
+CONFIGS["c4"] = dict(preset="bench-terrain-10m", width=1920, height=1080,
+                     workload="C4: Cornell enclosure + procedural terrain mesh (9 999 392 triangles), 1920x1080")
 SEED = 20240928
 
 

@@ -313,3 +313,15 @@ def test_full_size_properties(dev):
     for x in (r, r2):
         x.release()
     sc.release()
+
+
+def test_movie_frame_renders_and_differs_between_frames(dev, tmp_path):
+    """BASELINE config 5 in miniature: two orbit frames of the glossy-spheres scene through the headless driver."""
+    from clive2_b200.movie import render_frame, write_image
+    imgs = [render_frame(dev, "bench-spheres", 64, 36, 4, frame_idx=f, total_frames=120, seed=3) for f in (0, 30)]
+    for img in imgs:
+        assert img.shape == (36, 64, 3) and img.dtype == np.uint8 and img.max() > 0
+    assert (imgs[0] != imgs[1]).mean() > 0.2  # the camera moved a quarter turn
+    again = render_frame(dev, "bench-spheres", 64, 36, 4, frame_idx=0, total_frames=120, seed=3)
+    assert np.abs(again.astype(int) - imgs[0].astype(int)).max() <= 2  # same seeds => same image (atomic order aside)
+    assert write_image(str(tmp_path / "f.png"), imgs[0])
