@@ -462,8 +462,14 @@ k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, c
     flush_counters<COUNT>(cnt, counters);
 }
 
+/* no minimum-blocks bound here: measured 0.81 ms unbounded (90 registers) vs 0.83 / 0.94 / 1.32 ms at 5 / 6 / 7 blocks */
+#ifdef CLV_FINISH_MIN_BLOCKS
+#define CLV_FINISH_BOUNDS __launch_bounds__(CLV_BLOCK, CLV_FINISH_MIN_BLOCKS)
+#else
+#define CLV_FINISH_BOUNDS __launch_bounds__(CLV_BLOCK)
+#endif
 template <bool SPLAT, bool COUNT>
-__global__ void __launch_bounds__(CLV_BLOCK)
+__global__ void CLV_FINISH_BOUNDS
 k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_paths, const Path *light_paths,
                  const Material *materials, const Camera *camera, ConnectScratch cs, WeightAggregator *aggs, V4 *out,
                  LightSink sink, Counters *counters) {
@@ -579,8 +585,9 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 /* ---- fused per-pass kernels (Renderer.run_sample without host round trips) ---------------------------------------- */
 /* stages 1-4: both ray generators and both random walks of one sample, RNG streams in the reference's order
  * (light gen, camera gen, light walk, camera walk; renderer.py:281-285) */
+/* measured at C2: 1.36 ms unbounded (94 regs), 1.19 ms at 6 blocks/SM (80 regs), 1.07 ms at 8 (64 regs, some spills) */
 #ifndef CLV_WALK_MIN_BLOCKS
-#define CLV_WALK_MIN_BLOCKS 6
+#define CLV_WALK_MIN_BLOCKS 8
 #endif
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(CLV_BLOCK, CLV_WALK_MIN_BLOCKS)
