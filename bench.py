@@ -270,28 +270,37 @@ def run_ours(args, cfg, rank, local_rank, world):
     kernel_ms, timed_passes = r._fr.kernel_times(reset=True)
     r._fr.kernel_timing(False)
 
-    # ---- 3. end-to-end timed run: host seeds in, host accumulators out, every step ----------------------------------
-    r._fr.reset(seeds)
+    # ---- 3. end-to-end timed runs through the public API, HOST buffers in and out every step ---------------------------
+    # (a) Renderer.run_sample_preview: seeds in, tone-mapped uint8 preview out = the loop body of the reference's
+    #     render.py:31-37 (pass + `renderer.image`); (b) Renderer.run_sample_e2e: seeds in, raw float accumulators out.
     h_seeds = runtime.PinnedArray((batch, 2), np.uint32)
     h_accum = runtime.PinnedArray((height, width, 8), np.float32)
-    h_seeds.array[:] = seeds
-    for _ in range(W):
-        r.run_sample_e2e(h_seeds, h_accum)
-    dev.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        # a fresh host-side RNG state per step (cheap in-place update so that the upload is real work every step)
-        h_seeds.array[:, 0] ^= np.uint32(k + 1)
-        r.run_sample_e2e(h_seeds, h_accum)
-    dev.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    checksum = float(np.nan_to_num(h_accum.array[..., 3]).sum())
+    h_image = runtime.PinnedArray((height, width, 3), np.uint8)
+
+    def timed_e2e(step):
+        r._fr.reset(seeds)
+        h_seeds.array[:] = seeds
+        for _ in range(W):
+            step()
+        dev.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            # a fresh host-side RNG state per step (cheap in-place update so that the upload is real work every step)
+            h_seeds.array[:, 0] ^= np.uint32(k + 1)
+            step()
+        dev.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    e2e_s = timed_e2e(lambda: r.run_sample_preview(h_seeds, h_image))
+    checksum = int(h_image.array.astype(np.int64).sum())
+    e2e_acc_s = timed_e2e(lambda: r.run_sample_e2e(h_seeds, h_accum))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -357,9 +366,12 @@ def run_ours(args, cfg, rank, local_rank, world):
                                "(connection rays whose target test fails first are skipped)",
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * 8,
-                    "d2h_bytes_per_step": batch * 32, "ms_per_step": e2e_s / K * 1e3, "checksum": checksum,
-                    "api": "Renderer.run_sample_e2e -> clv_renderer_run_sample_e2e (pinned host seeds in, packed "
-                           "accumulators out)"},
+                    "d2h_bytes_per_step": batch * 3, "ms_per_step": e2e_s / K * 1e3, "checksum": checksum,
+                    "api": "Renderer.run_sample_preview -> clv_renderer_run_sample_preview: pinned host seeds in, one "
+                           "pass, device tone map, uint8 preview image out (render.py:31-37)"},
+            "e2e_accumulators": {"value": samples / e2e_acc_s / 1e6, "unit": "Msamples/s",
+                                 "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": batch * 32,
+                                 "api": "Renderer.run_sample_e2e: seeds in, packed float accumulators [H][W][8] out"},
             "gpu_launches": launches,
             "roofline": roofline,
         }
@@ -369,6 +381,7 @@ def run_ours(args, cfg, rank, local_rank, world):
 
     h_seeds.release()
     h_accum.release()
+    h_image.release()
     r.release()
     sc.release()
     dev.release()

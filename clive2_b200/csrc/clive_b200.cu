@@ -625,6 +625,36 @@ k_fused_finalize(uint32_t n_pixels, const WeightAggregator *aggs, const Camera *
     }
 }
 
+/* ---- device tone map: Renderer.image (renderer.py:293-300) + camera.tone_map (camera.py:73-82) ----------------------- *
+ * estimate = nan_to_num(summed_image / summed_sample_weights) in float32; log-average luminance, scaling and the
+ * 255 * s / (s + white^2) curve in float64 exactly as numpy promotes them (float32 array * python float stays float32,
+ * dividing by the float64 log-average promotes).  Only the order of the float64 sum of logs differs from numpy's. */
+__global__ void k_tone_reduce(uint32_t n_pixels, const Accum *accum, double *sum_log) {
+    double acc = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+        const Accum a = accum[i];
+        float b = nan_to_num0(a.image[0] / a.weight), g = nan_to_num0(a.image[1] / a.weight), r = nan_to_num0(a.image[2] / a.weight);
+        double lum = __dadd_rn(__dadd_rn(__dmul_rn((double)b, 0.0722), __dmul_rn((double)g, 0.7152)), __dmul_rn((double)r, 0.2126));
+        acc += log(0.1 + lum);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum_log, acc);
+}
+__global__ void k_tone_map(uint32_t n_pixels, const Accum *accum, const double *sum_log, float exposure, double white2,
+                           uint8_t *out_bgr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const double log_avg = exp(*sum_log / (double)n_pixels);
+    const Accum a = accum[i];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float e = nan_to_num0(a.image[ch] / a.weight) * exposure;
+        double s = (double)e / log_avg;
+        double m = 255.0 * s / (s + white2);
+        out_bgr[3 * (size_t)i + ch] = (uint8_t)(int)m; /* astype(uint8): truncation */
+    }
+}
+
 /* ---- parity hooks -------------------------------------------------------------------------------------------------- */
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(CLV_BLOCK)
@@ -863,6 +893,8 @@ struct clv_renderer {
     Accum *d_accum;
     float *d_pass_weight;
     void *d_connect_scratch;
+    double *d_tone_sum;
+    uint8_t *d_tone_image;
     std::vector<uint32_t> sample_ids;
     unsigned long long passes;
     /* optional per-kernel timing: events around each of the three kernels of every pass */
@@ -881,6 +913,8 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     cudaFree(r->d_camera_paths); cudaFree(r->d_aggs); cudaFree(r->d_light_image); cudaFree(r->d_accum);
     cudaFree(r->d_pass_weight);
     cudaFree(r->d_connect_scratch);
+    cudaFree(r->d_tone_sum);
+    cudaFree(r->d_tone_image);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     delete r;
     return CLV_OK;
@@ -955,6 +989,8 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     TRY(zalloc((void **)&r->d_accum, (size_t)n_pixels * sizeof(Accum)));
     TRY(zalloc((void **)&r->d_pass_weight, 16));
     TRY(zalloc((void **)&r->d_connect_scratch, connect_scratch_bytes(n_local)));
+    TRY(zalloc((void **)&r->d_tone_sum, 16));
+    TRY(zalloc((void **)&r->d_tone_image, (size_t)n_pixels * 3));
     TRY(load_seeds(r, h_seeds));
 #undef TRY
     CK(cudaStreamSynchronize(c->stream));
@@ -1054,6 +1090,42 @@ extern "C" int clv_renderer_run_sample_e2e(clv_renderer *r, const uint32_t *h_se
         CK(cudaMemcpyAsync(h_accum, r->d_accum, (size_t)r->n_pixels * sizeof(Accum), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
+    return CLV_OK;
+}
+
+static int launch_tone_map(clv_renderer *r, float exposure) {
+    clv_ctx *c = r->ctx;
+    CK(cudaMemsetAsync(r->d_tone_sum, 0, sizeof(double), c->stream));
+    k_tone_reduce<<<std::min<unsigned>((r->n_pixels + 255) / 256, 148u * 8u), 256, 0, c->stream>>>(r->n_pixels, r->d_accum, r->d_tone_sum);
+    LAUNCHED(c);
+    k_tone_map<<<(r->n_pixels + 255) / 256, 256, 0, c->stream>>>(r->n_pixels, r->d_accum, r->d_tone_sum, exposure, 1.0, r->d_tone_image);
+    LAUNCHED(c);
+    return CLV_OK;
+}
+
+/* Renderer.image on the device: tone-mapped uint8 BGR image [H][W][3] of the current estimate, downloaded to h_out */
+extern "C" int clv_renderer_tone_map(clv_renderer *r, float exposure, uint8_t *h_out) {
+    REQUIRE(r && h_out, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    int rc = launch_tone_map(r, exposure);
+    if (rc != CLV_OK) return rc;
+    CK(cudaMemcpyAsync(h_out, r->d_tone_image, (size_t)r->n_pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CLV_OK;
+}
+
+/* the interactive loop of render.py:31-37 in one call: seeds in (NULL = keep streams), one pass, preview image out */
+extern "C" int clv_renderer_run_sample_preview(clv_renderer *r, const uint32_t *h_seeds, float exposure, uint8_t *h_image) {
+    REQUIRE(r && h_image, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (h_seeds && (rc = load_seeds(r, h_seeds)) != CLV_OK) return rc;
+    if ((rc = launch_pass(r)) != CLV_OK) return rc;
+    if ((rc = launch_tone_map(r, exposure)) != CLV_OK) return rc;
+    CK(cudaMemcpyAsync(h_image, r->d_tone_image, (size_t)r->n_pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return CLV_OK;
 }
 

@@ -46,10 +46,7 @@ def render_frame(device, preset, width, height, samples, frame_idx=None, total_f
         r.run_sample()
     image = r.image
     r.release()
-    sc.release()
-    for acc in list(device._accels.values()):  # the per-frame BVH is not needed again
-        acc.release()
-    device._accels.clear()
+    sc.release()  # also drops the per-frame BVH cached for these buffers
     return image
 
 

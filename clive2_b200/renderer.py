@@ -2,7 +2,7 @@
 
 Two ways to run a sample pass, same results:
 
-* **fused** (default): `run_sample()` is ONE call into the C ABI (`clv_renderer_run_sample`): three kernels on one
+* **fused** (default): `run_sample()` is ONE call into the C ABI (`clv_renderer_run_sample`): five kernels on one
   stream, no host synchronisation, light image splatted with atomics instead of sorted, accumulators resident on the
   device.  `summed_image` & co. are read back only when asked for.
 * **staged** (`fused=False`): the reference's eight stage methods, each launching the same-named kernel through
@@ -110,6 +110,22 @@ class Renderer:
                                 None if host_accum is None else host_accum.ptr)
         self._cache = None
         self.samples += 1
+
+    def run_sample_preview(self, host_seeds, host_image):
+        """The interactive loop body of the reference's render.py:31-37 with HOST buffers: upload seeds (or None), one
+        pass, device tone map (exposure 4), download the uint8 (H,W,3) preview into `host_image` (PinnedArray)."""
+        if not self.fused:
+            raise ValueError("run_sample_preview is a fused-renderer call")
+        self._fr.run_sample_preview(None if host_seeds is None else host_seeds.ptr, TONE_MAP_EXPOSURE, host_image.ptr)
+        self._cache = None
+        self.samples += 1
+
+    def image_device(self, out=None):
+        """`image` computed on the device (log-average tone map as camera.tone_map; equal up to +-1 per channel because
+        only the order of the float64 sum of logs differs)."""
+        if not self.fused:
+            raise ValueError("image_device needs the fused renderer")
+        return self._fr.tone_map(TONE_MAP_EXPOSURE, out)
 
     # ================================================================================================================
     # staged path: renderer.py:47-84 buffers and :113-278 stages

@@ -66,6 +66,8 @@ SIGNATURES = {
     "clv_renderer_run_sample": [_vp],
     "clv_renderer_run_sample_e2e": [_vp, _vp, _vp],
     "clv_renderer_reset": [_vp, _vp],
+    "clv_renderer_tone_map": [_vp, C.c_float, _vp],
+    "clv_renderer_run_sample_preview": [_vp, _vp, C.c_float, _vp],
     "clv_renderer_read": [_vp, _int, _vp, _sz],
     "clv_renderer_device_ptr": [_vp, _int, _pp, C.POINTER(_sz)],
     "clv_renderer_set_traverse_mode": [_vp, _int],
@@ -164,6 +166,8 @@ class Buffer:
 
     def release(self):
         if getattr(self, "ptr", None):
+            # an acceleration structure cached for this buffer must not outlive it: the allocator reuses addresses
+            self.device._forget_accels(self.ptr)
             self.device.lib.clv_mem_free(self.device.ctx, self.ptr)
             self.ptr = None
 
@@ -294,6 +298,10 @@ class Device:
             t = triangles.numpy(T.Triangle) if isinstance(triangles, Buffer) else triangles
             acc = self._accels[key] = Accel(self, b, t)
         return acc
+
+    def _forget_accels(self, ptr):
+        for key in [k for k in getattr(self, "_accels", {}) if ptr in k]:
+            self._accels.pop(key).release()
 
     def synchronize(self):
         _check(self.lib.clv_ctx_synchronize(self.ctx))
@@ -504,6 +512,17 @@ class FusedRenderer:
 
     def set_traverse_mode(self, mode):
         _check(self.device.lib.clv_renderer_set_traverse_mode(self.handle, int(mode)))
+
+    def tone_map(self, exposure, out=None):
+        """uint8 (H,W,3) BGR preview computed on the device (clv_renderer_tone_map)."""
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.uint8)
+        ptr = out.ptr if isinstance(out, PinnedArray) else _host_ptr(out)
+        _check(self.device.lib.clv_renderer_tone_map(self.handle, float(exposure), ptr))
+        return out.array if isinstance(out, PinnedArray) else out
+
+    def run_sample_preview(self, h_seeds_ptr, exposure, h_image_ptr):
+        _check(self.device.lib.clv_renderer_run_sample_preview(self.handle, h_seeds_ptr, float(exposure), h_image_ptr))
 
     def kernel_timing(self, enabled=True):
         _check(self.device.lib.clv_renderer_kernel_timing(self.handle, int(bool(enabled))))

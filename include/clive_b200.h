@@ -200,6 +200,12 @@ CLV_API int clv_renderer_run_sample(clv_renderer *r);
  * waits.  Page-locked memory from clv_host_alloc makes both copies asynchronous DMA. */
 CLV_API int clv_renderer_run_sample_e2e(clv_renderer *r, const uint32_t *h_seeds, float *h_accum_packed);
 CLV_API int clv_renderer_reset(clv_renderer *r, const uint32_t *h_seeds); /* zero accumulators, reload seeds */
+/* Renderer.image (renderer.py:293-300 + camera.py:73-82) on the device: tone-mapped uint8 BGR [H][W][3] of the current
+ * estimate summed_image / summed_sample_weights, downloaded into h_out_bgr (waits) */
+CLV_API int clv_renderer_tone_map(clv_renderer *r, float exposure, uint8_t *h_out_bgr);
+/* the interactive loop body of render.py:31-37 with HOST buffers: upload a seed buffer (NULL = keep the device
+ * streams), run one pass, tone map, download the uint8 preview (waits) */
+CLV_API int clv_renderer_run_sample_preview(clv_renderer *r, const uint32_t *h_seeds, float exposure, uint8_t *h_image_bgr);
 
 typedef enum clv_buffer_id {
     CLV_BUF_SUMMED_IMAGE = 0,          /* float[H][W][3]   renderer.py:41  */

@@ -325,3 +325,41 @@ def test_movie_frame_renders_and_differs_between_frames(dev, tmp_path):
     again = render_frame(dev, "bench-spheres", 64, 36, 4, frame_idx=0, total_frames=120, seed=3)
     assert np.abs(again.astype(int) - imgs[0].astype(int)).max() <= 2  # same seeds => same image (atomic order aside)
     assert write_image(str(tmp_path / "f.png"), imgs[0])
+
+
+def test_device_tone_map_matches_host_tone_map(dev):
+    w, h = 96, 64
+    a = arrays("bench-spheres", w, h)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seed=5)
+    for _ in range(6):
+        r.run_sample()
+    host = r.image.astype(int)
+    devimg = r.image_device().astype(int)
+    assert devimg.shape == (h, w, 3)
+    assert np.abs(devimg - host).max() <= 1 and (devimg != host).mean() < 0.01
+    # preview call = pass + tone map + download
+    pin = runtime.PinnedArray((h, w, 3), np.uint8)
+    r.run_sample_preview(None, pin)
+    assert np.abs(pin.array.astype(int) - r.image.astype(int)).max() <= 1
+    pin.release()
+    r.release()
+    sc.release()
+
+
+def test_accel_cache_does_not_survive_its_buffers(dev, O):
+    """The allocator hands the addresses of a released scene to the next one; a BVH cached for the old buffers must
+    not be served for the new scene."""
+    first = None
+    for preset in ("empty", "bench-spheres", "empty"):
+        a = arrays(preset, 32, 32)
+        sc = scene.scene_from_arrays(a, dev)
+        acc = dev.accel(sc.boxes, sc.triangles)
+        assert acc.n_triangles == len(a.triangles)
+        rays = random_rays(20000, [-9, -1.9, -9], [9, 9, 9], seed=9)
+        tri, _, _, _ = O.traverse(rays, a.boxes, a.triangles)
+        tri2, _, _, _ = dev.traverse(acc, rays)
+        assert np.array_equal(tri, tri2)
+        first = first or acc
+        sc.release()
+        assert not dev._accels
