@@ -217,7 +217,12 @@ def run_ours(args, cfg, rank, local_rank, world):
     t_up = time.perf_counter()
     sc = scene.scene_from_arrays(arrays, dev)
     seeds = seeds_for(batch, rank)
-    r = Renderer(sc, seeds=seeds)
+    ids = None
+    if args.tile:
+        from clive2_b200 import sharding
+        tw, th = (int(x) for x in args.tile.lower().split("x"))
+        ids = sharding.tiled_order(width, height, tw, th)
+    r = Renderer(sc, seeds=seeds, sample_ids=ids)
     dev.synchronize()
     t_up = time.perf_counter() - t_up
     accel_stats = dev.accel(sc.boxes, sc.triangles).stats()
@@ -397,6 +402,8 @@ def main():
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile", default=os.environ.get("CLV_BENCH_TILE", ""),
+                    help="WxH: trace samples in tiles of WxH pixels per warp-sized group (e.g. 8x4); default row-major")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     args.steps = max(args.steps, 1)

@@ -60,6 +60,7 @@ struct clv_ctx {
     unsigned long long launches;
     int sm_count;
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
+    int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
     void *cs_mem;
     uint32_t cs_capacity;
@@ -96,6 +97,7 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     c->launches = 0;
     c->sm_count = prop.multiProcessorCount;
     c->refill_below = getenv("CLV_REFILL_BELOW") ? atoi(getenv("CLV_REFILL_BELOW")) : 24;
+    c->ray_schedule = getenv("CLV_RAY_SCHEDULE") ? atoi(getenv("CLV_RAY_SCHEDULE")) : 8; /* measured: C2 1.15 -> 1.10 ms, C3 8.07 -> 7.10 ms */
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -414,7 +416,7 @@ k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_path
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(CLV_BLOCK)
 k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, const Camera *camera, ConnectScratch cs,
-               Counters *counters, int refill_below) {
+               Counters *counters, int refill_below, int schedule) {
     const uint32_t count = *cs.task_count;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -449,14 +451,24 @@ k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, c
         } else if (holding == 0u) {
             break;
         }
-        if (have) {
-            int st = occ_round<COUNT>(A, ray, stack, cnt);
-            if (st != OCC_RUNNING) {
-                have = false;
-                const uint32_t slot = task >> 6;
-                const int q = (int)(task & 63u);
-                if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
-            }
+        int st = OCC_RUNNING;
+        if (schedule == 0) {
+            /* round form: every lane walks down to its next leaf, then every lane tests its leaf */
+            if (have) st = occ_round<COUNT>(A, ray, stack, cnt);
+        } else {
+            /* majority vote: per iteration the warp runs ONE kind of step — an inner node for the lanes that sit at
+             * one, or a whole leaf for the lanes that hold one — whichever more lanes wait for */
+            const bool at_inner = have && ray.cur >= 0;
+            const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
+            const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && !at_inner));
+            if (n_inner * schedule >= n_leaf * 4) { if (at_inner) st = occ_inner_step<COUNT>(A, ray, stack, cnt); }
+            else if (have && !at_inner) st = occ_leaf_step<COUNT>(A, ray, stack, cnt);
+        }
+        if (st != OCC_RUNNING) {
+            have = false;
+            const uint32_t slot = task >> 6;
+            const int q = (int)(task & 63u);
+            if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
         }
     }
     flush_counters<COUNT>(cnt, counters);
@@ -735,7 +747,7 @@ static int launch_connect(clv_ctx *c, int mode, bool splat, uint32_t n, const ui
     if (mid_events) CK(cudaEventRecord(mid_events[0], c->stream));
     const uint64_t warps = ((uint64_t)n * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
     const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
-#define CALL(M, CT) k_connect_rays<M, CT><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(cp, lp, view, cam, cs, ctr, c->refill_below)
+#define CALL(M, CT) k_connect_rays<M, CT><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(cp, lp, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
     DISPATCH_MC(mode, c->counting, CALL);
 #undef CALL
     LAUNCHED(c);

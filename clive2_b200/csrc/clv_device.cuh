@@ -372,6 +372,44 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
     return status;
 }
 
+/* the two halves of a round as separate steps, for the majority-vote schedule of k_connect_rays: one inner node ... */
+template <bool COUNT>
+CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt) {
+    const V4 *n = A.nodes + 4 * (size_t)r.cur;
+    V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
+    cnt.node();
+    bool hl, hr;
+    float tl, tr;
+    slab_test(r.o, r.inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
+    slab_test(r.o, r.inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
+    int lref = f2i(n3.x), rref = f2i(n3.y);
+    bool go_l = hl && tl <= r.t_bound, go_r = hr && tr <= r.t_bound;
+    bool left_first = tl < tr;
+    if (go_l && go_r && r.sp < CLV_STACK) stack[r.sp++] = left_first ? rref : lref;
+    if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return OCC_RUNNING; }
+    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
+    return OCC_CLEAR;
+}
+/* ... or one whole leaf */
+template <bool COUNT>
+CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<COUNT> &cnt) {
+    int code = ~r.cur;
+    int first = code >> 4, count = code & 15;
+    bool blocked = false;
+    for (int i = first; i < first + count; i++) {
+        const V4 *tp = A.tris + 3 * (size_t)i;
+        V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+        cnt.tri();
+        float t, u, v;
+        if (i != r.skip && tri_test(r.o, r.d, xyz(a), xyz(b), xyz(c), t, u, v) &&
+            (t < r.t_bound || (t == r.t_bound && f2i(a.w) < r.rank_bound)))
+            blocked = true;
+    }
+    if (blocked) return OCC_BLOCKED;
+    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
+    return OCC_CLEAR;
+}
+
 /* direct test of one triangle of the reference numbering; also returns its reference rank */
 CLV_HD bool test_one(const AccelView &A, int tri, V3 o, V3 d, float &t, int &rank) {
     const V4 *tp = A.tris + 3 * (size_t)tri;

@@ -36,3 +36,13 @@ def reduce_accumulators(tensor, dst=0, group=None):
         return tensor
     dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return tensor
+
+
+def tiled_order(width, height, tile_w=8, tile_h=4):
+    """All sample ids of a frame ordered tile by tile (tile_w x tile_h pixels, row-major inside a tile), so that the 32
+    lanes of a warp hold a compact block of pixels instead of a 32 x 1 strip.  Passing it as `sample_ids` changes
+    which thread traces which sample, not any sample's result (ids keep their own seed rows and pixels)."""
+    ys, xs = np.divmod(np.arange(width * height, dtype=np.int64), width)
+    tiles_x = (width + tile_w - 1) // tile_w
+    key = ((ys // tile_h) * tiles_x + xs // tile_w) * (tile_w * tile_h) + (ys % tile_h) * tile_w + xs % tile_w
+    return np.argsort(key, kind="stable").astype(np.uint32)
