@@ -781,8 +781,9 @@ struct TArr {
     CLV_HDM float &operator[](int k) const { return base[k * stride]; }
 };
 /* scratch layout of one sample in the connection stage (floats) */
-enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30, C_COS = 36, C_TOT = 42, G_LL = 48, G_CC = 53 };
-#define CLV_CONNECT_SCRATCH 58
+enum { L_LIMP = 0, L_CIMP = 6, L_COS = 12, L_TOT = 18, C_LIMP = 24, C_CIMP = 30, C_COS = 36, C_TOT = 42, G_LL = 48, G_CC = 53,
+       P_BACK = 58 /* p_values[0..s-1] of the strategy being evaluated */ };
+#define CLV_CONNECT_SCRATCH 64
 /* per-sample record of the t = 1 projections (12 words): [s-1] = t of the nearest sensor-triangle hit of light vertex
  * s-1, [6 + s-1] = index of that triangle (int bits) */
 enum { T_SENSOR = 0, CAM_TRI = 6 };
@@ -1043,67 +1044,40 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
             g_conn = geometry_from(S[L_COS + s - 1], S[C_COS + t - 1], lig_o, cam_o);
         }
 
-        /* full-path accessors: vertex i < s is light vertex i, otherwise camera vertex t+s-i-1 (:546-549) */
+        /* MIS weight (:693-776).  Full-path vertex i < s is light vertex i, otherwise camera vertex j = k-1-i (:546-549).
+         * p_values[i] = p_i: p_s at i = s, divided down the light side by the ratios p_ratios[i] (:751-755), multiplied
+         * up the camera side (:745-749); entries i and i+1 of every specular vertex i and entry k are zero (:759-766);
+         * the sum runs over ascending i (:768-770).  Same operations in the same order as the reference, written as
+         * three short loops over the vertices that exist instead of fixed-size arrays. */
         const int k = s + t; /* number of vertices */
-        auto limp = [&](int i) { return i < s ? S[L_LIMP + i] : S[C_LIMP + (k - i - 1)]; };
-        auto cimp = [&](int i) { return i < s ? S[L_CIMP + i] : S[C_CIMP + (k - i - 1)]; };
-        auto edge = [&](int i) { /* geometry term of the edge between full-path vertices i and i+1 */
-            if (i + 1 < s) return S[G_LL + i];
-            if (i == s - 1) return g_conn;
-            return S[G_CC + (k - i - 2)];
-        };
-        auto ratio = [&](int i) { /* p_ratios[i], :709-735 */
-            float num, denom;
-            if (i == 0) { num = limp(0); denom = cimp(0) * edge(0); }
-            else if (i == k - 1) { num = limp(i) * edge(i - 1); denom = cimp(i); }
-            else { num = limp(i) * edge(i - 1); denom = cimp(i) * edge(i); }
-            return num / denom;
-        };
-        auto specular = [&](int i) {
-            if (i < s) return ((spec_l >> i) & 1u) != 0;
-            int j = k - i - 1;
-            if (j == 0 && sensor_vertex) return X.spec_sensor;
-            return ((spec_c >> j) & 1u) != 0;
-        };
+        unsigned specmask = spec_l & ((1u << s) - 1u);
+        for (int j = 0; j < t; j++) {
+            bool sp = (j == 0 && sensor_vertex) ? X.spec_sensor : (((spec_c >> j) & 1u) != 0);
+            if (sp) specmask |= 1u << (k - 1 - j);
+        }
+        const unsigned zmask = specmask | (specmask << 1) | (1u << k);
 
         float prior_light_importance = (s == 0) ? 1.0f : S[L_TOT + s - 1];
         float p_s = cam_tot * prior_light_importance;
 
-        /* p_values[0..k] (:737-766); p_values[k] is forced to zero, p_values[k+1] is never read */
-        float pv[14];
-#pragma unroll
-        for (int i = 0; i < 14; i++) pv[i] = 0.0f;
-        {
-            float p_i = p_s;
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                if (i >= s && i < k - 1) {
-                    p_i = ratio(i) * p_i;
-                    pv[i + 1] = p_i;
-                }
-            }
-            p_i = p_s;
-#pragma unroll
-            for (int i = 11; i >= 0; i--) {
-                if (i <= s - 1) {
-                    p_i = p_i / ratio(i);
-                    pv[i] = p_i;
-                }
-            }
+        float p_i = p_s;
+        for (int i = s - 1; i >= 0; i--) { /* light side, p_ratios[i] = num / denom of :711-734 */
+            float num = (i == 0) ? S[L_LIMP] : S[L_LIMP + i] * S[G_LL + i - 1];
+            float denom = S[L_CIMP + i] * ((i == s - 1) ? g_conn : S[G_LL + i]);
+            p_i = p_i / (num / denom);
+            S[P_BACK + i] = p_i;
         }
-#pragma unroll
-        for (int i = 0; i < 13; i++)
-            if (i == s) pv[i] = p_s;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            if (i < k && specular(i)) { pv[i] = 0.0f; pv[i + 1] = 0.0f; }
-        }
-        float p_at_s = 0.0f, sum = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 13; i++) {
-            if (i == k) pv[i] = 0.0f;
-            if (i <= k) sum += pv[i];
-            if (i == s) p_at_s = pv[i];
+        float sum = 0.0f;
+        for (int i = 0; i < s; i++) sum += ((zmask >> i) & 1u) ? 0.0f : S[P_BACK + i];
+        const float p_at_s = ((zmask >> s) & 1u) ? 0.0f : p_s;
+        sum += p_at_s;
+        p_i = p_s;
+        for (int i = s; i <= k - 2; i++) { /* camera side */
+            const int j = k - 1 - i;
+            float num = (i == 0) ? S[C_LIMP + j] : S[C_LIMP + j] * ((i == s) ? g_conn : S[G_CC + j]);
+            float denom = S[C_CIMP + j] * S[G_CC + j - 1];
+            p_i = (num / denom) * p_i;
+            sum += ((zmask >> (i + 1)) & 1u) ? 0.0f : p_i;
         }
 
         if (!(p_at_s > 0.0f && sum > 0.0f)) continue;
