@@ -489,6 +489,7 @@ k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_path
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
     if (id == 0) *cs.task_count = 0u; /* every ray of this pass is done (stream order): reset the list for the next */
+    const unsigned warp_lanes = __ballot_sync(0xffffffffu, id < n);
     if (id < n) {
         Camera c = camera[0];
         TArr S, Sens;
@@ -502,7 +503,7 @@ k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_path
         unsigned long long visible = (unsigned long long)cs.vis[2 * (size_t)id] | ((unsigned long long)cs.vis[2 * (size_t)id + 1] << 32);
         /* staged ABI: aggregator slot == id.  Fused renderer: aggregators are per pixel */
         uint32_t agg_slot = sample_ids ? sample_ids[id] : id;
-        connect_finish<SPLAT>(X, valid0 | visible, id, agg_slot, materials, c, aggs, out, sink);
+        connect_finish<SPLAT>(X, valid0 | visible, id, agg_slot, materials, c, aggs, out, sink, warp_lanes);
     }
     flush_counters<COUNT>(cnt, counters);
 }

@@ -45,6 +45,9 @@
 #define CLV_INF (clv_bits_to_float(0x7f800000u))
 #define CLV_MAX_BOUNCES 6     /* trace.metal:407 */
 #define CLV_STACK 64          /* trace.metal:145 */
+#ifndef CLV_WALK_SCHEDULE
+#define CLV_WALK_SCHEDULE 0    /* closest_hit: 0 = while-while, w > 0 = majority vote with weight w */
+#endif
 
 namespace clv {
 
@@ -228,77 +231,95 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
     int cur = A.root_ref;
     bool have = true; /* `cur` holds a node that still has to be processed */
 
-    while (have) {
-        /* ---- phase 1: walk down inner nodes ------------------------------------------------------------------ */
-        while (have && cur >= 0) {
-            const V4 *n = A.nodes + 4 * (size_t)cur;
-            V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
-            cnt.node();
-            bool hl, hr;
-            float tl, tr;
-            slab_test(o, inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
-            slab_test(o, inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
-            int lref = f2i(n3.x), rref = f2i(n3.y);
-            bool go_l, go_r, push;
-            int push_ref;
-            float push_t;
-            if (MODE == TRAVERSE_REFERENCE) {
-                /* the reference pushes left then right and pops right first; the deferred left child is re-checked
-                 * against best_t when popped = the predicate the reference evaluates at pop time */
-                go_r = hr && tr < best_t;
-                go_l = hl && tl < best_t;
-                push = go_r && hl;
-                push_ref = lref;
-                push_t = tl;
-                cur = go_r ? rref : lref;
-                have = go_r || go_l;
-            } else {
-                go_l = hl && tl <= best_t;
-                go_r = hr && tr <= best_t;
-                bool left_first = tl < tr; /* tie: right first, the reference's order */
-                push = go_l && go_r;
-                push_ref = left_first ? rref : lref;
-                push_t = left_first ? tr : tl;
-                cur = (go_l && (left_first || !go_r)) ? lref : rref;
-                have = go_l || go_r;
-            }
-            if (push && sp < CLV_STACK) { st_ref[sp] = push_ref; st_t[sp] = push_t; sp++; }
-            while (!have && sp > 0) {
-                sp--;
-                float t = st_t[sp];
-                if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
-            }
+    /* one inner node: test both child boxes, continue with the nearer surviving child, keep the other */
+    auto inner_step = [&]() {
+        const V4 *n = A.nodes + 4 * (size_t)cur;
+        V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
+        cnt.node();
+        bool hl, hr;
+        float tl, tr;
+        slab_test(o, inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
+        slab_test(o, inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
+        int lref = f2i(n3.x), rref = f2i(n3.y);
+        bool go_l, go_r, push;
+        int push_ref;
+        float push_t;
+        if (MODE == TRAVERSE_REFERENCE) {
+            /* the reference pushes left then right and pops right first; the deferred left child is re-checked
+             * against best_t when popped = the predicate the reference evaluates at pop time */
+            go_r = hr && tr < best_t;
+            go_l = hl && tl < best_t;
+            push = go_r && hl;
+            push_ref = lref;
+            push_t = tl;
+            cur = go_r ? rref : lref;
+            have = go_r || go_l;
+        } else {
+            go_l = hl && tl <= best_t;
+            go_r = hr && tr <= best_t;
+            bool left_first = tl < tr; /* tie: right first, the reference's order */
+            push = go_l && go_r;
+            push_ref = left_first ? rref : lref;
+            push_t = left_first ? tr : tl;
+            cur = (go_l && (left_first || !go_r)) ? lref : rref;
+            have = go_l || go_r;
         }
-        /* ---- phase 2: one leaf ----------------------------------------------------------------------------------- */
-        if (have) {
-            int code = ~cur;
-            int first = code >> 4, count = code & 15;
-            bool stop = false;
-            for (int i = first; i < first + count; i++) {
-                const V4 *tp = A.tris + 3 * (size_t)i;
-                V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-                cnt.tri();
-                float t, u, v;
-                if (tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v)) {
-                    bool accept;
-                    if (MODE == TRAVERSE_REFERENCE) accept = t < best_t;
-                    else accept = t < best_t || (t == best_t && f2i(a.w) < best_rank);
-                    if (accept) {
-                        best_i = i; best_t = t; bu = u; bv = v;
-                        best_rank = f2i(a.w);
-                        stop = stop || (i != stop_skip && t < stop_below);
-                    }
+        if (push && sp < CLV_STACK) { st_ref[sp] = push_ref; st_t[sp] = push_t; sp++; }
+        while (!have && sp > 0) {
+            sp--;
+            float t = st_t[sp];
+            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+        }
+    };
+    /* one leaf: test its triangles */
+    auto leaf_step = [&]() {
+        int code = ~cur;
+        int first = code >> 4, count = code & 15;
+        bool stop = false;
+        for (int i = first; i < first + count; i++) {
+            const V4 *tp = A.tris + 3 * (size_t)i;
+            V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+            cnt.tri();
+            float t, u, v;
+            if (tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v)) {
+                bool accept;
+                if (MODE == TRAVERSE_REFERENCE) accept = t < best_t;
+                else accept = t < best_t || (t == best_t && f2i(a.w) < best_rank);
+                if (accept) {
+                    best_i = i; best_t = t; bu = u; bv = v;
+                    best_rank = f2i(a.w);
+                    stop = stop || (i != stop_skip && t < stop_below);
                 }
             }
-            have = false;
-            if (stop) sp = 0; /* early exit of a predicate ray: nothing left to look at */
-            while (!have && sp > 0) {
-                sp--;
-                float t = st_t[sp];
-                if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
-            }
         }
+        have = false;
+        if (stop) sp = 0; /* early exit of a predicate ray: nothing left to look at */
+        while (!have && sp > 0) {
+            sp--;
+            float t = st_t[sp];
+            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+        }
+    };
+#if defined(__CUDA_ARCH__) && CLV_WALK_SCHEDULE > 0
+    /* majority vote (as in k_connect_rays): per iteration the converged lanes run ONE kind of step, the one more of
+     * them wait for (inner nodes win when n_inner * CLV_WALK_SCHEDULE >= n_leaf * 4).  Every lane still visits its own
+     * nodes in its own order, so results do not depend on the schedule. */
+    const unsigned lanes = __activemask();
+    for (;;) {
+        const bool at_inner = have && cur >= 0, at_leaf = have && cur < 0;
+        const unsigned m_inner = __ballot_sync(lanes, at_inner), m_leaf = __ballot_sync(lanes, at_leaf);
+        if ((m_inner | m_leaf) == 0u) break;
+        if (__popc(m_inner) * CLV_WALK_SCHEDULE >= __popc(m_leaf) * 4) { if (at_inner) inner_step(); }
+        else if (at_leaf) leaf_step();
     }
+#else
+    /* while-while: lanes at inner nodes step together until every lane has reached a leaf (or finished), then all
+     * leaves are processed together */
+    while (have) {
+        while (have && cur >= 0) inner_step();
+        if (have) leaf_step();
+    }
+#endif
 }
 
 /* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
@@ -986,7 +1007,7 @@ CLV_HD int connect_ray_begin(int q, const Ray *cr, const Ray *lr, TArr Sens, con
 template <bool SPLAT>
 CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
                            const Material *materials, const Camera &c, WeightAggregator *weight_aggregators, V4 *out,
-                           const LightSink &sink) {
+                           const LightSink &sink, unsigned warp_lanes /* device: lanes of the warp that make this call */) {
     const Ray *cr = X.cr, *lr = X.lr;
     TArr S = X.S;
     const unsigned spec_l = X.spec_l, spec_c = X.spec_c;
@@ -1141,6 +1162,11 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
         }
     }
 
+#if defined(__CUDA_ARCH__)
+    /* lanes leave the strategy loop at different times; without this the splat-weight code below ran with 2.3 of 32
+     * lanes active (ncu, profiles/r01_notes.md) */
+    __syncwarp(warp_lanes);
+#endif
     /* 3x3 splat weights (:827-864) */
     WeightAggregator agg;
     for (int i = 0; i < 3; i++) { agg.pad0[i] = 0.0f; agg.pad1[i] = 0.0f; }
@@ -1207,7 +1233,12 @@ CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, 
         while (st == OCC_RUNNING) st = occ_round<COUNT>(A, ray, stack, cnt);
         if (st == OCC_CLEAR) visible |= 1ull << q;
     }
-    connect_finish<SPLAT>(X, valid0 | visible, entry_id, agg_slot, materials, c, weight_aggregators, out, sink);
+#if defined(__CUDA_ARCH__)
+    const unsigned warp_lanes = __activemask();
+#else
+    const unsigned warp_lanes = 0u;
+#endif
+    connect_finish<SPLAT>(X, valid0 | visible, entry_id, agg_slot, materials, c, weight_aggregators, out, sink, warp_lanes);
 }
 
 /* adaptive_finalize_samples for one pixel, trace.metal:981-1018, with general sample bins */
