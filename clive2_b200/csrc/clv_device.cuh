@@ -45,6 +45,9 @@
 #define CLV_INF (clv_bits_to_float(0x7f800000u))
 #define CLV_MAX_BOUNCES 6     /* trace.metal:407 */
 #define CLV_STACK 64          /* trace.metal:145 */
+#ifndef CLV_WALK_INNER_BURST
+#define CLV_WALK_INNER_BURST 0 /* closest_hit, while-while form: 0 = walk down to the leaf, n > 0 = at most n node steps per round */
+#endif
 #ifndef CLV_WALK_SCHEDULE
 #define CLV_WALK_SCHEDULE 0    /* closest_hit: 0 = while-while, w > 0 = majority vote with weight w */
 #endif
@@ -316,8 +319,14 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
     /* while-while: lanes at inner nodes step together until every lane has reached a leaf (or finished), then all
      * leaves are processed together */
     while (have) {
+#if CLV_WALK_INNER_BURST > 0
+        /* bounded burst: lanes that already hold a leaf wait for at most CLV_WALK_INNER_BURST node steps of the others */
+        for (int burst = 0; burst < CLV_WALK_INNER_BURST && have && cur >= 0; burst++) inner_step();
+        if (have && cur < 0) leaf_step();
+#else
         while (have && cur >= 0) inner_step();
         if (have) leaf_step();
+#endif
     }
 #endif
 }
@@ -1101,7 +1110,8 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
             sum += ((zmask >> (i + 1)) & 1u) ? 0.0f : p_i;
         }
 
-        if (!(p_at_s > 0.0f && sum > 0.0f)) continue;
+        /* one back edge only: a `continue` here would let the lanes that skip drift apart from the rest for good */
+        if (p_at_s > 0.0f && sum > 0.0f) {
         float w = p_at_s / sum;
 
         V3 color;
@@ -1159,6 +1169,7 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
                 sink.weights[e] = w;
                 sink.shade[e] = shade;
             }
+        }
         }
     }
 
