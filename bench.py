@@ -226,6 +226,8 @@ def run_ours(args, cfg, rank, local_rank, world):
     dev.synchronize()
     t_up = time.perf_counter() - t_up
     accel_stats = dev.accel(sc.boxes, sc.triangles).stats()
+    l2_read_gbs = dev.read_bandwidth(32 << 20, 50) if rank == 0 else None     # 32 MB: L2 resident
+    hbm_read_gbs = dev.read_bandwidth(2 << 30, 5) if rank == 0 else None      # 2 GB: streams from HBM
     K, W = args.steps, args.warmup
 
     # ---- 1. instrumented run: work counters of exactly the passes that will be timed (same seeds => same work) ----
@@ -338,6 +340,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         roofline = {"bound": "hbm", "kernel": dom,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms,
+                    "l2_read_peak_gbs_measured_here": l2_read_gbs, "hbm_read_peak_gbs_measured_here": hbm_read_gbs,
+                    "frac_of_l2_read_peak": achieved / l2_read_gbs if l2_read_gbs else None,
                     "kernel_ms_per_pass": {k: v / max(timed_passes, 1) for k, v in kernel_ms.items()},
                     "algorithmic_gbs_per_kernel": {k: alg[k] / (kernel_ms[k] / max(timed_passes, 1) * 1e-3) / 1e9
                                                    for k in kernel_ms if kernel_ms[k] > 0},

@@ -78,6 +78,7 @@ SIGNATURES = {
     "clv_counters_enable": [_vp, _int],
     "clv_counters_read": [_vp, C.POINTER(C.c_uint64), _int],
     "clv_launch_count": [_vp, C.POINTER(C.c_uint64)],
+    "clv_measure_read_bandwidth": [_vp, _sz, _int, C.POINTER(C.c_double)],
     "clv_renderer_kernel_timing": [_vp, _int],
     "clv_renderer_kernel_times": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), _int],
     "clv_last_error": [],
@@ -325,6 +326,12 @@ class Device:
         if per_class:
             return classes
         return {n: classes["walk"][n] + classes["connect"][n] for n in names}
+
+    def read_bandwidth(self, nbytes, iters=20):
+        """Streaming-read GB/s of an nbytes scratch buffer (L2 peak when it fits L2, HBM read peak when far larger)."""
+        g = C.c_double()
+        _check(self.lib.clv_measure_read_bandwidth(self.ctx, int(nbytes), int(iters), C.byref(g)))
+        return float(g.value)
 
     @property
     def launch_count(self):

@@ -253,6 +253,9 @@ CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
  * returns the accumulated milliseconds and the number of passes they cover */
 CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
 CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_t *passes_out, int reset);
+/* streaming-read bandwidth (GB/s) of a scratch buffer of nbytes read iters times: the L2 read peak for nbytes well
+ * below the 126 MB L2 (the bound of the cache-resident configurations), the HBM read peak for nbytes >> L2 */
+CLV_API int clv_measure_read_bandwidth(clv_ctx *ctx, size_t nbytes, int iters, double *gbs_out);
 /* number of kernel launches issued on this context so far */
 CLV_API int clv_launch_count(clv_ctx *ctx, uint64_t *count);
 

@@ -363,3 +363,43 @@ def test_accel_cache_does_not_survive_its_buffers(dev, O):
         first = first or acc
         sc.release()
         assert not dev._accels
+
+
+def test_renderer_argument_errors(dev):
+    a = arrays("empty", 16, 16)
+    sc = scene.scene_from_arrays(a, dev)
+    acc = dev.accel(sc.boxes, sc.triangles)
+    seeds = seeds_for(256)
+    with pytest.raises(runtime.CliveError):  # sample id outside the frame
+        runtime.FusedRenderer(dev, acc, a, seeds, sample_ids=np.array([0, 999999], np.uint32))
+    import copy
+    dark = copy.copy(a)
+    dark.light_triangles = a.light_triangles[:0]
+    dark.light_surface_areas = a.light_surface_areas[:0]
+    dark.light_triangle_indices = a.light_triangle_indices[:0]
+    with pytest.raises(runtime.CliveError):  # the light-ray generator needs at least one emitter
+        runtime.FusedRenderer(dev, acc, dark, seeds)
+    r = Renderer(sc, seeds=seeds)
+    with pytest.raises(runtime.CliveError):  # wrong readback size
+        r._fr.read(runtime.BUF_SEEDS, np.uint32, 7)
+    r.release()
+    sc.release()
+
+
+def test_tiled_sample_order_gives_the_same_render(dev):
+    from clive2_b200 import sharding
+    w, h = 48, 40
+    a = arrays("bench-spheres", w, h)
+    seeds = seeds_for(w * h)
+    sc = scene.scene_from_arrays(a, dev)
+    plain = Renderer(sc, seeds=seeds)
+    tiled = Renderer(sc, seeds=seeds, sample_ids=sharding.tiled_order(w, h, 8, 4))
+    for _ in range(2):
+        plain.run_sample()
+        tiled.run_sample()
+    p, t = plain._accum(), tiled._accum()
+    assert np.array_equal(p[..., 4:8].view(np.uint32), t[..., 4:8].view(np.uint32))
+    np.testing.assert_allclose(t[..., 0:4], p[..., 0:4], rtol=5e-4, atol=1e-6)
+    for x in (plain, tiled):
+        x.release()
+    sc.release()

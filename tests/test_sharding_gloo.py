@@ -86,3 +86,13 @@ def test_two_rank_tile_sharded_render_equals_single(tmp_path):
     assert np.array_equal(reduced[:, 7], full[:, 7]) and (full[:, 7] == passes).all()
     assert np.array_equal(reduced[:, 4:7].view(np.uint32), full[:, 4:7].view(np.uint32))
     np.testing.assert_allclose(reduced[:, 0:4], full[:, 0:4], rtol=2e-4, atol=1e-6)
+
+
+def test_tiled_order_is_a_permutation_of_compact_blocks():
+    o = sharding.tiled_order(64, 32, 8, 4)
+    assert np.array_equal(np.sort(o), np.arange(64 * 32, dtype=np.uint32))
+    first = o[:32]
+    ys, xs = np.divmod(first.astype(int), 64)
+    assert xs.max() - xs.min() == 7 and ys.max() - ys.min() == 3  # one warp = one 8x4 pixel block
+    o2 = sharding.tiled_order(70, 33, 8, 4)  # ragged edges
+    assert np.array_equal(np.sort(o2), np.arange(70 * 33, dtype=np.uint32))
