@@ -1270,15 +1270,17 @@ extern "C" int clv_visibility(clv_ctx *c, const clv_accel *accel, const clv_Ray 
 /* streaming-read bandwidth of a buffer of `nbytes` read `iters` times back to back (first sweep untimed): with
  * nbytes well below the 126 MB L2 this is the L2 read peak the cache-resident configurations are bounded by, with
  * nbytes >> L2 the HBM read peak.  GB/s out. */
-__global__ void k_stream_read(const uint4 *src, size_t n_vec, unsigned long long *sink) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_stream_read(const uint4 *src, size_t n_vec, int sweeps, unsigned long long *sink) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     unsigned acc = 0;
-    for (; i + 3 * stride < n_vec; i += 4 * stride) {
-        uint4 a = __ldcg(src + i), b = __ldcg(src + i + stride), c = __ldcg(src + i + 2 * stride), d = __ldcg(src + i + 3 * stride);
-        acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    for (int sweep = 0; sweep < sweeps; sweep++) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n_vec; i += 4 * stride) {
+            uint4 a = __ldcg(src + i), b = __ldcg(src + i + stride), c = __ldcg(src + i + 2 * stride), d = __ldcg(src + i + 3 * stride);
+            acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+        }
+        for (; i < n_vec; i += stride) { uint4 a = __ldcg(src + i); acc += a.x ^ a.y ^ a.z ^ a.w; }
     }
-    for (; i < n_vec; i += stride) { uint4 a = __ldcg(src + i); acc += a.x ^ a.y ^ a.z ^ a.w; }
     if (acc == 0x9e3779b9u) atomicAdd(sink, 1ull); /* keeps the loads alive */
 }
 extern "C" int clv_measure_read_bandwidth(clv_ctx *c, size_t nbytes, int iters, double *gbs_out) {
@@ -1291,22 +1293,24 @@ extern "C" int clv_measure_read_bandwidth(clv_ctx *c, size_t nbytes, int iters, 
     CK(cudaMemsetAsync(buf, 1, nbytes, c->stream));
     CK(cudaMemsetAsync(sink, 0, 8, c->stream));
     const size_t n_vec = nbytes / 16;
-    const unsigned grid = (unsigned)c->sm_count * 16u;
+    const unsigned grid = (unsigned)c->sm_count * 8u;
+    /* enough sweeps per launch that launch latency does not matter (>= ~1 GB read per launch) */
+    const int sweeps = (int)std::max<size_t>(1, ((size_t)1 << 30) / nbytes);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    k_stream_read<<<grid, 256, 0, c->stream>>>(buf, n_vec, sink);
+    k_stream_read<<<grid, 256, 0, c->stream>>>(buf, n_vec, sweeps, sink);
     LAUNCHED(c);
     CK(cudaEventRecord(e0, c->stream));
     for (int k = 0; k < iters; k++) {
-        k_stream_read<<<grid, 256, 0, c->stream>>>(buf, n_vec, sink);
+        k_stream_read<<<grid, 256, 0, c->stream>>>(buf, n_vec, sweeps, sink);
         LAUNCHED(c);
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    *gbs_out = (double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9;
+    *gbs_out = (double)n_vec * 16.0 * iters * sweeps / (ms * 1e-3) / 1e9;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(buf);
