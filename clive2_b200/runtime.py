@@ -505,6 +505,9 @@ class FusedRenderer:
                          _host_ptr(keep[4]), len(keep[2]))
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32).reshape(self.n_pixels, 2)
         ids = None if sample_ids is None else np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        if ids is not None and len(np.unique(ids)) != len(ids):
+            # every pixel's accumulator is updated without atomics by the one sample that owns it
+            raise ValueError("sample_ids must not contain duplicates")
         self.n_local = self.n_pixels if ids is None else len(ids)
         h = C.c_void_p()
         _check(device.lib.clv_renderer_create(device.ctx, accel.handle, C.byref(desc), _host_ptr(seeds),
