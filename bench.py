@@ -322,13 +322,15 @@ def run_ours(args, cfg, rank, local_rank, world):
         # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
         cw, cc = ({k: v / K for k, v in counters[x].items()} for x in ("walk", "connect"))
+        NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
+        NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
         alg = {
-            # node (64 B) + triangle (48 B) records fetched + the hit triangle's shading record (80 B of the reference
+            # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record (80 B of the reference
             # Triangle) + path vertices written (128 B) + seeds RMW (16 B) + accumulator RMW (64 B)
-            "k_fused_walks": cw["node_fetches"] * 64 + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * 128
+            "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * 128
                              + batch * (16 + 64),
             # node + triangle records fetched + per task: 4 B task word, two vertex origins and triangle ids (2 x 20 B)
-            "k_connect_rays": cc["node_fetches"] * 64 + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 40),
+            "k_connect_rays": cc["node_fetches"] * NBR + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 40),
             # path vertices staged (128 B each), visibility bits + projection record (8 + 48 B), aggregator written (80 B)
             "k_connect_finish": cc["vertices"] * 128 + batch * (8 + 48 + 80),
             # vertex origins/normals/materials of both subpaths (~48 B per vertex), task words + projection record written
@@ -367,7 +369,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                        "l2": f"per-pass working set {2 * 1040 * batch / 1e6:.0f} MB of path records "
                              f"(> 126 MB L2) is rewritten every step; no explicit flush" if 2 * 1040 * batch > 126e6
                              else "working set below L2 size; steps run back to back without flush",
-                       "accel_bytes": accel_stats["node_bytes"] + accel_stats["triangle_bytes"],
+                       "accel_bytes": accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"],
                        "scene_build_s": t_scene, "scene_upload_s": t_up},
             "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,
             "mrays_traced_per_s": tot["rays_traced"] * world / (elapsed_ms * 1e-3) / 1e6,

@@ -204,11 +204,11 @@ extern "C" int clv_host_free(void *h_ptr) {
  * ------------------------------------------------------------------------------------------------------------- */
 struct clv_accel {
     clv_ctx *ctx;
-    V4 *d_nodes, *d_tris;
+    V4 *d_nodes, *d_wnodes, *d_tris;
     Triangle *d_ref_triangles;
     int32_t *d_camera_tris;
     AccelView view;
-    uint64_t n_nodes, n_tris;
+    uint64_t n_nodes, n_wide, n_tris;
 };
 
 extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_boxes, const clv_Triangle *h_tris_,
@@ -240,6 +240,9 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     size_t nb_ref = (size_t)n_tris * sizeof(Triangle);
     size_t nb_cam = std::max<size_t>(camera_tris.size(), 1) * sizeof(int32_t);
     CK(cudaMalloc(&a->d_nodes, nb_nodes));
+    size_t nb_wide = std::max<size_t>(H.wide.size(), 1) * sizeof(WideRec);
+    CK(cudaMalloc(&a->d_wnodes, nb_wide));
+    if (!H.wide.empty()) CK(cudaMemcpyAsync(a->d_wnodes, H.wide.data(), H.wide.size() * sizeof(WideRec), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMalloc(&a->d_tris, nb_tris));
     CK(cudaMalloc(&a->d_ref_triangles, nb_ref));
     CK(cudaMalloc(&a->d_camera_tris, nb_cam));
@@ -249,6 +252,9 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     if (!camera_tris.empty()) CK(cudaMemcpyAsync(a->d_camera_tris, camera_tris.data(), camera_tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     a->view.nodes = a->d_nodes;
+    a->view.wnodes = a->d_wnodes;
+    a->view.wroot_ref = H.wide_root_ref;
+    a->n_wide = H.wide.size();
     a->view.tris = a->d_tris;
     a->view.ref_triangles = a->d_ref_triangles;
     a->view.root_min = boxes[0].min;
@@ -265,6 +271,7 @@ extern "C" int clv_accel_destroy(clv_accel *a) {
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
     cudaFree(a->d_nodes);
+    cudaFree(a->d_wnodes);
     cudaFree(a->d_tris);
     cudaFree(a->d_ref_triangles);
     cudaFree(a->d_camera_tris);
@@ -274,10 +281,14 @@ extern "C" int clv_accel_destroy(clv_accel *a) {
 
 extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[4]) {
     REQUIRE(a && out, "null");
-    out[0] = a->n_nodes * sizeof(NodeRec);
+    out[0] = a->n_nodes * sizeof(NodeRec); /* binary nodes */
     out[1] = a->n_tris * 3 * sizeof(V4);
     out[2] = a->n_nodes;
     out[3] = a->n_tris;
+    out[4] = a->n_wide * sizeof(WideRec);  /* 4-wide nodes */
+    out[5] = a->n_wide;
+    out[6] = CLV_WIDE_CLOSEST;             /* which of the two each search kind traverses in the ORDERED flavour */
+    out[7] = CLV_WIDE_OCCLUSION;
     return CLV_OK;
 }
 

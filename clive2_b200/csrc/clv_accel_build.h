@@ -16,8 +16,18 @@ namespace clv {
 struct NodeRec { V4 a, b, c, d; };
 static_assert(sizeof(NodeRec) == 64, "NodeRec");
 
+/* 4-wide node of the ORDERED flavour: 8 x V4 = [minx x4][miny x4][minz x4][maxx x4][maxy x4][maxz x4][refs x4][-],
+ * empty slots have ref -1.  Obtained by collapsing the binary nodes (a slot that is an inner node is replaced by its two
+ * children, largest box first, until four slots are used): every box kept is one of the reference's boxes, the boxes
+ * skipped contain the ones kept, so a ray that passes a kept box also passes the skipped one (the slab test is monotone
+ * in the box bounds) and the set of triangles a ray can reach is unchanged. */
+struct WideRec { V4 q[8]; };
+static_assert(sizeof(WideRec) == 128, "WideRec");
+
 struct HostAccel {
     std::vector<NodeRec> nodes;       /* inner nodes; reference inner boxes first (in reference order), then synthetic */
+    std::vector<WideRec> wide;        /* collapsed 4-wide nodes */
+    int32_t wide_root_ref;
     std::vector<V4> tris;             /* 3 per triangle, reference order */
     std::vector<int32_t> camera_tris; /* indices of is_camera triangles */
     int32_t root_ref;
@@ -48,6 +58,56 @@ inline int32_t leaf_ref(std::vector<NodeRec> &nodes, const Box &bx, int32_t firs
     int32_t left = leaf_ref(nodes, bx, mid, last);
     nodes[me] = pack_node(bx, bx, left, right);
     return (int32_t)me;
+}
+
+struct WideSlot { float mn[3], mx[3]; int32_t ref; };
+inline void slots_of(const NodeRec &n, WideSlot out[2]) {
+    out[0].mn[0] = n.a.x; out[0].mn[1] = n.a.y; out[0].mn[2] = n.a.z; out[0].mx[0] = n.a.w; out[0].mx[1] = n.b.x; out[0].mx[2] = n.b.y;
+    out[1].mn[0] = n.b.z; out[1].mn[1] = n.b.w; out[1].mn[2] = n.c.x; out[1].mx[0] = n.c.y; out[1].mx[1] = n.c.z; out[1].mx[2] = n.c.w;
+    memcpy(&out[0].ref, &n.d.x, 4);
+    memcpy(&out[1].ref, &n.d.y, 4);
+}
+inline int32_t wide_of(HostAccel &H, int32_t bin_ref) {
+    if (bin_ref < 0) return bin_ref; /* leaf refs are shared */
+    WideSlot slots[4];
+    int n = 2;
+    slots_of(H.nodes[bin_ref], slots);
+    while (n < 4) {
+        int pick = -1;
+        float best = -1.0f;
+        for (int k = 0; k < n; k++) {
+            if (slots[k].ref < 0) continue;
+            float sx = slots[k].mx[0] - slots[k].mn[0], sy = slots[k].mx[1] - slots[k].mn[1], sz = slots[k].mx[2] - slots[k].mn[2];
+            float area = sx * sy + sy * sz + sz * sx;
+            if (!(area <= best)) { best = area; pick = k; }
+        }
+        if (pick < 0) break;
+        WideSlot kids[2];
+        slots_of(H.nodes[slots[pick].ref], kids);
+        slots[pick] = kids[0];
+        slots[n++] = kids[1];
+    }
+    size_t me = H.wide.size();
+    H.wide.push_back(WideRec());
+    int32_t refs[4] = {-1, -1, -1, -1};
+    for (int k = 0; k < n; k++) refs[k] = wide_of(H, slots[k].ref);
+    WideRec w;
+    for (int c = 0; c < 3; c++) {
+        float mn[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+        for (int k = 0; k < n; k++) { mn[k] = slots[k].mn[c]; mx[k] = slots[k].mx[c]; }
+        w.q[c] = v4(mn[0], mn[1], mn[2], mn[3]);
+        w.q[3 + c] = v4(mx[0], mx[1], mx[2], mx[3]);
+    }
+    float rf[4];
+    memcpy(rf, refs, 16);
+    w.q[6] = v4(rf[0], rf[1], rf[2], rf[3]);
+    w.q[7] = v4(0.0f, 0.0f, 0.0f, 0.0f);
+    H.wide[me] = w;
+    return (int32_t)me;
+}
+inline void build_wide(HostAccel &H) {
+    H.wide.clear();
+    H.wide_root_ref = wide_of(H, H.root_ref);
 }
 
 /* returns NULL on success, else a description of what is wrong with the input */
@@ -101,6 +161,7 @@ inline const char *build_host_accel(const Box *boxes, int32_t n_boxes, const Tri
             else for (int32_t i = bx.left; i < bx.right; i++) rank[i] = next++;
         }
     }
+    build_wide(H);
     H.tris.resize((size_t)n_tris * 3);
     H.camera_tris.clear();
     for (int32_t i = 0; i < n_tris; i++) {

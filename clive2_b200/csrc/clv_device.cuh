@@ -44,7 +44,15 @@
 #define CLV_DELTA 0.0001f     /* trace.metal:5 */
 #define CLV_INF (clv_bits_to_float(0x7f800000u))
 #define CLV_MAX_BOUNCES 6     /* trace.metal:407 */
-#define CLV_STACK 64          /* trace.metal:145 */
+#define CLV_STACK 96          /* trace.metal:145 has 64; the 4-wide flavour keeps up to 3 siblings per level */
+/* which node layout the ORDERED flavour traverses: the 4-wide collapse of the BVH (1) or the binary nodes (0),
+ * separately for closest-hit searches (random walks) and occlusion queries (connection rays) */
+#ifndef CLV_WIDE_CLOSEST
+#define CLV_WIDE_CLOSEST 0
+#endif
+#ifndef CLV_WIDE_OCCLUSION
+#define CLV_WIDE_OCCLUSION 1
+#endif
 #ifndef CLV_WALK_INNER_BURST
 #define CLV_WALK_INNER_BURST 0 /* closest_hit, while-while form: 0 = walk down to the leaf, n > 0 = at most n node steps per round */
 #endif
@@ -168,6 +176,8 @@ CLV_HD float xorshift_random(uint32_t &seed) {
  */
 struct AccelView {
     const V4 *nodes;
+    const V4 *wnodes;  /* 4-wide nodes of the ORDERED flavour (clv_accel_build.h WideRec), 8 x V4 each */
+    int32_t wroot_ref;
     const V4 *tris;
     const Triangle *ref_triangles; /* shading data (normals, material, flags), reference records */
     V4 root_min, root_max;
@@ -185,6 +195,30 @@ CLV_HD void slab_test(V3 o, V3 inv, V3 bmin, V3 bmax, bool &hit, float &t_entry)
     float tmax_final = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, CLV_INF));
     hit = tmin_final <= tmax_final;
     t_entry = tmin_final;
+}
+
+/* one 4-wide node: the reference's slab test on each of its up to four boxes.  t[k] = entry distance of slot k if the
+ * ray passes it with t_entry <= t_limit, +INF otherwise (also for empty slots); ref[k] = the slot's child ref. */
+CLV_HD void wide_test(const V4 *n, V3 o, V3 inv, float t_limit, float t[4], int ref[4]) {
+    V4 mnx = ld4(n), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5), rf = ld4(n + 6);
+    const float bmnx[4] = {mnx.x, mnx.y, mnx.z, mnx.w}, bmny[4] = {mny.x, mny.y, mny.z, mny.w}, bmnz[4] = {mnz.x, mnz.y, mnz.z, mnz.w};
+    const float bmxx[4] = {mxx.x, mxx.y, mxx.z, mxx.w}, bmxy[4] = {mxy.x, mxy.y, mxy.z, mxy.w}, bmxz[4] = {mxz.x, mxz.y, mxz.z, mxz.w};
+    const float rfk[4] = {rf.x, rf.y, rf.z, rf.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        bool hit;
+        float te;
+        slab_test(o, inv, v3(bmnx[k], bmny[k], bmnz[k]), v3(bmxx[k], bmxy[k], bmxz[k]), hit, te);
+        ref[k] = f2i(rfk[k]);
+        t[k] = (ref[k] != -1 && hit && te <= t_limit) ? te : CLV_INF;
+    }
+}
+/* order the four slots by descending t (empty/missed slots, t = +INF, first; the nearest one last) */
+CLV_HD void wide_sort(float t[4], int ref[4]) {
+#define CLV_CSWAP(a, b) { bool sw = t[a] < t[b]; float tt = sw ? t[b] : t[a]; int rr = sw ? ref[b] : ref[a]; \
+                          t[b] = sw ? t[a] : t[b]; ref[b] = sw ? ref[a] : ref[b]; t[a] = tt; ref[a] = rr; }
+    CLV_CSWAP(0, 1) CLV_CSWAP(2, 3) CLV_CSWAP(0, 2) CLV_CSWAP(1, 3) CLV_CSWAP(1, 2)
+#undef CLV_CSWAP
 }
 
 /* Moeller-Trumbore exactly as trace.metal:117-142 with edge1/edge2 already formed */
@@ -231,11 +265,31 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
     float te;
     slab_test(o, inv, xyz(A.root_min), xyz(A.root_max), hit, te);
     if (!(hit && te < best_t)) return;
-    int cur = A.root_ref;
+    const bool wide = (MODE == TRAVERSE_ORDERED) && CLV_WIDE_CLOSEST; /* ORDERED walks the 4-wide collapse of the tree */
+    int cur = wide ? A.wroot_ref : A.root_ref;
     bool have = true; /* `cur` holds a node that still has to be processed */
 
     /* one inner node: test both child boxes, continue with the nearer surviving child, keep the other */
     auto inner_step = [&]() {
+        if (wide) {
+            /* up to four children at once: continue with the nearest that survives, keep the others farthest first */
+            float tk[4];
+            int rk[4];
+            wide_test(A.wnodes + 8 * (size_t)cur, o, inv, best_t, tk, rk);
+            cnt.node();
+            wide_sort(tk, rk);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (tk[k] < CLV_INF && sp < CLV_STACK) { st_ref[sp] = rk[k]; st_t[sp] = tk[k]; sp++; }
+            have = tk[3] < CLV_INF;
+            cur = rk[3];
+            while (!have && sp > 0) {
+                sp--;
+                float t = st_t[sp];
+                if (t <= best_t) { cur = st_ref[sp]; have = true; }
+            }
+            return;
+        }
         const V4 *n = A.nodes + 4 * (size_t)cur;
         V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
         cnt.node();
@@ -355,7 +409,7 @@ CLV_HD int occ_begin(const AccelView &A, OccRay &r, Cnt<COUNT> &cnt) {
     slab_test(r.o, r.inv, xyz(A.root_min), xyz(A.root_max), hit, te);
     /* a ray that misses the scene box finds nothing in the reference either: its target is then not "the closest hit" */
     if (!hit) return OCC_BLOCKED;
-    r.cur = A.root_ref;
+    r.cur = CLV_WIDE_OCCLUSION ? A.wroot_ref : A.root_ref;
     r.sp = 0;
     return OCC_RUNNING;
 }
@@ -365,6 +419,27 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
     int cur = r.cur, sp = r.sp;
     int status = OCC_RUNNING;
     while (status == OCC_RUNNING && cur >= 0) {
+#if CLV_WIDE_OCCLUSION
+        {
+            float tk[4];
+            int rk[4];
+            wide_test(A.wnodes + 8 * (size_t)cur, r.o, r.inv, r.t_bound, tk, rk);
+            cnt.node();
+            /* any order finds an occluder; take the nearest surviving child, keep the rest */
+            int near = 0;
+#pragma unroll
+            for (int k = 1; k < 4; k++)
+                if (tk[k] < tk[near]) near = k;
+            const bool any = tk[near] < CLV_INF;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k != near && tk[k] < CLV_INF && sp < CLV_STACK) stack[sp++] = rk[k];
+            if (any) cur = rk[near];
+            else if (sp > 0) cur = stack[--sp];
+            else status = OCC_CLEAR;
+            continue;
+        }
+#endif
         const V4 *n = A.nodes + 4 * (size_t)cur;
         V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
         cnt.node();
@@ -405,6 +480,24 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
 /* the two halves of a round as separate steps, for the majority-vote schedule of k_connect_rays: one inner node ... */
 template <bool COUNT>
 CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt) {
+#if CLV_WIDE_OCCLUSION
+    {
+        float tk[4];
+        int rk[4];
+        wide_test(A.wnodes + 8 * (size_t)r.cur, r.o, r.inv, r.t_bound, tk, rk);
+        cnt.node();
+        int near = 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++)
+            if (tk[k] < tk[near]) near = k;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k != near && tk[k] < CLV_INF && r.sp < CLV_STACK) stack[r.sp++] = rk[k];
+        if (tk[near] < CLV_INF) { r.cur = rk[near]; return OCC_RUNNING; }
+        if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
+        return OCC_CLEAR;
+    }
+#endif
     const V4 *n = A.nodes + 4 * (size_t)r.cur;
     V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
     cnt.node();

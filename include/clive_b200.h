@@ -121,8 +121,10 @@ typedef struct clv_accel clv_accel;
 CLV_API int clv_accel_create(clv_ctx *ctx, const clv_Box *h_boxes, int32_t n_boxes, const clv_Triangle *h_triangles,
                              int32_t n_triangles, clv_accel **out);
 CLV_API int clv_accel_destroy(clv_accel *accel);
-/* bytes of the compact layout: [0] node records, [1] triangle records, [2] node count, [3] triangle count */
-CLV_API int clv_accel_stats(clv_accel *accel, uint64_t out[4]);
+/* the compact layout: [0] bytes of binary node records, [1] bytes of triangle records, [2] binary node count,
+ * [3] triangle count, [4] bytes of 4-wide node records, [5] 4-wide node count, [6]/[7] 1 if closest-hit / occlusion
+ * searches of the ORDERED flavour traverse the 4-wide nodes */
+CLV_API int clv_accel_stats(clv_accel *accel, uint64_t out[8]);
 
 /* ---- 4. the eight kernels (trace.metal entry points), reference argument order, device pointers ----------------- */
 /* generate_light_rays, trace.metal:1070-1124 / renderer.py:114-125 */

@@ -26,6 +26,8 @@ EXPORT EmuAccel *emu_accel_create(const Box *boxes, int32_t n_boxes, const Trian
     if (build_host_accel(boxes, n_boxes, tris, n_tris, a->h)) { delete a; return nullptr; }
     a->ref.assign(tris, tris + n_tris);
     a->view.nodes = &a->h.nodes.data()->a;
+    a->view.wnodes = a->h.wide.empty() ? nullptr : a->h.wide.data()->q;
+    a->view.wroot_ref = a->h.wide_root_ref;
     a->view.tris = a->h.tris.data();
     a->view.ref_triangles = a->ref.data();
     a->view.root_min = boxes[0].min;
