@@ -403,3 +403,33 @@ def test_tiled_sample_order_gives_the_same_render(dev):
     for x in (plain, tiled):
         x.release()
     sc.release()
+
+
+def test_ragged_frame_size_partial_warps(dev):
+    """37 x 25 = 925 samples: neither a multiple of the warp nor of the block size; also a shard of 77 ids."""
+    w, h = 37, 25
+    a = arrays("bench-spheres", w, h)
+    b = w * h
+    seeds = seeds_for(b)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(2):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_paths_equal(ref.buffer("light_paths", T.Path), r._fr.read(runtime.BUF_LIGHT_PATHS, T.Path, b), "light paths")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=5e-5, atol=1e-6)
+    ids = np.arange(5, b, 12, dtype=np.uint32)
+    part = Renderer(sc, seeds=seeds, sample_ids=ids)
+    part.run_sample()
+    got = part._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * len(ids)).reshape(-1, 2)
+    one = OracleRenderer(a, seeds, shared_math=True)
+    one.run_sample()
+    assert_bits_equal(one.buffer("rand", np.uint32).reshape(b, 2)[ids], got, "shard RNG")
+    assert (part.summed_sample_counts.reshape(-1)[ids] == 1).all() and part.summed_sample_counts.sum() == len(ids)
+    for x in (r, part):
+        x.release()
+    sc.release()
