@@ -828,17 +828,16 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         nr.normal = pad0(n);
 
         float fresnel = degreve_fresnel(wi, m, ni, no);
-        if (mat_type == 0) {
-            diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
-        } else if (mat_type == 1) {
-            if (rand_x_b <= fresnel) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-            else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-        } else if (mat_type == 2) {
-            if (rand_x_b <= fresnel) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-            else diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
-        } else {
-            reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-        }
+        /* material dispatch of :474-487 resolved to one of three bounce kinds first, so that each bounce function is
+         * instantiated once (the walk kernel is larger than the instruction cache) */
+        int kind; /* 0 diffuse, 1 reflect, 2 transmit */
+        if (mat_type == 0) kind = 0;
+        else if (mat_type == 1) kind = (rand_x_b <= fresnel) ? 1 : 2;
+        else if (mat_type == 2) kind = (rand_x_b <= fresnel) ? 1 : 0;
+        else kind = 1;
+        if (kind == 0) diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
+        else if (kind == 1) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+        else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
 
         float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
         if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);

@@ -24,8 +24,16 @@
 
 #if defined(__CUDACC__)
 #define CLV_MATH_FN __host__ __device__ __forceinline__
+/* the public entry points can be kept out of line on the device (-DCLV_MATH_NOINLINE): the walk kernel evaluates ~10
+ * of them per bounce and is larger than the instruction cache */
+#if defined(CLV_MATH_NOINLINE)
+#define CLV_MATH_API __host__ __device__ __noinline__
+#else
+#define CLV_MATH_API __host__ __device__ __forceinline__
+#endif
 #else
 #define CLV_MATH_FN static inline
+#define CLV_MATH_API static inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -85,14 +93,14 @@ CLV_MATH_FN float clv_cos_poly(float r) {
     return CLV_ADD(CLV_SUB(1.0f, CLV_MUL(0.5f, z)), CLV_MUL(CLV_MUL(z, z), p));
 }
 
-CLV_MATH_FN float clv_sinf(float x) {
+CLV_MATH_API float clv_sinf(float x) {
     int q;
     float r = clv_reduce_pio2(x, &q);
     float v = (q & 1) ? clv_cos_poly(r) : clv_sin_poly(r);
     return (q & 2) ? -v : v;
 }
 
-CLV_MATH_FN float clv_cosf(float x) {
+CLV_MATH_API float clv_cosf(float x) {
     int q;
     float r = clv_reduce_pio2(x, &q);
     float v = (q & 1) ? clv_sin_poly(r) : clv_cos_poly(r);
@@ -109,7 +117,7 @@ CLV_MATH_FN float clv_asin_poly(float x) { /* |x| <= 0.5 */
     return CLV_ADD(CLV_MUL(CLV_MUL(p, z), x), x);
 }
 
-CLV_MATH_FN float clv_acosf(float x) {
+CLV_MATH_API float clv_acosf(float x) {
     const float pi = 3.14159265358979323846f;
     const float pio2 = 1.57079632679489661923f;
     float a = fabsf(x);
@@ -123,7 +131,7 @@ CLV_MATH_FN float clv_acosf(float x) {
 }
 
 /* ---- atan ------------------------------------------------------------------------------------------------ */
-CLV_MATH_FN float clv_atanf(float x) {
+CLV_MATH_API float clv_atanf(float x) {
     const float pio2 = 1.57079632679489661923f;
     const float pio4 = 0.78539816339744830962f;
     float a = fabsf(x);
@@ -147,7 +155,7 @@ CLV_MATH_FN float clv_atanf(float x) {
 }
 
 /* ---- exp ------------------------------------------------------------------------------------------------- */
-CLV_MATH_FN float clv_expf(float x) {
+CLV_MATH_API float clv_expf(float x) {
     if (!(x == x)) return x;
     if (x > 88.7f) return clv_bits_to_float(0x7f800000u);
     if (x < -87.3f) return 0.0f;
