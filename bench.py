@@ -216,9 +216,14 @@ def run_ours(args, cfg, rank, local_rank, world):
     dev = runtime.Device(local_rank)
     t_up = time.perf_counter()
     sc = scene.scene_from_arrays(arrays, dev)
-    seeds = seeds_for(batch, rank)
+    tile_sharded = args.shard == "tile" and world > 1
+    seeds = seeds_for(batch, 0 if tile_sharded else rank)
     ids = None
-    if args.tile:
+    if tile_sharded:
+        # strong scaling of ONE frame: this rank traces its 16x16 tiles with the global RNG rows (same streams as 1 GPU)
+        from clive2_b200 import sharding
+        ids = sharding.tile_ids(width, height, rank, world, 16)
+    elif args.tile:
         from clive2_b200 import sharding
         tw, th = (int(x) for x in args.tile.lower().split("x"))
         ids = sharding.tiled_order(width, height, tw, th)
@@ -313,7 +318,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        samples = batch * K * world
+        samples = batch * K * (1 if tile_sharded else world)
         value = samples / (elapsed_ms * 1e-3) / 1e6
         e2e_value = samples / e2e_s / 1e6
         tot = {k: counters["walk"][k] + counters["connect"][k] for k in counters["walk"]}
@@ -361,11 +366,13 @@ def run_ours(args, cfg, rank, local_rank, world):
                 pass
         line = {
             "metric": "bdpt_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong" if tile_sharded else "weak",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "width": width, "height": height, "samples_per_step_per_gpu": batch,
                        "triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)),
-                       "parallelism": f"pass-sharded x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"tile-sharded x{world} (16x16 tiles round-robin, one NCCL reduce)" if tile_sharded else
+                                       f"pass-sharded x{world} (one NCCL reduce)") if world > 1 else "single GPU",
                        "l2": f"per-pass working set {2 * 1040 * batch / 1e6:.0f} MB of path records "
                              f"(> 126 MB L2) is rewritten every step; no explicit flush" if 2 * 1040 * batch > 126e6
                              else "working set below L2 size; steps run back to back without flush",
@@ -373,7 +380,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                        "scene_build_s": t_scene, "scene_upload_s": t_up},
             "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,
             "mrays_traced_per_s": tot["rays_traced"] * world / (elapsed_ms * 1e-3) / 1e6,
-            "rays_per_sample": rays_ref_per_pass / batch,
+            "rays_per_sample": rays_ref_per_pass / (len(ids) if ids is not None else batch),
             "rays_definition": "mrays_per_s counts traverse_bvh invocations the reference makes for the same paths "
                                "(SURVEY.md 8d); mrays_traced_per_s counts traversals this implementation starts "
                                "(connection rays whose target test fails first are skipped)",
@@ -411,6 +418,9 @@ def main():
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", choices=("pass", "tile"), default="pass",
+                    help="N > 1: 'pass' = every rank renders full-frame passes from its own seeds (weak scaling, default); "
+                         "'tile' = the ranks split every pass of ONE frame by 16x16 tiles (strong scaling)")
     ap.add_argument("--tile", default=os.environ.get("CLV_BENCH_TILE", ""),
                     help="WxH: trace samples in tiles of WxH pixels per warp-sized group (e.g. 8x4); default row-major")
     args = ap.parse_args()

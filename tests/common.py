@@ -117,3 +117,26 @@ def random_rays(n, lo, hi, seed=1):
         rays["inv_direction"][:, :3] = np.float32(1.0) / d
     rays["triangle"] = -1
     return rays
+
+
+@functools.lru_cache(maxsize=None)
+def zoo_arrays(width, height):
+    """Cornell box + two small spheres with a material table that exercises every branch of the material dispatch
+    (trace.metal:474-487): walls mirror (type 3), glossy coated (type 2, alpha 0.3), rough/smooth dielectrics (type 1,
+    alpha 0 and 0.1, different ior), a coloured emitter and a rough diffuse with alpha > 0 (GGX normal != n)."""
+    import numpy as _np
+    from clive2_b200 import meshgen
+    from clive2_b200.load import make_materials
+    mats = make_materials({
+        0: dict(type=1, alpha=0.0, ior=1.33),             # smooth dielectric sphere
+        5: dict(type=1, alpha=0.1, ior=1.8),              # rough dielectric sphere
+        1: dict(type=3, alpha=0.0),                       # left wall: mirror
+        2: dict(type=2, alpha=0.3),                       # right wall: coated
+        3: dict(type=0, alpha=0.25),                      # front wall: diffuse, but its microfacet normal wanders
+        6: dict(emission=[0.9, 1.0, 0.8]),                # tinted light
+    })
+    mesh = meshgen.icosphere(2, 1.2)
+    specs = [{"mesh": mesh, "offset": _np.array([1.5, -0.5, 1.0]), "material": 5},
+             {"mesh": mesh, "offset": _np.array([-1.8, 0.2, -1.0]), "material": 0}]
+    return scene.build_scene_arrays(width, height, _np.array([0, 1.5, 6]), _np.array([0, 0, -1]), specs, mats,
+                                    bvh_builder="numpy")

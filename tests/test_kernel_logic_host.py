@@ -6,7 +6,7 @@ import pytest
 from clive2_b200 import struct_types as T
 from oracle.oracle import Oracle, OracleRenderer
 from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, oracle_stages, random_rays,
-                          rel_rmse, seeds_for)
+                          rel_rmse, seeds_for, zoo_arrays)
 from tests.hostemu import MODE_ORDERED, MODE_REFERENCE, HostEmu
 
 SCENES = [("empty", 40, 40), ("bench-spheres", 48, 32)]
@@ -217,3 +217,29 @@ def test_sharded_fused_pass_sums_to_full_render(E):
     np.testing.assert_allclose(total[:, 0:4], full[:, 0:4], rtol=2e-4, atol=1e-6)
     for r in (0, 1):
         assert_bits_equal(parts[r][1], s_full[stripe == r], "shard RNG streams")
+
+
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_ORDERED])
+def test_every_material_branch_bit_exact(O, E, mode):
+    """Mirror, coated, smooth and rough dielectrics, alpha > 0 on a diffuse surface: all stage buffers against the oracle."""
+    w, h = 40, 30
+    a = zoo_arrays(w, h)
+    seeds = seeds_for(w * h, seed=77)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+    finally:
+        E.accel_destroy(acc)
+    used = np.unique(np.concatenate([R.camera_paths["rays"]["material"][R.camera_paths["length"] > 1, 1],
+                                     R.light_paths["rays"]["material"][R.light_paths["length"] > 1, 1]]))
+    assert {0, 1, 2, 3, 5}.issubset(set(used.tolist())), used  # the walk really visited every material kind
+    assert_bits_equal(R.rand, S.rand, "RNG state")
+    assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+    assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+    for name in ("pix", "pth", "ry", "w", "sh"):
+        assert_bits_equal(getattr(R, name), getattr(S, name), "light entries " + name)
+    assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+    assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    assert_bits_equal(R.sample_weights, S.sample_weights, "sample weights")
+    assert (R.camera_paths["length"] < 6).any()  # glass/mirror paths also terminate early
