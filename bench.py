@@ -329,16 +329,17 @@ def run_ours(args, cfg, rank, local_rank, world):
         cw, cc = ({k: v / K for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
+        VB = 64  # bytes of one stored path vertex in the renderer's SoA records (four 16-byte parts)
         alg = {
-            # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record (80 B of the reference
-            # Triangle) + path vertices written (128 B) + seeds RMW (16 B) + accumulator RMW (64 B)
-            "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * 128
+            # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record
+            # (80 B of the reference Triangle) + path vertices written (64 B) + seeds RMW (16 B) + accumulator RMW (64 B)
+            "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * VB
                              + batch * (16 + 64),
-            # node + triangle records fetched + per task: 4 B task word, two vertex origins and triangle ids (2 x 20 B)
-            "k_connect_rays": cc["node_fetches"] * NBR + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 40),
-            # path vertices staged (128 B each), visibility bits + projection record (8 + 48 B), aggregator written (80 B)
-            "k_connect_finish": cc["vertices"] * 128 + batch * (8 + 48 + 80),
-            # vertex origins/normals/materials of both subpaths (~48 B per vertex), task words + projection record written
+            # node + triangle records fetched + per task: 4 B task word, origin + triangle parts of two vertices (4 x 16 B)
+            "k_connect_rays": cc["node_fetches"] * NBR + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 64),
+            # path vertices staged (64 B each), visibility bits + projection record (8 + 48 B), aggregator written (80 B)
+            "k_connect_finish": cc["vertices"] * VB + batch * (8 + 48 + 80),
+            # origin / normal / material parts of every vertex (48 B), task words + projection record written
             "k_connect_enumerate": cc["vertices"] * 48 + cc["rays_ref"] * 4 + batch * (48 + 8),
             # 9 aggregators read (80 B), light image RMW (32 B), accumulator RMW (64 B) per pixel
             "k_fused_finalize": batch * (9 * 80 + 32 + 64),
@@ -373,9 +374,10 @@ def run_ours(args, cfg, rank, local_rank, world):
                        "triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)),
                        "parallelism": (f"tile-sharded x{world} (16x16 tiles round-robin, one NCCL reduce)" if tile_sharded else
                                        f"pass-sharded x{world} (one NCCL reduce)") if world > 1 else "single GPU",
-                       "l2": f"per-pass working set {2 * 1040 * batch / 1e6:.0f} MB of path records "
-                             f"(> 126 MB L2) is rewritten every step; no explicit flush" if 2 * 1040 * batch > 126e6
-                             else "working set below L2 size; steps run back to back without flush",
+                       "l2": f"per-pass working set {(768 + 200 + 128) * batch / 1e6:.0f} MB (path vertex records, connection "
+                             f"scratch, aggregators + accumulators) is rewritten every step (> 126 MB L2); no explicit flush"
+                             if (768 + 200 + 128) * batch > 126e6
+                             else "per-pass working set below the 126 MB L2; steps run back to back without flush",
                        "accel_bytes": accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"],
                        "scene_build_s": t_scene, "scene_upload_s": t_up},
             "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,

@@ -350,7 +350,9 @@ k_generate_paths(uint32_t n, const Ray *rays, AccelView A, const Material *mater
         uint2 sd = reinterpret_cast<uint2 *>(random_buffer)[id];
         uint32_t seed0 = sd.x, seed1 = sd.y;
         V4 uni;
-        random_walk<MODE, COUNT>(rays[id], A, materials, seed0, seed1, output_paths + id, &uni, cnt);
+        AosSink sink;
+        sink.path = output_paths + id;
+        random_walk<MODE, COUNT>(rays[id], A, materials, seed0, seed1, sink, &uni, cnt);
         out[id] = uni;
         if (float_debug) float_debug[id] = v4(100.0f, 100.0f, 100.0f, 100.0f);
         reinterpret_cast<uint2 *>(random_buffer)[id] = make_uint2(seed0, seed1);
@@ -384,9 +386,26 @@ struct ConnectScratch { /* device buffers shared by the three kernels */
     float *sensor;        /* [n][CLV_SENSOR_WORDS] */
 };
 
-template <int MODE, bool COUNT>
+/* this sample's stored vertices in whichever layout the launch uses */
+template <bool SOA> struct PathViewOf;
+template <> struct PathViewOf<false> {
+    typedef AosPaths type;
+    static __device__ __forceinline__ AosPaths make(const PathStore &st, uint32_t slot, uint32_t) {
+        return aos_paths(st.camera_paths, st.light_paths, slot);
+    }
+};
+template <> struct PathViewOf<true> {
+    typedef SoaPaths type;
+    static __device__ __forceinline__ SoaPaths make(const PathStore &st, uint32_t slot, uint32_t pixel) {
+        SoaPaths P;
+        P.v = st.soa; P.len = st.soa_len; P.n = st.n; P.slot = slot; P.pixel0 = (int32_t)pixel;
+        return P;
+    }
+};
+
+template <int MODE, bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK)
-k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_paths, AccelView A, const Material *materials,
+k_connect_enumerate(uint32_t n, PathStore store, AccelView A, const Material *materials,
                     const Camera *camera, ConnectScratch cs, Counters *counters) {
     __shared__ float cam_scratch[CLV_ENUM_SCRATCH * CLV_BLOCK];
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,7 +420,7 @@ k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_path
         TArr Cam;
         Cam.base = cam_scratch + threadIdx.x;
         Cam.stride = CLV_BLOCK;
-        cand = connect_enumerate<MODE, COUNT>(id, camera_paths, light_paths, A, materials, c, Sens, Cam, cnt);
+        cand = connect_enumerate<MODE, COUNT>(PathViewOf<SOA>::make(store, id, 0u), A, materials, c, Sens, Cam, cnt);
         cs.vis[2 * (size_t)id] = 0u;
         cs.vis[2 * (size_t)id + 1] = 0u;
     }
@@ -424,9 +443,9 @@ k_connect_enumerate(uint32_t n, const Path *camera_paths, const Path *light_path
     flush_counters<COUNT>(cnt, counters);
 }
 
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK)
-k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, const Camera *camera, ConnectScratch cs,
+k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratch cs,
                Counters *counters, int refill_below, int schedule) {
     const uint32_t count = *cs.task_count;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -454,7 +473,7 @@ k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, c
                 TArr Sens;
                 Sens.base = cs.sensor + (size_t)slot * CLV_SENSOR_WORDS;
                 Sens.stride = 1;
-                int st = connect_ray_begin<MODE, COUNT>(q, camera_paths[slot].rays, light_paths[slot].rays, Sens, A, c, ray, cnt);
+                int st = connect_ray_begin<MODE, COUNT>(q, PathViewOf<SOA>::make(store, slot, 0u), Sens, A, c, ray, cnt);
                 have = st == OCC_RUNNING;
                 if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
             }
@@ -491,9 +510,9 @@ k_connect_rays(const Path *camera_paths, const Path *light_paths, AccelView A, c
 #else
 #define CLV_FINISH_BOUNDS __launch_bounds__(CLV_BLOCK)
 #endif
-template <bool SPLAT, bool COUNT>
+template <bool SPLAT, bool COUNT, bool SOA>
 __global__ void CLV_FINISH_BOUNDS
-k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_paths, const Path *light_paths,
+k_connect_finish(uint32_t n, const uint32_t *sample_ids, PathStore store,
                  const Material *materials, const Camera *camera, ConnectScratch cs, WeightAggregator *aggs, V4 *out,
                  LightSink sink, Counters *counters) {
     __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
@@ -508,12 +527,13 @@ k_connect_finish(uint32_t n, const uint32_t *sample_ids, const Path *camera_path
         S.stride = CLV_BLOCK;
         Sens.base = cs.sensor + (size_t)id * CLV_SENSOR_WORDS;
         Sens.stride = 1;
-        ConnectCtx X;
-        unsigned long long valid0;
-        connect_stage<COUNT>(id, camera_paths, light_paths, materials, S, Sens, X, valid0, cnt);
-        unsigned long long visible = (unsigned long long)cs.vis[2 * (size_t)id] | ((unsigned long long)cs.vis[2 * (size_t)id + 1] << 32);
         /* staged ABI: aggregator slot == id.  Fused renderer: aggregators are per pixel */
         uint32_t agg_slot = sample_ids ? sample_ids[id] : id;
+        typedef typename PathViewOf<SOA>::type PV;
+        ConnectCtx<PV> X;
+        unsigned long long valid0;
+        connect_stage<COUNT>(PathViewOf<SOA>::make(store, id, agg_slot), materials, S, Sens, X, valid0, cnt);
+        unsigned long long visible = (unsigned long long)cs.vis[2 * (size_t)id] | ((unsigned long long)cs.vis[2 * (size_t)id + 1] << 32);
         connect_finish<SPLAT>(X, valid0 | visible, id, agg_slot, materials, c, aggs, out, sink, warp_lanes);
     }
     flush_counters<COUNT>(cnt, counters);
@@ -613,11 +633,11 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 #ifndef CLV_WALK_MIN_BLOCKS
 #define CLV_WALK_MIN_BLOCKS 8
 #endif
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK, CLV_WALK_MIN_BLOCKS)
 k_fused_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
               const int32_t *light_triangle_indices, int light_count, const Material *materials, const Camera *camera,
-              AccelView A, uint32_t *seeds, Path *light_paths, Path *camera_paths, Accum *accum, Counters *counters) {
+              AccelView A, uint32_t *seeds, PathStore store, Accum *accum, Counters *counters) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
     if (id < n_local) {
@@ -625,8 +645,8 @@ k_fused_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *ligh
         uint32_t gid = sample_ids ? sample_ids[id] : id;
         uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
         uint32_t seed0 = sd.x, seed1 = sd.y;
-        fused_walk_sample<MODE, COUNT>(id, gid, light_triangles, surface_areas, light_triangle_indices, light_count,
-                                       materials, c, A, seed0, seed1, light_paths, camera_paths, accum, cnt);
+        fused_walk_sample<MODE, COUNT, SOA>(id, gid, light_triangles, surface_areas, light_triangle_indices, light_count,
+                                            materials, c, A, seed0, seed1, store, accum, cnt);
         reinterpret_cast<uint2 *>(seeds)[id] = make_uint2(seed0, seed1);
     }
     flush_counters<COUNT>(cnt, counters);
@@ -739,6 +759,24 @@ static ConnectScratch connect_scratch_at(void *mem, uint32_t n) {
         }                                                                              \
     } while (0)
 
+/* ... and on the path layout */
+#define DISPATCH_MCS(mode, counting, soa, CALL)                                      \
+    do {                                                                             \
+        if (soa) {                                                                   \
+            if ((mode) == CLV_TRAVERSE_REFERENCE_ORDER) {                            \
+                if (counting) { CALL(TRAVERSE_REFERENCE, true, true); } else { CALL(TRAVERSE_REFERENCE, false, true); } \
+            } else {                                                                 \
+                if (counting) { CALL(TRAVERSE_ORDERED, true, true); } else { CALL(TRAVERSE_ORDERED, false, true); }     \
+            }                                                                        \
+        } else {                                                                     \
+            if ((mode) == CLV_TRAVERSE_REFERENCE_ORDER) {                            \
+                if (counting) { CALL(TRAVERSE_REFERENCE, true, false); } else { CALL(TRAVERSE_REFERENCE, false, false); } \
+            } else {                                                                 \
+                if (counting) { CALL(TRAVERSE_ORDERED, true, false); } else { CALL(TRAVERSE_ORDERED, false, false); }     \
+            }                                                                        \
+        }                                                                            \
+    } while (0)
+
 static int g_stage_mode = CLV_TRAVERSE_ORDERED;
 extern "C" int clv_set_stage_traverse_mode(int mode) {
     REQUIRE(mode == CLV_TRAVERSE_REFERENCE_ORDER || mode == CLV_TRAVERSE_ORDERED, "bad mode");
@@ -747,30 +785,32 @@ extern "C" int clv_set_stage_traverse_mode(int mode) {
 }
 
 /* enumerate -> rays -> finish on the context's stream */
-static int launch_connect(clv_ctx *c, int mode, bool splat, uint32_t n, const uint32_t *sample_ids, const Path *cp,
-                          const Path *lp, const AccelView &view, const Material *mats, const Camera *cam,
+static int launch_connect(clv_ctx *c, int mode, bool splat, uint32_t n, const uint32_t *sample_ids, const PathStore &store,
+                          bool soa, const AccelView &view, const Material *mats, const Camera *cam,
                           ConnectScratch cs, WeightAggregator *aggs, V4 *out, const LightSink &sink,
                           cudaEvent_t *mid_events /* NULL or 2 events: after enumerate, after rays */) {
     Counters *ctr = c->d_counters + COUNTERS_CONNECT;
-#define CALL(M, CT) k_connect_enumerate<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, cp, lp, view, mats, cam, cs, ctr)
-    DISPATCH_MC(mode, c->counting, CALL);
+#define CALL(M, CT, SO) k_connect_enumerate<M, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, store, view, mats, cam, cs, ctr)
+    DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
     if (mid_events) CK(cudaEventRecord(mid_events[0], c->stream));
     const uint64_t warps = ((uint64_t)n * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
     const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
-#define CALL(M, CT) k_connect_rays<M, CT><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(cp, lp, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
-    DISPATCH_MC(mode, c->counting, CALL);
+#define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
+    DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
     if (mid_events) CK(cudaEventRecord(mid_events[1], c->stream));
-    if (splat) {
-        if (c->counting) k_connect_finish<true, true><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
-        else k_connect_finish<true, false><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+#define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
+    if (soa) {
+        if (splat) { if (c->counting) FIN(true, true, true); else FIN(true, false, true); }
+        else { if (c->counting) FIN(false, true, true); else FIN(false, false, true); }
     } else {
-        if (c->counting) k_connect_finish<false, true><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
-        else k_connect_finish<false, false><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, cp, lp, mats, cam, cs, aggs, out, sink, ctr);
+        if (splat) { if (c->counting) FIN(true, true, false); else FIN(true, false, false); }
+        else { if (c->counting) FIN(false, true, false); else FIN(false, false, false); }
     }
+#undef FIN
     LAUNCHED(c);
     return CLV_OK;
 }
@@ -837,7 +877,12 @@ extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, con
     }
     ConnectScratch cs = connect_scratch_at(c->cs_mem, n);
     CK(cudaMemsetAsync(cs.task_count, 0, 64, c->stream));
-    return launch_connect(c, g_stage_mode, false, n, nullptr, (const Path *)cp, (const Path *)lp, accel->view,
+    PathStore store;
+    memset(&store, 0, sizeof store);
+    store.camera_paths = (Path *)cp; /* read only here */
+    store.light_paths = (Path *)lp;
+    store.n = n;
+    return launch_connect(c, g_stage_mode, false, n, nullptr, store, false, accel->view,
                           (const Material *)mats, (const Camera *)cam, cs, (WeightAggregator *)aggs, (V4 *)out, sink, nullptr);
 }
 
@@ -911,7 +956,10 @@ struct clv_renderer {
     int32_t *d_light_tri_idx;
     /* work buffers */
     uint32_t *d_seeds, *d_sample_ids;
-    Path *d_light_paths, *d_camera_paths;
+    Path *d_light_paths, *d_camera_paths; /* reference-layout path records: only while path_records is on */
+    V4 *d_soa;                            /* compact SoA vertex records (the default) */
+    int32_t *d_soa_len;
+    int path_records;
     WeightAggregator *d_aggs;
     V4 *d_light_image;
     Accum *d_accum;
@@ -934,7 +982,7 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     cudaStreamSynchronize(r->ctx->stream);
     cudaFree(r->d_materials); cudaFree(r->d_camera); cudaFree(r->d_light_triangles); cudaFree(r->d_light_areas);
     cudaFree(r->d_light_tri_idx); cudaFree(r->d_seeds); cudaFree(r->d_sample_ids); cudaFree(r->d_light_paths);
-    cudaFree(r->d_camera_paths); cudaFree(r->d_aggs); cudaFree(r->d_light_image); cudaFree(r->d_accum);
+    cudaFree(r->d_camera_paths); cudaFree(r->d_soa); cudaFree(r->d_soa_len); cudaFree(r->d_aggs); cudaFree(r->d_light_image); cudaFree(r->d_accum);
     cudaFree(r->d_pass_weight);
     cudaFree(r->d_connect_scratch);
     cudaFree(r->d_tone_sum);
@@ -1006,8 +1054,10 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
         return CLV_OK;
     };
     TRY(zalloc((void **)&r->d_seeds, (size_t)n_local * 8));
-    TRY(zalloc((void **)&r->d_light_paths, (size_t)n_local * sizeof(Path)));
-    TRY(zalloc((void **)&r->d_camera_paths, (size_t)n_local * sizeof(Path)));
+    r->d_light_paths = r->d_camera_paths = nullptr;
+    r->path_records = 0;
+    TRY(zalloc((void **)&r->d_soa, (size_t)n_local * 2 * 6 * 4 * sizeof(V4)));
+    TRY(zalloc((void **)&r->d_soa_len, (size_t)n_local * 2 * sizeof(int32_t)));
     TRY(zalloc((void **)&r->d_aggs, (size_t)n_pixels * sizeof(WeightAggregator)));
     TRY(zalloc((void **)&r->d_light_image, (size_t)n_pixels * sizeof(V4)));
     TRY(zalloc((void **)&r->d_accum, (size_t)n_pixels * sizeof(Accum)));
@@ -1019,6 +1069,22 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
 #undef TRY
     CK(cudaStreamSynchronize(c->stream));
     *out = r;
+    return CLV_OK;
+}
+
+/* keep the reference-layout Path records of every pass (1040 B per subpath and sample) instead of the compact SoA
+ * vertex records: for differential tests and tools that read CLV_BUF_LIGHT_PATHS / CLV_BUF_CAMERA_PATHS */
+extern "C" int clv_renderer_set_path_records(clv_renderer *r, int enabled) {
+    REQUIRE(r, "null");
+    clv_ctx *c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    if (enabled && !r->d_light_paths) {
+        CK(cudaMalloc(&r->d_light_paths, (size_t)r->n_local * sizeof(Path)));
+        CK(cudaMemsetAsync(r->d_light_paths, 0, (size_t)r->n_local * sizeof(Path), c->stream));
+        CK(cudaMalloc(&r->d_camera_paths, (size_t)r->n_local * sizeof(Path)));
+        CK(cudaMemsetAsync(r->d_camera_paths, 0, (size_t)r->n_local * sizeof(Path), c->stream));
+    }
+    r->path_records = enabled ? 1 : 0;
     return CLV_OK;
 }
 
@@ -1042,8 +1108,16 @@ static int launch_pass(clv_renderer *r) {
         }
         CK(cudaEventRecord(r->events[ev0], c->stream));
     }
-#define CALL(M, CT) k_fused_walks<M, CT><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, r->d_light_paths, r->d_camera_paths, r->d_accum, c->d_counters)
-    DISPATCH_MC(r->mode, c->counting, CALL);
+    PathStore store;
+    memset(&store, 0, sizeof store);
+    store.light_paths = r->d_light_paths;
+    store.camera_paths = r->d_camera_paths;
+    store.soa = r->d_soa;
+    store.soa_len = r->d_soa_len;
+    store.n = n;
+    const bool soa = !r->path_records;
+#define CALL(M, CT, SO) k_fused_walks<M, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters)
+    DISPATCH_MCS(r->mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
     if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], c->stream));
@@ -1052,7 +1126,7 @@ static int launch_pass(clv_renderer *r) {
     sink.splat_image = r->d_light_image;
     sink.n_pixels = (int)r->n_pixels;
     {
-        int rc = launch_connect(c, r->mode, true, n, ids, r->d_camera_paths, r->d_light_paths, r->accel->view, r->d_materials,
+        int rc = launch_connect(c, r->mode, true, n, ids, store, soa, r->accel->view, r->d_materials,
                                 r->d_camera, connect_scratch_at(r->d_connect_scratch, n), r->d_aggs, nullptr, sink,
                                 r->timing ? &r->events[ev0 + 2] : nullptr);
         if (rc != CLV_OK) return rc;
@@ -1171,8 +1245,12 @@ extern "C" int clv_renderer_device_ptr(clv_renderer *r, int buffer_id, void **d_
     switch (buffer_id) {
     case CLV_BUF_ACCUM_PACKED: *d_ptr = r->d_accum; *nbytes = (size_t)r->n_pixels * sizeof(Accum); return CLV_OK;
     case CLV_BUF_SEEDS: *d_ptr = r->d_seeds; *nbytes = (size_t)r->n_local * 8; return CLV_OK;
-    case CLV_BUF_LIGHT_PATHS: *d_ptr = r->d_light_paths; *nbytes = (size_t)r->n_local * sizeof(Path); return CLV_OK;
-    case CLV_BUF_CAMERA_PATHS: *d_ptr = r->d_camera_paths; *nbytes = (size_t)r->n_local * sizeof(Path); return CLV_OK;
+    case CLV_BUF_LIGHT_PATHS:
+    case CLV_BUF_CAMERA_PATHS:
+        if (!r->path_records) return fail(CLV_ERR_INVALID, "path records are off: call clv_renderer_set_path_records(r, 1) before the pass");
+        *d_ptr = buffer_id == CLV_BUF_LIGHT_PATHS ? r->d_light_paths : r->d_camera_paths;
+        *nbytes = (size_t)r->n_local * sizeof(Path);
+        return CLV_OK;
     case CLV_BUF_AGGREGATORS: *d_ptr = r->d_aggs; *nbytes = (size_t)r->n_pixels * sizeof(WeightAggregator); return CLV_OK;
     case CLV_BUF_PASS_WEIGHT: *d_ptr = r->d_pass_weight; *nbytes = 4; return CLV_OK;
     default: return fail(CLV_ERR_INVALID, "buffer %d has no device-side representation of its own", buffer_id);

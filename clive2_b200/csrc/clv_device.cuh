@@ -759,15 +759,100 @@ CLV_HD Ray make_light_ray(const Triangle *light_triangles, const float *surface_
     return ray;
 }
 
+/* ---- where stored path vertices live ------------------------------------------------------------------------------ *
+ * Two layouts behind one interface.  AoS = the reference's Path records (1040 B per subpath, 128 B per vertex): what the
+ * stage-level ABI reads and writes.  SoA = the fused renderer's own compact layout: 64 B per vertex in four 16-byte
+ * parts, part-major over the samples ([(subpath*6 + vertex)*4 + part][n_samples]), so that a warp reads or writes 512
+ * contiguous bytes per part; only what the connection stage consumes is kept (the direction survives as |dir.n|):
+ *   part 0: origin.xyz, tot_importance      part 1: normal.xyz, |direction . normal|
+ *   part 2: color.xyz, c_importance         part 3: l_importance, material, triangle, hit_light (int bits)
+ * Values are the same bits in both layouts; k_connect_finish missed L1 on 90 % of its AoS reads and moved twice the path
+ * data through DRAM (profiles/r01_notes.md). */
+enum { SUB_LIGHT = 0, SUB_CAMERA = 1 };
+
+struct AosPaths {
+    const Path *paths[2]; /* this sample's two records */
+    CLV_HDM int length(int sub) const { return paths[sub]->length; }
+    CLV_HDM V3 origin(int sub, int k) const { return xyz(paths[sub]->rays[k].origin); }
+    CLV_HDM V3 normal(int sub, int k) const { return xyz(paths[sub]->rays[k].normal); }
+    CLV_HDM V3 color(int sub, int k) const { return xyz(paths[sub]->rays[k].color); }
+    CLV_HDM float abs_cos(int sub, int k) const {
+        return fabsf(dot(xyz(paths[sub]->rays[k].direction), xyz(paths[sub]->rays[k].normal)));
+    }
+    CLV_HDM float limp(int sub, int k) const { return paths[sub]->rays[k].l_importance; }
+    CLV_HDM float cimp(int sub, int k) const { return paths[sub]->rays[k].c_importance; }
+    CLV_HDM float tot(int sub, int k) const { return paths[sub]->rays[k].tot_importance; }
+    CLV_HDM int material(int sub, int k) const { return paths[sub]->rays[k].material; }
+    CLV_HDM int triangle(int sub, int k) const { return paths[sub]->rays[k].triangle; }
+    CLV_HDM bool hit_light(int sub, int k) const { return paths[sub]->rays[k].hit_light >= 0; }
+    CLV_HDM int pixel_idx0() const { return paths[SUB_CAMERA]->rays[0].pixel_idx; }
+};
+CLV_HD AosPaths aos_paths(const Path *camera_paths, const Path *light_paths, uint32_t slot) {
+    AosPaths P;
+    P.paths[SUB_LIGHT] = light_paths + slot;
+    P.paths[SUB_CAMERA] = camera_paths + slot;
+    return P;
+}
+
+struct SoaPaths {
+    const V4 *v;        /* [(sub*6 + k)*4 + part][n] */
+    const int32_t *len; /* [2][n] */
+    uint32_t n, slot;
+    int32_t pixel0;     /* the pixel this sample belongs to (its global id) */
+    CLV_HDM V4 part(int sub, int k, int part_) const { return ld4(v + ((size_t)((sub * 6 + k) * 4 + part_) * n + slot)); }
+    CLV_HDM int length(int sub) const { return len[(size_t)sub * n + slot]; }
+    CLV_HDM V3 origin(int sub, int k) const { return xyz(part(sub, k, 0)); }
+    CLV_HDM V3 normal(int sub, int k) const { return xyz(part(sub, k, 1)); }
+    CLV_HDM V3 color(int sub, int k) const { return xyz(part(sub, k, 2)); }
+    CLV_HDM float abs_cos(int sub, int k) const { return part(sub, k, 1).w; }
+    CLV_HDM float limp(int sub, int k) const { return part(sub, k, 3).x; }
+    CLV_HDM float cimp(int sub, int k) const { return part(sub, k, 2).w; }
+    CLV_HDM float tot(int sub, int k) const { return part(sub, k, 0).w; }
+    CLV_HDM int material(int sub, int k) const { return f2i(part(sub, k, 3).y); }
+    CLV_HDM int triangle(int sub, int k) const { return f2i(part(sub, k, 3).z); }
+    CLV_HDM bool hit_light(int sub, int k) const { return f2i(part(sub, k, 3).w) >= 0; }
+    /* an empty camera path leaves a zeroed slot 0 behind, whose pixel index is 0 (see random_walk) */
+    CLV_HDM int pixel_idx0() const { return length(SUB_CAMERA) > 0 ? pixel0 : 0; }
+};
+
+/* where a random walk puts its vertices */
+struct AosSink {
+    Path *path;
+    CLV_HDM void store(int i, const Ray &ray) const { path->rays[i] = ray; }
+    CLV_HDM void patch(int i, bool from_camera, float value) const {
+        if (from_camera) path->rays[i].l_importance = value;
+        else path->rays[i].c_importance = value;
+    }
+    CLV_HDM void finish(int length, bool from_camera) const;
+};
+struct SoaSink {
+    V4 *v;
+    int32_t *len;
+    uint32_t n, slot;
+    int sub;
+    CLV_HDM V4 *part(int k, int part_) const { return v + ((size_t)((sub * 6 + k) * 4 + part_) * n + slot); }
+    CLV_HDM void store(int i, const Ray &ray) const {
+        *part(i, 0) = v4(ray.origin.x, ray.origin.y, ray.origin.z, ray.tot_importance);
+        *part(i, 1) = v4(ray.normal.x, ray.normal.y, ray.normal.z, fabsf(dot(xyz(ray.direction), xyz(ray.normal))));
+        *part(i, 2) = v4(ray.color.x, ray.color.y, ray.color.z, ray.c_importance);
+        *part(i, 3) = v4(ray.l_importance, i2f(ray.material), i2f(ray.triangle), i2f(ray.hit_light));
+    }
+    CLV_HDM void patch(int i, bool from_camera, float value) const {
+        if (from_camera) part(i, 3)->x = value;
+        else part(i, 2)->w = value;
+    }
+    CLV_HDM void finish(int length, bool from_camera) const;
+};
+
 /* ---- random walk: generate_paths, trace.metal:381-532 ----------------------------------------------------------- *
  * Vertices are written to out_path->rays[i] as they are produced (the reference builds the Path in thread memory and
  * copies 1040 bytes at the end).  Slots >= length keep whatever they held; nothing downstream reads them.  A path of
  * length 0 gets a zeroed rays[0], which is what connect_paths' splat-weight code then reads (the reference reads
  * uninitialised memory there; the oracle reads zeros).
  */
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, typename SINK>
 CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, uint32_t &seed0, uint32_t &seed1,
-                        Path *out_path, V4 *out_uni, Cnt<COUNT> &cnt) {
+                        const SINK &sink, V4 *out_uni, Cnt<COUNT> &cnt) {
     const bool from_camera = ray.from_camera != 0;
     float carry_imp = from_camera ? ray.c_importance : 1.0f / (2.0f * CLV_PI);
     int length = 0;
@@ -779,7 +864,7 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         /* The vertex goes to its slot BEFORE the bounce is known to succeed (slot i only counts once length > i; the
          * one field the bounce still changes is patched below).  That ends the live range of the 32-word record here
          * instead of across the traversal, which is what bounds this kernel's registers and therefore its occupancy. */
-        out_path->rays[i] = ray;
+        sink.store(i, ray);
         const V3 o = xyz(ray.origin), d = xyz(ray.direction), inv = xyz(ray.inv_direction), rc = xyz(ray.color);
         const float ray_tot = ray.tot_importance;
         const int ray_hit_light = ray.hit_light;
@@ -856,8 +941,7 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         if (f == 0.0f) break;
 
         /* path.rays[i] = ray with the reverse-direction pdf the bounce produced (:499-507, :512) */
-        if (from_camera) out_path->rays[i].l_importance = l_p;
-        else out_path->rays[i].c_importance = c_p;
+        sink.patch(i, from_camera, from_camera ? l_p : c_p);
         cnt.vertex(1);
         length = i + 1;
         if (!uni_found && ray_hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
@@ -870,12 +954,19 @@ CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, 
         ray = nr;
         carry_imp = next_carry;
     }
-    if (length == 0) out_path->rays[0] = zero_ray();
-    out_path->length = length;
-    out_path->from_camera = from_camera ? 1 : 0;
-    out_path->pad[0] = 0;
-    out_path->pad[1] = 0;
+    sink.finish(length, from_camera);
     *out_uni = uni;
+}
+CLV_HDM void AosSink::finish(int length, bool from_camera) const {
+    if (length == 0) path->rays[0] = zero_ray();
+    path->length = length;
+    path->from_camera = from_camera ? 1 : 0;
+    path->pad[0] = 0;
+    path->pad[1] = 0;
+}
+CLV_HDM void SoaSink::finish(int length, bool) const {
+    if (length == 0) store(0, zero_ray());
+    len[(size_t)sub * n + slot] = length;
 }
 
 /* ---- connection helpers (trace.metal:539-617) ---------------------------------------------------------------------- */
@@ -945,8 +1036,9 @@ CLV_HD void atomic_add(float *p, float v) {
  * ray) and the finish phase a loop over survivors only.
  * Strategy index q = (t-1)*7 + s, t = 1..6, s = 0..6; ascending q is the reference's loop order.
  */
+template <typename PV>
 struct ConnectCtx {
-    const Ray *cr, *lr;
+    PV P;
     int len_c, len_l;
     unsigned spec_l, spec_c; /* bit i: vertex i has a specular material */
     bool spec_sensor;        /* material of the rewritten sensor vertex (:611) is specular */
@@ -970,64 +1062,56 @@ CLV_HD bool sensor_hit(const AccelView &A, V3 origin, V3 direction, float &t_bes
 }
 
 /* phase 1a: stage the MIS terms of one sample and find the s = 0 strategies (camera subpath ends on an emitter) */
-template <bool COUNT>
-CLV_HD void connect_stage(uint32_t slot, const Path *camera_paths, const Path *light_paths, const Material *materials,
-                          TArr S, TArr Sens, ConnectCtx &X, unsigned long long &valid0, Cnt<COUNT> &cnt) {
-    const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
-    const Ray *cr = cpath->rays, *lr = lpath->rays;
-    const int len_c = cpath->length, len_l = lpath->length;
-    X.cr = cr; X.lr = lr; X.len_c = len_c; X.len_l = len_l; X.S = S; X.Sens = Sens;
+template <bool COUNT, typename PV>
+CLV_HD void connect_stage(const PV &P, const Material *materials, TArr S, TArr Sens, ConnectCtx<PV> &X,
+                          unsigned long long &valid0, Cnt<COUNT> &cnt) {
+    const int len_c = P.length(SUB_CAMERA), len_l = P.length(SUB_LIGHT);
+    X.P = P; X.len_c = len_c; X.len_l = len_l; X.S = S; X.Sens = Sens;
     unsigned spec_l = 0, spec_c = 0;
     cnt.vertex(len_l + len_c);
     for (int i = 0; i < len_l; i++) {
-        const Ray *r = lr + i;
-        S[L_LIMP + i] = r->l_importance;
-        S[L_CIMP + i] = r->c_importance;
-        S[L_COS + i] = fabsf(dot(xyz(r->direction), xyz(r->normal)));
-        S[L_TOT + i] = r->tot_importance;
-        if (materials[r->material].type > 0) spec_l |= 1u << i;
+        S[L_LIMP + i] = P.limp(SUB_LIGHT, i);
+        S[L_CIMP + i] = P.cimp(SUB_LIGHT, i);
+        S[L_COS + i] = P.abs_cos(SUB_LIGHT, i);
+        S[L_TOT + i] = P.tot(SUB_LIGHT, i);
+        if (materials[P.material(SUB_LIGHT, i)].type > 0) spec_l |= 1u << i;
     }
     for (int i = 0; i + 1 < len_l; i++)
-        S[G_LL + i] = geometry_from(S[L_COS + i], S[L_COS + i + 1], xyz(lr[i].origin), xyz(lr[i + 1].origin));
+        S[G_LL + i] = geometry_from(S[L_COS + i], S[L_COS + i + 1], P.origin(SUB_LIGHT, i), P.origin(SUB_LIGHT, i + 1));
     valid0 = 0ull;
     for (int j = 0; j < len_c; j++) {
-        const Ray *r = cr + j;
-        S[C_LIMP + j] = r->l_importance;
-        S[C_CIMP + j] = r->c_importance;
-        S[C_COS + j] = fabsf(dot(xyz(r->direction), xyz(r->normal)));
-        S[C_TOT + j] = r->tot_importance;
-        if (materials[r->material].type > 0) spec_c |= 1u << j;
-        if (j >= 1 && r->hit_light >= 0) valid0 |= 1ull << (j * 7); /* t = j + 1, s = 0 (t + s >= 2) */
+        S[C_LIMP + j] = P.limp(SUB_CAMERA, j);
+        S[C_CIMP + j] = P.cimp(SUB_CAMERA, j);
+        S[C_COS + j] = P.abs_cos(SUB_CAMERA, j);
+        S[C_TOT + j] = P.tot(SUB_CAMERA, j);
+        if (materials[P.material(SUB_CAMERA, j)].type > 0) spec_c |= 1u << j;
+        if (j >= 1 && P.hit_light(SUB_CAMERA, j)) valid0 |= 1ull << (j * 7); /* t = j + 1, s = 0 (t + s >= 2) */
     }
     for (int j = 0; j + 1 < len_c; j++)
-        S[G_CC + j] = geometry_from(S[C_COS + j], S[C_COS + j + 1], xyz(cr[j].origin), xyz(cr[j + 1].origin));
+        S[G_CC + j] = geometry_from(S[C_COS + j], S[C_COS + j + 1], P.origin(SUB_CAMERA, j), P.origin(SUB_CAMERA, j + 1));
     X.spec_l = spec_l; X.spec_c = spec_c;
     X.spec_sensor = materials[7].type > 0;
 }
 
 /* phase 1b: the strategies that need a predicate ray, after the reference's cheap rejections */
-template <int MODE, bool COUNT>
-CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_paths, const Path *light_paths,
-                                            const AccelView &A, const Material *materials, const Camera &c, TArr Sens,
-                                            TArr Cam /* CLV_ENUM_SCRATCH floats */, Cnt<COUNT> &cnt) {
-    const Path *cpath = camera_paths + slot, *lpath = light_paths + slot;
-    const Ray *cr = cpath->rays, *lr = lpath->rays;
-    const int len_c = cpath->length, len_l = lpath->length;
+template <int MODE, bool COUNT, typename PV>
+CLV_HD unsigned long long connect_enumerate(const PV &P, const AccelView &A, const Material *materials, const Camera &c,
+                                            TArr Sens, TArr Cam /* CLV_ENUM_SCRATCH floats */, Cnt<COUNT> &cnt) {
+    const int len_c = P.length(SUB_CAMERA), len_l = P.length(SUB_LIGHT);
     unsigned long long cand = 0ull;
     unsigned spec_c = 0;
     /* camera vertices are needed once per light vertex: read each from global memory once (the per-thread working set
      * of path records is far larger than L1, so re-reads went to L2/DRAM: 1.26 GB per launch at C2 before this) */
     for (int j = 0; j < len_c; j++) {
-        if (materials[cr[j].material].type > 0) spec_c |= 1u << j;
-        V4 o = cr[j].origin, nn = cr[j].normal;
+        if (materials[P.material(SUB_CAMERA, j)].type > 0) spec_c |= 1u << j;
+        V3 o = P.origin(SUB_CAMERA, j), nn = P.normal(SUB_CAMERA, j);
         Cam[6 * j + 0] = o.x; Cam[6 * j + 1] = o.y; Cam[6 * j + 2] = o.z;
         Cam[6 * j + 3] = nn.x; Cam[6 * j + 4] = nn.y; Cam[6 * j + 5] = nn.z;
     }
     for (int s = 1; s < len_l + 1; s++) {
-        const Ray *light_ray = lr + (s - 1);
-        V3 lig_o = xyz(light_ray->origin);
+        V3 lig_o = P.origin(SUB_LIGHT, s - 1);
         /* t = 1: world_ray_to_camera_ray up to its traversal (:577-586) */
-        if (len_c >= 1 && !(materials[A.ref_triangles[light_ray->triangle].material].type > 0)) {
+        if (len_c >= 1 && !(materials[A.ref_triangles[P.triangle(SUB_LIGHT, s - 1)].material].type > 0)) {
             V3 direction = normalize(xyz(c.focal_point) - lig_o);
             if (!(dot(direction, xyz(c.direction)) > 0.0f)) {
                 cnt.ray_ref();
@@ -1044,8 +1128,8 @@ CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_pa
             }
         }
         /* t >= 2: regular joins up to visibility_test (:676-688) */
-        if (materials[light_ray->material].type > 0) continue;
-        V3 lig_n = xyz(light_ray->normal);
+        if (materials[P.material(SUB_LIGHT, s - 1)].type > 0) continue;
+        V3 lig_n = P.normal(SUB_LIGHT, s - 1);
         for (int t = 2; t < len_c + 1; t++) {
             if ((spec_c >> (t - 1)) & 1u) continue;
             const int j = t - 1;
@@ -1061,12 +1145,11 @@ CLV_HD unsigned long long connect_enumerate(uint32_t slot, const Path *camera_pa
 
 /* Start the predicate ray of strategy q of the sample whose paths are (cr, lr) and whose scratch is S (which may belong
  * to another lane of the warp).  Returns OCC_RUNNING with `ray` set up, or the final status. */
-template <int MODE, bool COUNT>
-CLV_HD int connect_ray_begin(int q, const Ray *cr, const Ray *lr, TArr Sens, const AccelView &A, const Camera &c, OccRay &ray,
+template <int MODE, bool COUNT, typename PV>
+CLV_HD int connect_ray_begin(int q, const PV &P, TArr Sens, const AccelView &A, const Camera &c, OccRay &ray,
                              Cnt<COUNT> &cnt) {
     const int t = q / 7 + 1, s = q % 7;
-    const Ray *light_ray = lr + (s - 1);
-    V3 lig_o = xyz(light_ray->origin);
+    V3 lig_o = P.origin(SUB_LIGHT, s - 1);
     if (t == 1) {
         V3 direction = normalize(xyz(c.focal_point) - lig_o);
         if (MODE == TRAVERSE_ORDERED) {
@@ -1085,9 +1168,8 @@ CLV_HD int connect_ray_begin(int q, const Ray *cr, const Ray *lr, TArr Sens, con
         Sens[CAM_TRI + s - 1] = i2f(best_i);
         return OCC_CLEAR;
     }
-    const Ray *camera_ray = cr + (t - 1);
-    V3 cam_o = xyz(camera_ray->origin);
-    int a_triangle = light_ray->triangle, b_triangle = camera_ray->triangle;
+    V3 cam_o = P.origin(SUB_CAMERA, t - 1);
+    int a_triangle = P.triangle(SUB_LIGHT, s - 1), b_triangle = P.triangle(SUB_CAMERA, t - 1);
     if (MODE == TRAVERSE_ORDERED) {
         V3 direction = normalize(cam_o - lig_o);
         if (b_triangle < 0 || b_triangle == a_triangle) return OCC_BLOCKED;
@@ -1105,11 +1187,11 @@ CLV_HD int connect_ray_begin(int q, const Ray *cr, const Ray *lr, TArr Sens, con
 }
 
 /* finish: MIS + contributions of the surviving strategies, splat weights, aggregator */
-template <bool SPLAT>
-CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
+template <bool SPLAT, typename PV>
+CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
                            const Material *materials, const Camera &c, WeightAggregator *weight_aggregators, V4 *out,
                            const LightSink &sink, unsigned warp_lanes /* device: lanes of the warp that make this call */) {
-    const Ray *cr = X.cr, *lr = X.lr;
+    const PV &P = X.P;
     TArr S = X.S;
     const unsigned spec_l = X.spec_l, spec_c = X.spec_c;
     const int total_pixels = c.pixel_width * c.pixel_height;
@@ -1134,11 +1216,10 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
 
         if (s == 0) {
             cam_tot = S[C_TOT + t - 1];
-            cam_material = cr[t - 1].material;
+            cam_material = P.material(SUB_CAMERA, t - 1);
         } else if (t == 1) {
-            const Ray *light_ray = lr + (s - 1);
-            lig_o = xyz(light_ray->origin);
-            lig_n = xyz(light_ray->normal);
+            lig_o = P.origin(SUB_LIGHT, s - 1);
+            lig_n = P.normal(SUB_LIGHT, s - 1);
             V3 direction = normalize(xyz(c.focal_point) - lig_o);
             V3 camera_point = lig_o + direction * X.Sens[T_SENSOR + s - 1];
             float x = dot(camera_point - xyz(c.center), xyz(c.dx));
@@ -1154,15 +1235,13 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
             dir_l_to_c = normalize(camera_point - lig_o);
             g_conn = geometry_from(S[L_COS + s - 1], cam_cos, lig_o, camera_point);
         } else {
-            const Ray *camera_ray = cr + (t - 1);
-            const Ray *light_ray = lr + (s - 1);
-            V3 cam_o = xyz(camera_ray->origin);
-            cam_n = xyz(camera_ray->normal);
-            lig_o = xyz(light_ray->origin);
-            lig_n = xyz(light_ray->normal);
+            V3 cam_o = P.origin(SUB_CAMERA, t - 1);
+            cam_n = P.normal(SUB_CAMERA, t - 1);
+            lig_o = P.origin(SUB_LIGHT, s - 1);
+            lig_n = P.normal(SUB_LIGHT, s - 1);
             dir_l_to_c = normalize(cam_o - lig_o);
             cam_tot = S[C_TOT + t - 1];
-            cam_material = camera_ray->material;
+            cam_material = P.material(SUB_CAMERA, t - 1);
             g_conn = geometry_from(S[L_COS + s - 1], S[C_COS + t - 1], lig_o, cam_o);
         }
 
@@ -1209,28 +1288,26 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
         V3 color;
         float g = 1.0f, new_light_f = 1.0f;
         if (s == 0) {
-            V3 prior_color = xyz(cr[t - 2].color);
+            V3 prior_color = P.color(SUB_CAMERA, t - 2);
             V3 emission = xyz(ld4(&materials[cam_material].emission));
             color = prior_color * emission;
         } else if (t == 1) {
-            const Ray *light_ray = lr + (s - 1);
             int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
-            V3 prior_color = xyz(lr[prior_light_ind].color);
+            V3 prior_color = P.color(SUB_LIGHT, prior_light_ind);
             if (s > 1) new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
-            color = (prior_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+            color = (prior_color * new_light_f) * xyz(ld4(&materials[P.material(SUB_LIGHT, s - 1)].color));
             g = g_conn; /* cosine_geometry_term(light_ray, camera_ray) */
         } else {
-            const Ray *light_ray = lr + (s - 1);
-            V3 prior_camera_color = xyz(cr[t - 2].color);
+            V3 prior_camera_color = P.color(SUB_CAMERA, t - 2);
             float new_camera_f = fabsf(dot(-dir_l_to_c, cam_n)) / CLV_PI;
             V3 camera_color = (prior_camera_color * new_camera_f) * xyz(ld4(&materials[cam_material].color));
             V3 light_color;
             if (s == 1) {
-                light_color = xyz(ld4(&materials[light_ray->material].emission));
+                light_color = xyz(ld4(&materials[P.material(SUB_LIGHT, s - 1)].emission));
             } else {
-                V3 prior_light_color = xyz(lr[s - 2].color);
+                V3 prior_light_color = P.color(SUB_LIGHT, s - 2);
                 new_light_f = fabsf(dot(dir_l_to_c, lig_n)) / CLV_PI;
-                light_color = (prior_light_color * new_light_f) * xyz(ld4(&materials[light_ray->material].color));
+                light_color = (prior_light_color * new_light_f) * xyz(ld4(&materials[P.material(SUB_LIGHT, s - 1)].color));
             }
             color = camera_color * light_color;
             g = g_conn; /* cosine_geometry_term(camera_ray, light_ray): symmetric, same bits */
@@ -1243,10 +1320,9 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
             if (SPLAT) {
                 /* light_image_gather (:937-964) applied on the spot: weights * shades * prior.color * mat.color */
                 if (light_pixel_idx >= 0 && light_pixel_idx < sink.n_pixels) {
-                    const Ray *light_ray = lr + (s - 1);
                     int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
-                    V3 contrib = (xyz(lr[prior_light_ind].color) * (w * shade)) *
-                                 xyz(ld4(&materials[light_ray->material].color));
+                    V3 contrib = (P.color(SUB_LIGHT, prior_light_ind) * (w * shade)) *
+                                 xyz(ld4(&materials[P.material(SUB_LIGHT, s - 1)].color));
                     float *px = &sink.splat_image[light_pixel_idx].x;
                     atomic_add(px + 0, contrib.x);
                     atomic_add(px + 1, contrib.y);
@@ -1273,8 +1349,8 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
     /* 3x3 splat weights (:827-864) */
     WeightAggregator agg;
     for (int i = 0; i < 3; i++) { agg.pad0[i] = 0.0f; agg.pad1[i] = 0.0f; }
-    const int pixel_idx = cr[0].pixel_idx;
-    const V3 sensor_origin = xyz(cr[0].origin);
+    const int pixel_idx = P.pixel_idx0();
+    const V3 sensor_origin = P.origin(SUB_CAMERA, 0);
     float weight_sum = 0.0f;
     float ppw = c.phys_width / (float)c.pixel_width;
     float pph = c.phys_height / (float)c.pixel_height;
@@ -1305,23 +1381,22 @@ CLV_HD void connect_finish(const ConnectCtx &X, unsigned long long survivors, ui
 
 /* the three phases for one sample, rays traced one after the other by the calling thread (host build; also the shape
  * of the computation the warp-cooperative kernel distributes) */
-template <int MODE, bool SPLAT, bool COUNT>
-CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, const Path *camera_paths,
-                           const Path *light_paths, const AccelView &A, const Material *materials, const Camera &c,
-                           WeightAggregator *weight_aggregators, V4 *out, const LightSink &sink, TArr S,
+template <int MODE, bool SPLAT, bool COUNT, typename PV>
+CLV_HD void connect_sample(const PV &P, uint32_t entry_id, uint32_t agg_slot, const AccelView &A, const Material *materials,
+                           const Camera &c, WeightAggregator *weight_aggregators, V4 *out, const LightSink &sink, TArr S,
                            Cnt<COUNT> &cnt) {
-    ConnectCtx X;
+    ConnectCtx<PV> X;
     unsigned long long valid0;
     float sens_words[CLV_SENSOR_WORDS];
     TArr Sens;
     Sens.base = sens_words;
     Sens.stride = 1;
-    connect_stage<COUNT>(slot, camera_paths, light_paths, materials, S, Sens, X, valid0, cnt);
+    connect_stage<COUNT>(P, materials, S, Sens, X, valid0, cnt);
     float cam_words[CLV_ENUM_SCRATCH];
     TArr Cam;
     Cam.base = cam_words;
     Cam.stride = 1;
-    unsigned long long cand = connect_enumerate<MODE, COUNT>(slot, camera_paths, light_paths, A, materials, c, Sens, Cam, cnt);
+    unsigned long long cand = connect_enumerate<MODE, COUNT>(P, A, materials, c, Sens, Cam, cnt);
     unsigned long long visible = 0ull, m = cand;
     while (m) {
 #if defined(__CUDA_ARCH__)
@@ -1332,7 +1407,7 @@ CLV_HD void connect_sample(uint32_t slot, uint32_t entry_id, uint32_t agg_slot, 
         m &= m - 1;
         OccRay ray;
         int stack[CLV_STACK];
-        int st = connect_ray_begin<MODE, COUNT>(q, X.cr, X.lr, Sens, A, c, ray, cnt);
+        int st = connect_ray_begin<MODE, COUNT>(q, P, Sens, A, c, ray, cnt);
         while (st == OCC_RUNNING) st = occ_round<COUNT>(A, ray, stack, cnt);
         if (st == OCC_CLEAR) visible |= 1ull << q;
     }
@@ -1378,11 +1453,18 @@ static_assert(sizeof(Accum) == 32, "Accum");
  * the reference's order (light gen, camera gen, light walk, camera walk), then the unidirectional part of
  * process_images (renderer.py:273-278).  `gid` = global sample id = pixel; this pixel's accumulator is touched by
  * exactly one sample per pass, so the read-modify-write needs no atomics. */
-template <int MODE, bool COUNT>
+/* the fused renderer's path storage: SoA records (default) or the reference's Path records */
+struct PathStore {
+    Path *light_paths, *camera_paths; /* AoS, or NULL */
+    V4 *soa;                          /* SoA vertex parts, or NULL */
+    int32_t *soa_len;
+    uint32_t n;
+};
+template <int MODE, bool COUNT, bool SOA>
 CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light_triangles, const float *surface_areas,
                               const int32_t *light_triangle_indices, int light_count, const Material *materials,
-                              const Camera &c, const AccelView &A, uint32_t &seed0, uint32_t &seed1, Path *light_paths,
-                              Path *camera_paths, Accum *accum, Cnt<COUNT> &cnt) {
+                              const Camera &c, const AccelView &A, uint32_t &seed0, uint32_t &seed1, const PathStore &store,
+                              Accum *accum, Cnt<COUNT> &cnt) {
     Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
     Ray cray = make_camera_ray(c, (int)gid, seed0, seed1);
     V4 uni;
@@ -1390,9 +1472,17 @@ CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int which = 0; which < 2; which++)
-        random_walk<MODE, COUNT>(which ? cray : lray, A, materials, seed0, seed1,
-                                 (which ? camera_paths : light_paths) + slot, &uni, cnt);
+    for (int which = 0; which < 2; which++) { /* which = SUB_LIGHT, then SUB_CAMERA */
+        if (SOA) {
+            SoaSink sink;
+            sink.v = store.soa; sink.len = store.soa_len; sink.n = store.n; sink.slot = slot; sink.sub = which;
+            random_walk<MODE, COUNT>(which ? cray : lray, A, materials, seed0, seed1, sink, &uni, cnt);
+        } else {
+            AosSink sink;
+            sink.path = (which ? store.camera_paths : store.light_paths) + slot;
+            random_walk<MODE, COUNT>(which ? cray : lray, A, materials, seed0, seed1, sink, &uni, cnt);
+        }
+    }
     Accum *a = accum + gid;
     a->uni[0] += nan_to_num0(uni.x);
     a->uni[1] += nan_to_num0(uni.y);

@@ -41,7 +41,7 @@ def make_seeds(batch_size, seed=None):
 
 class Renderer:
     def __init__(self, scene, kernel_path=None, fused=True, seed=None, seeds=None, sample_ids=None,
-                 traverse_mode=runtime.TRAVERSE_ORDERED):
+                 traverse_mode=runtime.TRAVERSE_ORDERED, path_records=False):
         dev = scene.device
         self.device = dev
         self.scene = scene
@@ -60,6 +60,8 @@ class Renderer:
             accel = dev.accel(scene.boxes, scene.triangles)
             self._fr = runtime.FusedRenderer(dev, accel, scene.arrays, self._initial_seeds, sample_ids)
             self._fr.set_traverse_mode(traverse_mode)
+            if path_records:  # keep the reference's Path records readable (tests, tools); default: compact SoA records
+                self._fr.set_path_records(True)
             self._cache = None
         else:
             if sample_ids is not None:

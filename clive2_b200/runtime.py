@@ -71,6 +71,7 @@ SIGNATURES = {
     "clv_renderer_read": [_vp, _int, _vp, _sz],
     "clv_renderer_device_ptr": [_vp, _int, _pp, C.POINTER(_sz)],
     "clv_renderer_set_traverse_mode": [_vp, _int],
+    "clv_renderer_set_path_records": [_vp, _int],
     "clv_set_stage_traverse_mode": [_int],
     "clv_traverse": [_vp, _vp, _vp, _u32, _int, _vp, _vp, _vp, _vp],
     "clv_traverse_device": [_vp, _vp, _vp, _u32, _int, _vp, _vp, _vp, _vp],
@@ -535,6 +536,10 @@ class FusedRenderer:
 
     def run_sample_preview(self, h_seeds_ptr, exposure, h_image_ptr):
         _check(self.device.lib.clv_renderer_run_sample_preview(self.handle, h_seeds_ptr, float(exposure), h_image_ptr))
+
+    def set_path_records(self, enabled=True):
+        """Keep the reference-layout Path records of each pass (readable as BUF_LIGHT_PATHS / BUF_CAMERA_PATHS)."""
+        _check(self.device.lib.clv_renderer_set_path_records(self.handle, int(bool(enabled))))
 
     def kernel_timing(self, enabled=True):
         _check(self.device.lib.clv_renderer_kernel_timing(self.handle, int(bool(enabled))))

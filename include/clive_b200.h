@@ -217,8 +217,8 @@ typedef enum clv_buffer_id {
     CLV_BUF_SEEDS = 4,                 /* uint32[W*H][2]                   */
     CLV_BUF_ACCUM_PACKED = 5,          /* float[H][W][8]: image3, weight, uni3, count — the accumulators as stored
                                           on the device, and the multi-GPU reduce payload */
-    CLV_BUF_LIGHT_PATHS = 6,           /* Path[n_local]  (last pass)  renderer.py:79 */
-    CLV_BUF_CAMERA_PATHS = 7,          /* Path[n_local]  (last pass)  renderer.py:58 */
+    CLV_BUF_LIGHT_PATHS = 6,           /* Path[n_local]  (last pass)  renderer.py:79; needs clv_renderer_set_path_records */
+    CLV_BUF_CAMERA_PATHS = 7,          /* Path[n_local]  (last pass)  renderer.py:58; needs clv_renderer_set_path_records */
     CLV_BUF_AGGREGATORS = 8,           /* WeightAggregator[W*H] (last pass, indexed by pixel) */
     CLV_BUF_PASS_WEIGHT = 9            /* float: running sum over passes and pixels of the per-pass sample weights */
 } clv_buffer_id;
@@ -244,6 +244,10 @@ CLV_API int clv_visibility(clv_ctx *ctx, const clv_accel *accel, const clv_Ray *
  * fused renderer (default ORDERED).  REFERENCE_ORDER visits boxes exactly like trace.metal:144-176. */
 CLV_API int clv_set_stage_traverse_mode(int mode);
 CLV_API int clv_renderer_set_traverse_mode(clv_renderer *r, int mode);
+/* By default the fused renderer keeps the vertices of a pass in its own compact SoA records (64 B per vertex, coalesced);
+ * with path records ON it writes and reads the reference's Path records (renderer.py:58,79) instead, so that
+ * CLV_BUF_LIGHT_PATHS / CLV_BUF_CAMERA_PATHS can be read back and compared.  Results are the same bits either way. */
+CLV_API int clv_renderer_set_path_records(clv_renderer *r, int enabled);
 /* work counters accumulated by kernels launched while counting is enabled (instrumented variants; the timed kernels
  * carry no counter code).  Two classes of five words: out[0..4] random-walk / traversal kernels, out[5..9] connection
  * kernels; per class: rays = traverse_bvh invocations the reference would make, traversals actually started,

@@ -80,7 +80,9 @@ static void gen_paths(uint32_t n, const Ray *rays, const EmuAccel *a, const Mate
         for (int64_t id = 0; id < (int64_t)n; id++) {
             uint32_t s0 = rnd[2 * id], s1 = rnd[2 * id + 1];
             V4 uni;
-            random_walk<MODE, true>(rays[id], a->view, mats, s0, s1, paths + id, &uni, cnt);
+            AosSink sink;
+            sink.path = paths + id;
+            random_walk<MODE, true>(rays[id], a->view, mats, s0, s1, sink, &uni, cnt);
             out[id] = uni;
             if (debug) debug[id] = v4(100.0f, 100.0f, 100.0f, 100.0f);
             rnd[2 * id] = s0; rnd[2 * id + 1] = s1;
@@ -105,8 +107,8 @@ static void connect(uint32_t n, const Path *cp, const Path *lp, const EmuAccel *
             float scratch[CLV_CONNECT_SCRATCH];
             TArr S;
             S.base = scratch; S.stride = 1;
-            connect_sample<MODE, SPLAT, true>((uint32_t)id, (uint32_t)id, (uint32_t)id, cp, lp, a->view, mats, cam[0],
-                                              aggs, out, sink, S, cnt);
+            connect_sample<MODE, SPLAT, true>(aos_paths(cp, lp, (uint32_t)id), (uint32_t)id, (uint32_t)id, a->view, mats,
+                                              cam[0], aggs, out, sink, S, cnt);
         }
         merge(cnt);
     }
@@ -185,11 +187,13 @@ EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAc
     }
 }
 
-/* one fused pass exactly as clv_renderer_run_sample launches it: walks -> connect (splat) -> finalize+accumulate */
-EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
-                           const int32_t *lti, int light_count, const Material *mats, const Camera *cam,
-                           const EmuAccel *a, uint32_t *seeds, Path *light_paths, Path *camera_paths,
-                           WeightAggregator *aggs, V4 *light_image, Accum *accum, int mode) {
+/* one fused pass exactly as clv_renderer_run_sample launches it: walks -> connect (splat) -> finalize+accumulate.
+ * soa != NULL selects the renderer's compact SoA vertex records (soa: V4[2*6*4*n_local], soa_len: int32[2*n_local]),
+ * otherwise the reference's Path records are used. */
+template <int MODE, bool SOA>
+static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
+                       const int32_t *lti, int light_count, const Material *mats, const Camera *cam, const EmuAccel *a,
+                       uint32_t *seeds, PathStore store, WeightAggregator *aggs, V4 *light_image, Accum *accum) {
     uint32_t n_pixels = (uint32_t)(cam[0].pixel_width * cam[0].pixel_height);
 #pragma omp parallel
     {
@@ -198,12 +202,8 @@ EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const T
         for (int64_t id = 0; id < (int64_t)n_local; id++) {
             uint32_t gid = sample_ids ? sample_ids[id] : (uint32_t)id;
             uint32_t s0 = seeds[2 * id], s1 = seeds[2 * id + 1];
-            if (mode == TRAVERSE_REFERENCE)
-                fused_walk_sample<TRAVERSE_REFERENCE, true>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0],
-                                                            a->view, s0, s1, light_paths, camera_paths, accum, cnt);
-            else
-                fused_walk_sample<TRAVERSE_ORDERED, true>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0],
-                                                          a->view, s0, s1, light_paths, camera_paths, accum, cnt);
+            fused_walk_sample<MODE, true, SOA>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0], a->view, s0, s1,
+                                               store, accum, cnt);
             seeds[2 * id] = s0; seeds[2 * id + 1] = s1;
         }
         LightSink sink;
@@ -216,15 +216,30 @@ EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const T
             float scratch[CLV_CONNECT_SCRATCH];
             TArr S;
             S.base = scratch; S.stride = 1;
-            if (mode == TRAVERSE_REFERENCE)
-                connect_sample<TRAVERSE_REFERENCE, true, true>((uint32_t)id, (uint32_t)id, gid, camera_paths, light_paths,
-                                                               a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
-            else
-                connect_sample<TRAVERSE_ORDERED, true, true>((uint32_t)id, (uint32_t)id, gid, camera_paths, light_paths,
-                                                             a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
+            if (SOA) {
+                SoaPaths P;
+                P.v = store.soa; P.len = store.soa_len; P.n = store.n; P.slot = (uint32_t)id; P.pixel0 = (int32_t)gid;
+                connect_sample<MODE, true, true>(P, (uint32_t)id, gid, a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
+            } else {
+                connect_sample<MODE, true, true>(aos_paths(store.camera_paths, store.light_paths, (uint32_t)id), (uint32_t)id,
+                                                 gid, a->view, mats, cam[0], aggs, nullptr, sink, S, cnt);
+            }
         }
 #pragma omp for schedule(static)
         for (int64_t id = 0; id < (int64_t)n_pixels; id++) fused_finalize_pixel((uint32_t)id, aggs, cam[0], light_image, accum);
         merge(cnt);
     }
+}
+EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
+                           const int32_t *lti, int light_count, const Material *mats, const Camera *cam,
+                           const EmuAccel *a, uint32_t *seeds, Path *light_paths, Path *camera_paths,
+                           WeightAggregator *aggs, V4 *light_image, Accum *accum, int mode, V4 *soa, int32_t *soa_len) {
+    PathStore store;
+    memset(&store, 0, sizeof store);
+    store.light_paths = light_paths; store.camera_paths = camera_paths; store.soa = soa; store.soa_len = soa_len;
+    store.n = n_local;
+#define GO(M, SO) fused_pass<M, SO>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, aggs, light_image, accum)
+    if (soa) { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, true); else GO(TRAVERSE_ORDERED, true); }
+    else { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, false); else GO(TRAVERSE_ORDERED, false); }
+#undef GO
 }

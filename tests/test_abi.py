@@ -73,3 +73,19 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(root, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", text, re.M), f
                 assert "trace_ref" not in text or f.endswith((".cuh", ".h", ".cu")), f
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` runs on CPU (the oracle on all host threads): check the JSON line's schema."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--config", "c1",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "bdpt_msamples_per_s" and line["unit"] == "Msamples/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]

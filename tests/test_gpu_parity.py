@@ -165,7 +165,7 @@ def test_fused_renderer_vs_oracle(dev, preset, w, h):
     ref = OracleRenderer(a, seeds, shared_math=True)
     ref.oracle.counters_reset()
     sc = scene.scene_from_arrays(a, dev)
-    r = Renderer(sc, seeds=seeds)
+    r = Renderer(sc, seeds=seeds, path_records=True)
     dev.counters(reset=True)
     dev.counters_enable(True)
     for _ in range(3):
@@ -198,7 +198,7 @@ def test_fused_reference_order_mode_gives_same_paths(dev):
     sc = scene.scene_from_arrays(a, dev)
     outs = []
     for mode in MODES:
-        r = Renderer(sc, seeds=seeds, traverse_mode=mode)
+        r = Renderer(sc, seeds=seeds, traverse_mode=mode, path_records=True)
         r.run_sample()
         r.run_sample()
         outs.append((r._fr.read(runtime.BUF_CAMERA_PATHS, T.Path, w * h), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * w * h)))
@@ -413,7 +413,7 @@ def test_ragged_frame_size_partial_warps(dev):
     seeds = seeds_for(b)
     ref = OracleRenderer(a, seeds, shared_math=True)
     sc = scene.scene_from_arrays(a, dev)
-    r = Renderer(sc, seeds=seeds)
+    r = Renderer(sc, seeds=seeds, path_records=True)
     for _ in range(2):
         ref.run_sample()
         r.run_sample()
@@ -423,7 +423,7 @@ def test_ragged_frame_size_partial_warps(dev):
     np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
     np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=5e-5, atol=1e-6)
     ids = np.arange(5, b, 12, dtype=np.uint32)
-    part = Renderer(sc, seeds=seeds, sample_ids=ids)
+    part = Renderer(sc, seeds=seeds, sample_ids=ids, path_records=True)
     part.run_sample()
     got = part._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * len(ids)).reshape(-1, 2)
     one = OracleRenderer(a, seeds, shared_math=True)
@@ -443,7 +443,7 @@ def test_every_material_branch_bit_exact(dev):
     seeds = seeds_for(b, seed=77)
     ref = OracleRenderer(a, seeds, shared_math=True)
     sc = scene.scene_from_arrays(a, dev)
-    r = Renderer(sc, seeds=seeds)
+    r = Renderer(sc, seeds=seeds, path_records=True)
     for _ in range(3):
         ref.run_sample()
         r.run_sample()
@@ -454,5 +454,30 @@ def test_every_material_branch_bit_exact(dev):
     assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3), "uni")
     np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=5e-5, atol=1e-6)
     np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    r.release()
+    sc.release()
+
+
+@pytest.mark.parametrize("preset,w,h", SCENES)
+def test_default_soa_vertex_records_vs_oracle(dev, preset, w, h):
+    """The default fused renderer keeps path vertices in its compact SoA records: RNG streams, aggregators and the
+    unidirectional image must equal the oracle bit for bit, exactly as with the reference's Path records."""
+    a = arrays(preset, w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=31)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(3):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3), "uni")
+    assert np.array_equal(ref.summed_sample_counts, r.summed_sample_counts)
+    np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    with pytest.raises(runtime.CliveError):  # Path records are not kept unless asked for
+        r._fr.read(runtime.BUF_CAMERA_PATHS, T.Path, b)
     r.release()
     sc.release()

@@ -282,3 +282,34 @@ def test_adversarial_rays_through_vertices_and_edges(O, E):
     rel = np.abs(t[both] - t_o[both]) / t[both]
     assert np.median(rel) < 1e-6 and rel.max() < 1e-3, (float(np.median(rel)), float(rel.max()))
     print(f"ordered-vs-reference disagreement on vertex/edge rays: {int(mm.sum())} of {n}")
+
+
+@pytest.mark.parametrize("preset,w,h", [("bench-spheres", 40, 30)])
+def test_soa_vertex_records_give_the_same_bits_as_path_records(E, preset, w, h):
+    """The fused renderer's compact SoA vertex layout vs the reference's Path records: identical RNG streams,
+    aggregators and accumulators apart from the atomic summation order of the light image."""
+    a = arrays(preset, w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=9)
+    acc = E.accel(a.boxes, a.triangles)
+    outs = []
+    try:
+        for use_soa in (False, True):
+            s = seeds.copy()
+            lp, cp = np.zeros(b, T.Path), np.zeros(b, T.Path)
+            aggs = np.zeros(b, T.WeightAggregator)
+            li = np.zeros((b, 4), np.float32)
+            accum = np.zeros((b, 8), np.float32)
+            soa = np.zeros((2 * 6 * 4 * b, 4), np.float32) if use_soa else None
+            soa_len = np.zeros(2 * b, np.int32) if use_soa else None
+            for _ in range(3):
+                E.fused_pass(a, acc, s, lp, cp, aggs, li, accum, soa=soa, soa_len=soa_len)
+            outs.append((s, aggs, accum, lp, soa_len))
+    finally:
+        E.accel_destroy(acc)
+    (s0, g0, a0, lp0, _), (s1, g1, a1, _, len1) = outs
+    assert_bits_equal(s0, s1, "RNG state")
+    assert_bits_equal(g0, g1, "aggregators")
+    assert_bits_equal(a0[:, 4:8].copy(), a1[:, 4:8].copy(), "unidirectional + counts")
+    np.testing.assert_allclose(a1[:, 0:4], a0[:, 0:4], rtol=2e-4, atol=1e-6)
+    assert np.array_equal(len1[:b], lp0["length"])  # SoA lengths: [light | camera]
