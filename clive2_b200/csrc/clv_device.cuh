@@ -53,6 +53,9 @@
 #ifndef CLV_WIDE_OCCLUSION
 #define CLV_WIDE_OCCLUSION 1
 #endif
+#ifndef CLV_TRI_TEST_BRANCHLESS
+#define CLV_TRI_TEST_BRANCHLESS 0
+#endif
 #ifndef CLV_WALK_INNER_BURST
 #define CLV_WALK_INNER_BURST 0 /* closest_hit, while-while form: 0 = walk down to the leaf, n > 0 = at most n node steps per round */
 #endif
@@ -228,6 +231,16 @@ CLV_HD bool tri_test(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float &t_out, float &u, fl
     float f = 1.0f / a;
     V3 s = o - v0;
     u = f * dot(s, h);
+#if CLV_TRI_TEST_BRANCHLESS
+    /* same predicate, evaluated at the end: the lanes of a warp test different triangles, so the early returns of the
+     * reference only add divergence (if one lane goes on, the warp pays for the rest of the test anyway) */
+    V3 q = cross(s, e1);
+    v = f * dot(d, q);
+    float t = f * dot(e2, q);
+    bool hit = !(u < 0 || u > 1) && !(v < 0 || u + v > 1) && t > CLV_DELTA;
+    if (hit) t_out = t;
+    return hit;
+#else
     if (u < 0 || u > 1) return false;
     V3 q = cross(s, e1);
     v = f * dot(d, q);
@@ -235,6 +248,7 @@ CLV_HD bool tri_test(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float &t_out, float &u, fl
     float t = f * dot(e2, q);
     if (t > CLV_DELTA) { t_out = t; return true; }
     return false;
+#endif
 }
 
 enum { TRAVERSE_REFERENCE = 0, TRAVERSE_ORDERED = 1 };
