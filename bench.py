@@ -131,6 +131,7 @@ def oracle_passes(arrays, seeds, n_passes):
     """Seconds per pass of the C transcription (glibc build, all host threads) over `n_passes` passes."""
     from oracle.oracle import OracleRenderer
     r = OracleRenderer(arrays, seeds, shared_math=False)
+    r.oracle.use_all_cores()
     times = []
     for _ in range(n_passes):
         t0 = time.perf_counter()
@@ -169,6 +170,7 @@ def run_reference(args, cfg, rank):
     batch = width * height
     from oracle.oracle import OracleRenderer
     r = OracleRenderer(arrays, seeds_for(batch, 0), shared_math=False)
+    threads = r.oracle.use_all_cores()
     for _ in range(args.warmup):
         r.run_sample()
     t0 = time.perf_counter()

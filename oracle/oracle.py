@@ -60,6 +60,15 @@ class Oracle:
     def num_threads(self):
         return int(self.lib.ref_num_threads())
 
+    def use_all_cores(self):
+        """Run on every host core even when the launcher (torchrun) exported OMP_NUM_THREADS=1."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        self.lib.ref_set_num_threads(C.c_int(n))
+        return self.num_threads
+
     # ---- the eight kernels, reference positional order ----------------------------------------------------------
     def _call(self, fn, n, *args):
         conv = []

@@ -1278,6 +1278,15 @@ EXPORT void *ref_renderer_buffer(RefRenderer *r, const char *name, uint64_t *nby
     return NULL;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use all host cores */
+EXPORT void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 EXPORT int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
