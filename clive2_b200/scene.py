@@ -33,6 +33,27 @@ class SceneArrays:
     camera_triangle_indices: np.ndarray  # int32[n_camera_tris]
 
 
+_SOUP_CACHE = {}
+
+
+def _mesh_soup_cached(spec):
+    """`_mesh_soup` memoised per (mesh source, scale, offset, material): the movie driver rebuilds the scene for every
+    frame (movie.py:29-55) although only the camera moves; loading and smoothing the meshes once removes most of the
+    per-frame host work (the BVH itself is rebuilt: the sensor triangles are part of it and shape it)."""
+    mesh = spec.get("mesh")
+    if "file_path" not in spec and not callable(mesh):
+        return _mesh_soup(spec)  # in-memory arrays: no identity that is safe to key on
+    src = spec.get("file_path") or mesh  # a preset's generator function object (kept alive by the preset table)
+    key = (src, float(spec.get("scale", 1.0)), tuple(np.asarray(spec.get("offset", ZERO_VECTOR), dtype=np.float64).tolist()),
+           int(spec.get("material", 0)))
+    soup = _SOUP_CACHE.get(key)
+    if soup is None:
+        if len(_SOUP_CACHE) > 16:
+            _SOUP_CACHE.clear()
+        soup = _SOUP_CACHE[key] = _mesh_soup(spec)
+    return soup
+
+
 def _mesh_soup(spec):
     """One entry of `file_specs` -> soup.  Besides the reference's `file_path` (.obj/.ply, scene.py:49-66) a spec may
     carry an in-memory mesh as `mesh=(vertices, faces)`; scale/offset/material mean the same in both cases."""
@@ -57,7 +78,7 @@ def build_scene_arrays(pixel_width=1280, pixel_height=720, cam_center=ZERO_VECTO
     # sensor triangles first, then the enclosure: this order fixes the soup order the BVH build starts from
     soup = FastTreeBox.from_triangle_objects(camera_geometry(camera) + triangles_for_box())
     for spec in file_specs or ():
-        soup = soup + _mesh_soup(spec)
+        soup = soup + _mesh_soup_cached(spec)
     boxes, triangles = build_flat_bvh(soup, builder=bvh_builder, sort_kind=sort_kind)
 
     is_light = triangles["is_light"] != 0
