@@ -43,7 +43,12 @@ def _mesh_soup_cached(spec):
     mesh = spec.get("mesh")
     if "file_path" not in spec and not callable(mesh):
         return _mesh_soup(spec)  # in-memory arrays: no identity that is safe to key on
-    src = spec.get("file_path") or mesh  # a preset's generator function object (kept alive by the preset table)
+    if "file_path" in spec:
+        import os
+        path = spec["file_path"]
+        src = (path, os.path.getmtime(path) if os.path.exists(path) else None)
+    else:
+        src = mesh  # a preset's generator function object (kept alive by the preset table)
     key = (src, float(spec.get("scale", 1.0)), tuple(np.asarray(spec.get("offset", ZERO_VECTOR), dtype=np.float64).tolist()),
            int(spec.get("material", 0)))
     soup = _SOUP_CACHE.get(key)
