@@ -973,7 +973,7 @@ struct clv_renderer {
     uint8_t *d_tone_image;
     std::vector<uint32_t> sample_ids;
     unsigned long long passes;
-    /* optional per-kernel timing: events around each of the three kernels of every pass */
+    /* optional per-kernel timing: events around each of the five kernels of every pass */
     int timing;
     std::vector<cudaEvent_t> events; /* CLV_PASS_EVENTS per pass: before walks, after each of the five kernels */
     double kernel_ms[CLV_PASS_KERNELS];

@@ -406,7 +406,7 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
  * lexicographically smaller (t, rank)", an any-hit search bounded by t from the start.  Unlike the closest-hit search
  * the bound never shrinks, so the stack holds node refs only and a box is pruned when it is pushed.
  * The search is resumable (one round = walk down to the next leaf, test it, pop) so that a warp can keep all lanes
- * busy by handing a finished lane the next ray of its task list (k_connect_paths). */
+ * busy by handing a finished lane the next ray of its task list (k_connect_rays). */
 struct OccRay { /* scalars only, so that they live in registers; the node stack is a separate local array */
     V3 o, d, inv;
     float t_bound;

@@ -154,7 +154,7 @@ def test_bad_bvh_arrays_are_rejected(E):
 
 
 def test_fused_pass_matches_oracle_renderer(E):
-    """clv_renderer_run_sample's three kernels vs the reference's eight stages (oracle): everything that does not go
+    """clv_renderer_run_sample's kernel sequence vs the reference's eight stages (oracle): everything that does not go
     through the atomically splatted light image is bit exact; the image agrees to float-summation-order tolerance."""
     w = h = 40
     a = arrays("empty", w, h)
