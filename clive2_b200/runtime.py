@@ -358,6 +358,16 @@ class Device:
         _check(self.lib.clv_visibility(self.ctx, accel.handle, _host_ptr(a), _host_ptr(b), len(a), mode, _host_ptr(out)))
         return out
 
+    def light_image_splat(self, n_entries, n_pixels, light_paths, materials, pixel_indices, path_indices, ray_indices,
+                          weights, shades, light_image, sum_weights):
+        """Device-side replacement of sort + `light_bins()` + `light_image_gather` on the UNSORTED light entries written
+        by `connect_paths` (clv_light_image_splat): same sums, atomic order."""
+        A = _Args(self)
+        _check(self.lib.clv_light_image_splat(self.ctx, int(n_entries), int(n_pixels), A.ptr(light_paths), A.ptr(materials),
+                                              A.ptr(pixel_indices), A.ptr(path_indices), A.ptr(ray_indices),
+                                              A.ptr(weights), A.ptr(shades), A.ptr(light_image), A.ptr(sum_weights)))
+        A.done()
+
     def release(self):
         for acc in list(getattr(self, "_accels", {}).values()):
             acc.release()

@@ -481,3 +481,29 @@ def test_default_soa_vertex_records_vs_oracle(dev, preset, w, h):
         r._fr.read(runtime.BUF_CAMERA_PATHS, T.Path, b)
     r.release()
     sc.release()
+
+
+def test_light_image_splat_equals_sort_and_gather(dev):
+    """clv_light_image_splat (atomics on the unsorted entries) vs the reference's bitonic sort + host bins + gather."""
+    w, h = 48, 40
+    a = arrays("empty", w, h)
+    b = w * h
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, fused=False, seeds=seeds_for(b, seed=12))
+    r.make_light_rays(); r.make_camera_rays(); r.trace_light_rays(); r.trace_camera_rays(); r.join_paths()
+    r.finalize_samples()
+    n = len(r.out_light_indices.numpy(np.int32))
+    splat_image = dev.buffer(b * 16)
+    splat_weights = dev.buffer(r.sample_weights.numpy(np.float32))  # finalize's weights, as gather adds onto them
+    dev.light_image_splat(n, b, r.out_light_paths, sc.materials, r.out_light_indices, r.out_light_path_indices,
+                          r.out_light_ray_indices, r.out_light_weights, r.out_light_shade, splat_image, splat_weights)
+    r.gather_light_image()  # sorts the entries in place, bins on the host, gathers
+    ref_img = r.out_light_image.numpy(np.float32).reshape(b, 4)
+    ref_w = r.sample_weights.numpy(np.float32)
+    got_img = splat_image.numpy(np.float32).reshape(b, 4)
+    assert (ref_img[:, 3] == 1).all() and (got_img[:, 3] == 1).all()
+    assert (ref_img[:, :3] > 0).any()
+    np.testing.assert_allclose(got_img[:, :3], ref_img[:, :3], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(splat_weights.numpy(np.float32), ref_w, rtol=1e-5, atol=1e-7)
+    r.release()
+    sc.release()
