@@ -5,7 +5,8 @@
     torchrun --nproc-per-node 8 -m clive2_b200.movie movie --scene bench-spheres --movie-frames 120 --samples 32
 
 Frames of a movie are independent (the reference rebuilds scene + BVH + renderer per frame, movie.py:29-55), so frame f
-goes to rank f mod world_size and no collective is needed.  PNGs are written with cv2 when it is importable, else as
+goes to rank f mod world_size and no collective is needed; within a rank the host work of neighbouring frames (scene
+arrays + BVH of the next one, PNG encode of the previous one) overlaps the GPU's passes of the current one.  PNGs are written with cv2 when it is importable, else as
 .npy arrays.
 """
 import argparse
@@ -15,7 +16,8 @@ import time
 import numpy as np
 
 from . import runtime, scene
-from .renderer import Renderer
+from .camera import tone_map
+from .renderer import TONE_MAP_EXPOSURE, Renderer
 
 
 def frames_for_rank(start_frame, total_frames, rank, world):
@@ -33,21 +35,63 @@ def write_image(path, image_bgr_u8):
         return path + ".npy"
 
 
-def render_frame(device, preset, width, height, samples, frame_idx=None, total_frames=None, seed=None):
-    """One image: scene (+ orbit camera when frame_idx is given) -> BVH -> `samples` fused passes -> tone-mapped BGR."""
+def frame_arrays(preset, width, height, frame_idx=None, total_frames=None):
+    """Host side of one frame: scene arrays + BVH (native builder; releases the GIL, so it overlaps a running render)."""
     if frame_idx is None:
-        arrays = scene.preset_arrays(preset, width, height)
-    else:
-        center, direction = scene.orbit_camera(frame_idx, total_frames)
-        arrays = scene.preset_arrays(preset, width, height, center, direction)
+        return scene.preset_arrays(preset, width, height)
+    center, direction = scene.orbit_camera(frame_idx, total_frames)
+    return scene.preset_arrays(preset, width, height, center, direction)
+
+
+def render_arrays(device, arrays, samples, seed=None, raw=False):
+    """Device side of one frame: upload -> `samples` fused passes -> tone-mapped BGR (`raw`: the packed float
+    accumulators [H][W][8] instead, for `image_from_accumulators` on another thread)."""
     sc = scene.scene_from_arrays(arrays, device)
     r = Renderer(sc, seed=seed)
     for _ in range(samples):
         r.run_sample()
-    image = r.image
+    result = r._accum() if raw else r.image
     r.release()
     sc.release()  # also drops the per-frame BVH cached for these buffers
-    return image
+    return result
+
+
+def image_from_accumulators(a):
+    """`Renderer.image` (renderer.py:293-300 of the reference) from the packed accumulators of `render_arrays(raw=True)`."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        est = a[:, :, 0:3] / a[:, :, 3:4]
+    return tone_map(np.nan_to_num(est, neginf=0, posinf=0), exposure=TONE_MAP_EXPOSURE)
+
+
+def render_frame(device, preset, width, height, samples, frame_idx=None, total_frames=None, seed=None):
+    """One image: scene (+ orbit camera when frame_idx is given) -> BVH -> `samples` fused passes -> tone-mapped BGR."""
+    return render_arrays(device, frame_arrays(preset, width, height, frame_idx, total_frames), samples, seed)
+
+
+def render_movie(device, preset, width, height, samples, frames, total_frames, seed=None, sink=None, overlap=True):
+    """Frames `frames` of the orbit movie, in order; `sink(frame_idx, image)` receives each image (e.g. the PNG
+    writer).  The reference does scene + BVH + render + imwrite serially per frame (movie.py:29-55); here the host
+    work is taken off the GPU's critical path: while frame f renders, one worker thread prepares the arrays and BVH
+    of the next frame and another tone-maps and encodes the previous image.  Images are identical to `render_frame`'s."""
+    frames = list(frames)
+    if not overlap:
+        for f in frames:
+            img = render_frame(device, preset, width, height, samples, f, total_frames, seed)
+            if sink is not None:
+                sink(f, img)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(1) as prep, ThreadPoolExecutor(1) as out:
+        pending = prep.submit(frame_arrays, preset, width, height, frames[0], total_frames) if frames else None
+        written = []
+        for k, f in enumerate(frames):
+            arrays = pending.result()
+            if k + 1 < len(frames):
+                pending = prep.submit(frame_arrays, preset, width, height, frames[k + 1], total_frames)
+            acc = render_arrays(device, arrays, samples, seed, raw=True)
+            written.append(out.submit(lambda f=f, acc=acc: sink and sink(f, image_from_accumulators(acc))))
+        for w in written:
+            w.result()  # surface writer errors
 
 
 def main(argv=None):
@@ -67,6 +111,7 @@ def main(argv=None):
             p.add_argument("--movie-frames", type=int, default=120)
             p.add_argument("--start-frame", type=int, default=0)
             p.add_argument("--out-dir", type=str, default="output")
+            p.add_argument("--serial", action="store_true", help="no overlap of host scene prep / PNG encode with the GPU")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = runtime.Device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -78,11 +123,21 @@ def main(argv=None):
         return
     out_dir = os.path.join(args.out_dir, args.movie_name)
     os.makedirs(out_dir, exist_ok=True)
-    for f in frames_for_rank(args.start_frame, args.movie_frames, rank, world):
-        t0 = time.time()
-        img = render_frame(dev, args.scene, args.width, args.height, args.samples, f, args.movie_frames, seed=args.seed)
+    stamp = [time.time()]
+
+    def sink(f, img):
         path = write_image(os.path.join(out_dir, f"frame_{f:04d}.png"), img)
-        print(f"rank {rank}: {path} in {time.time() - t0:.2f} s", flush=True)
+        now = time.time()
+        print(f"rank {rank}: {path} (+{now - stamp[0]:.2f} s)", flush=True)
+        stamp[0] = now
+
+    t0 = time.time()
+    mine = frames_for_rank(args.start_frame, args.movie_frames, rank, world)
+    render_movie(dev, args.scene, args.width, args.height, args.samples, mine, args.movie_frames, seed=args.seed,
+                 sink=sink, overlap=not args.serial)
+    if mine:
+        print(f"rank {rank}: {len(mine)} frames in {time.time() - t0:.2f} s = {(time.time() - t0) / len(mine):.3f} s/frame",
+              flush=True)
 
 
 if __name__ == "__main__":

@@ -507,3 +507,15 @@ def test_light_image_splat_equals_sort_and_gather(dev):
     np.testing.assert_allclose(splat_weights.numpy(np.float32), ref_w, rtol=1e-5, atol=1e-7)
     r.release()
     sc.release()
+
+
+def test_overlapped_movie_loop_equals_frame_by_frame(dev):
+    """render_movie (host prep / tone map + encode on worker threads, pooled device memory reused between frames)
+    gives the images render_frame gives."""
+    from clive2_b200.movie import render_frame, render_movie
+    frames = [0, 17, 45]
+    got = {}
+    render_movie(dev, "bench-spheres", 64, 36, 3, frames, 120, seed=5, sink=lambda f, img: got.__setitem__(f, img))
+    assert sorted(got) == frames
+    for f in frames:
+        assert np.array_equal(got[f], render_frame(dev, "bench-spheres", 64, 36, 3, frame_idx=f, total_frames=120, seed=5))

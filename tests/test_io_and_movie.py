@@ -66,3 +66,26 @@ def test_frames_are_dealt_round_robin():
 def test_orbit_camera_matches_reference_formula():
     c, d = scene.orbit_camera(30, 120)
     assert np.allclose(c, [7.5, 1.5, 0.0], atol=1e-12) and np.allclose(d, [-1.0, 0.0, 0.0], atol=1e-12)
+
+
+def test_render_movie_pipeline_keeps_frame_order_and_surfaces_writer_errors(monkeypatch):
+    """Host logic of the overlapped movie loop (no GPU: the two stages are stubbed)."""
+    import pytest
+    from clive2_b200 import movie
+    prepared = []
+    monkeypatch.setattr(movie, "frame_arrays", lambda preset, w, h, f, total: (prepared.append(f), {"frame": f})[1])
+    monkeypatch.setattr(movie, "render_arrays",
+                        lambda dev, arrays, samples, seed=None, raw=False: np.full((2, 2, 3), arrays["frame"], np.uint8))
+    monkeypatch.setattr(movie, "image_from_accumulators", lambda a: a)
+    for overlap in (False, True):
+        got = []
+        prepared.clear()
+        movie.render_movie(None, "x", 2, 2, 1, [3, 11, 19], 120, sink=lambda f, img: got.append((f, int(img[0, 0, 0]))),
+                           overlap=overlap)
+        assert got == [(3, 3), (11, 11), (19, 19)] and prepared == [3, 11, 19]
+    movie.render_movie(None, "x", 2, 2, 1, [], 120, sink=None)  # nothing to do
+
+    def bad_sink(f, img):
+        raise OSError("disk full")
+    with pytest.raises(OSError):
+        movie.render_movie(None, "x", 2, 2, 1, [0, 1], 120, sink=bad_sink)
