@@ -260,7 +260,6 @@ def run_ours(args, cfg, rank, local_rank, world):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    r._fr.kernel_timing(True)
     launches0 = dev.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -281,6 +280,12 @@ def run_ours(args, cfg, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
         dist.barrier()
+    # per-kernel durations for the roofline: K more passes of the same work with CUDA events between the kernels on the
+    # launch stream.  With events requested the pass runs as ONE slice on ONE stream (in the timed region above the
+    # slices of a pass overlap on several streams, where "the duration of a kernel" is not defined).
+    r._fr.kernel_timing(True)
+    for _ in range(K):
+        r.run_sample()
     kernel_ms, timed_passes = r._fr.kernel_times(reset=True)
     r._fr.kernel_timing(False)
 

@@ -52,6 +52,7 @@ extern "C" const char *clv_version(void) { return "clive_b200 0.1 (sm_100a, fmad
 /* ---------------------------------------------------------------------------------------------------------------
  * context + memory
  * ------------------------------------------------------------------------------------------------------------- */
+#define CLV_MAX_SLICES 8 /* <= 16: one task counter per slice in the 64-byte header of the connect scratch */
 struct clv_ctx {
     int device;
     cudaStream_t stream;
@@ -64,6 +65,12 @@ struct clv_ctx {
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
     void *cs_mem;
     uint32_t cs_capacity;
+    /* the fused pass runs as `pass_slices` independent slices of the samples, slice 0 on `stream`, the others on
+     * `slice_stream[]`, joined before the finalize kernel: the tail of one slice's kernel (SMs draining while the
+     * last blocks finish) is filled by blocks of another slice's kernel instead of idling */
+    int pass_slices;
+    cudaStream_t slice_stream[CLV_MAX_SLICES];
+    cudaEvent_t slice_fork, slice_join[CLV_MAX_SLICES];
 };
 
 extern "C" int clv_device_count(int *count) {
@@ -116,6 +123,20 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    /* 0 = automatic.  Measured: C2 (262 144 samples = 1.7 waves of resident threads) 1/2/3/4/6/8 slices ->
+     * 102.0/100.9/106.5/106.1/104.7/102.9 Msamples/s; C1 (65 536 samples, less than one wave) 125.7/119.8/119.7/119.2;
+     * C3 (1 M samples) 68.2/-/68.7/68.3.  Automatic = 3 slices from one full wave of samples up, else 1. */
+    c->pass_slices = getenv("CLV_PASS_SLICES") ? atoi(getenv("CLV_PASS_SLICES")) : 0;
+    if (c->pass_slices < 0) c->pass_slices = 0;
+    if (c->pass_slices > CLV_MAX_SLICES) c->pass_slices = CLV_MAX_SLICES;
+    CK(cudaEventCreateWithFlags(&c->slice_fork, cudaEventDisableTiming));
+    for (int k = 0; k < CLV_MAX_SLICES; k++) {
+        c->slice_stream[k] = nullptr;
+        c->slice_join[k] = nullptr;
+        if (k == 0) continue;
+        CK(cudaStreamCreateWithFlags(&c->slice_stream[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->slice_join[k], cudaEventDisableTiming));
+    }
     CK(dev_alloc(c, &c->d_counters, COUNTERS_CLASSES * sizeof(Counters)));
     CK(cudaMemsetAsync(c->d_counters, 0, COUNTERS_CLASSES * sizeof(Counters), c->stream));
     *out = c;
@@ -128,6 +149,12 @@ extern "C" int clv_ctx_destroy(clv_ctx *c) {
     cudaStreamSynchronize(c->stream);
     dev_free(c, c->d_counters);
     dev_free(c, c->cs_mem);
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->slice_fork);
+    for (int k = 1; k < CLV_MAX_SLICES; k++) {
+        if (c->slice_stream[k]) { cudaStreamSynchronize(c->slice_stream[k]); cudaStreamDestroy(c->slice_stream[k]); }
+        if (c->slice_join[k]) cudaEventDestroy(c->slice_join[k]);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
     return CLV_OK;
@@ -424,10 +451,10 @@ template <> struct PathViewOf<true> {
 
 template <int MODE, bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK)
-k_connect_enumerate(uint32_t n, PathStore store, AccelView A, const Material *materials,
+k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, const Material *materials,
                     const Camera *camera, ConnectScratch cs, Counters *counters) {
     __shared__ float cam_scratch[CLV_ENUM_SCRATCH * CLV_BLOCK];
-    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x; /* samples [first, n) of the launch's slice */
     const int lane = threadIdx.x & 31;
     Cnt<COUNT> cnt;
     unsigned long long cand = 0ull;
@@ -531,13 +558,13 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
 #endif
 template <bool SPLAT, bool COUNT, bool SOA>
 __global__ void CLV_FINISH_BOUNDS
-k_connect_finish(uint32_t n, const uint32_t *sample_ids, PathStore store,
+k_connect_finish(uint32_t first, uint32_t n, const uint32_t *sample_ids, PathStore store,
                  const Material *materials, const Camera *camera, ConnectScratch cs, WeightAggregator *aggs, V4 *out,
                  LightSink sink, Counters *counters) {
     __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
-    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
-    if (id == 0) *cs.task_count = 0u; /* every ray of this pass is done (stream order): reset the list for the next */
+    if (id == first) *cs.task_count = 0u; /* every ray of this pass is done (stream order): reset the list for the next */
     const unsigned warp_lanes = __ballot_sync(0xffffffffu, id < n);
     if (id < n) {
         Camera c = camera[0];
@@ -654,10 +681,10 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 #endif
 template <int MODE, bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK, CLV_WALK_MIN_BLOCKS)
-k_fused_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
+k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
               const int32_t *light_triangle_indices, int light_count, const Material *materials, const Camera *camera,
               AccelView A, uint32_t *seeds, PathStore store, Accum *accum, Counters *counters) {
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
     if (id < n_local) {
         Camera c = camera[0];
@@ -803,25 +830,27 @@ extern "C" int clv_set_stage_traverse_mode(int mode) {
     return CLV_OK;
 }
 
-/* enumerate -> rays -> finish on the context's stream */
-static int launch_connect(clv_ctx *c, int mode, bool splat, uint32_t n, const uint32_t *sample_ids, const PathStore &store,
+/* enumerate -> rays -> finish for the samples [first, n) on `stream`; `cs` holds this slice's own task list */
+static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat, uint32_t first, uint32_t n,
+                          const uint32_t *sample_ids, const PathStore &store,
                           bool soa, const AccelView &view, const Material *mats, const Camera *cam,
                           ConnectScratch cs, WeightAggregator *aggs, V4 *out, const LightSink &sink,
                           cudaEvent_t *mid_events /* NULL or 2 events: after enumerate, after rays */) {
     Counters *ctr = c->d_counters + COUNTERS_CONNECT;
-#define CALL(M, CT, SO) k_connect_enumerate<M, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, store, view, mats, cam, cs, ctr)
+    const uint32_t len = n - first;
+#define CALL(M, CT, SO) k_connect_enumerate<M, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, store, view, mats, cam, cs, ctr)
     DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
-    if (mid_events) CK(cudaEventRecord(mid_events[0], c->stream));
-    const uint64_t warps = ((uint64_t)n * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
+    if (mid_events) CK(cudaEventRecord(mid_events[0], stream));
+    const uint64_t warps = ((uint64_t)len * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
     const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
-#define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, c->stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
+#define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
     DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
-    if (mid_events) CK(cudaEventRecord(mid_events[1], c->stream));
-#define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
+    if (mid_events) CK(cudaEventRecord(mid_events[1], stream));
+#define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
     if (soa) {
         if (splat) { if (c->counting) FIN(true, true, true); else FIN(true, false, true); }
         else { if (c->counting) FIN(false, true, true); else FIN(false, false, true); }
@@ -901,7 +930,7 @@ extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, con
     store.camera_paths = (Path *)cp; /* read only here */
     store.light_paths = (Path *)lp;
     store.n = n;
-    return launch_connect(c, g_stage_mode, false, n, nullptr, store, false, accel->view,
+    return launch_connect(c, c->stream, g_stage_mode, false, 0u, n, nullptr, store, false, accel->view,
                           (const Material *)mats, (const Camera *)cam, cs, (WeightAggregator *)aggs, (V4 *)out, sink, nullptr);
 }
 
@@ -1135,20 +1164,38 @@ static int launch_pass(clv_renderer *r) {
     store.soa_len = r->d_soa_len;
     store.n = n;
     const bool soa = !r->path_records;
-#define CALL(M, CT, SO) k_fused_walks<M, CT, SO><<<GRID(n), CLV_BLOCK, 0, c->stream>>>(n, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters)
-    DISPATCH_MCS(r->mode, c->counting, soa, CALL);
-#undef CALL
-    LAUNCHED(c);
-    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], c->stream));
     LightSink sink;
     memset(&sink, 0, sizeof sink);
     sink.splat_image = r->d_light_image;
     sink.n_pixels = (int)r->n_pixels;
-    {
-        int rc = launch_connect(c, r->mode, true, n, ids, store, soa, r->accel->view, r->d_materials,
-                                r->d_camera, connect_scratch_at(r->d_connect_scratch, n), r->d_aggs, nullptr, sink,
-                                r->timing ? &r->events[ev0 + 2] : nullptr);
+    const ConnectScratch cs_all = connect_scratch_at(r->d_connect_scratch, n);
+    /* slices: whole blocks each; one slice (everything on the context's stream) when per-kernel events are wanted */
+    int slices = c->pass_slices > 0 ? c->pass_slices : (n >= (uint32_t)c->sm_count * 1024u ? 3 : 1);
+    if (r->timing) slices = 1;
+    uint32_t per = (uint32_t)(((uint64_t)n + slices - 1) / slices);
+    per = (per + CLV_BLOCK - 1) / CLV_BLOCK * CLV_BLOCK;
+    if (per == 0) per = CLV_BLOCK;
+    if (slices > 1) CK(cudaEventRecord(c->slice_fork, c->stream));
+    for (int k = 0; k < slices; k++) {
+        const uint32_t first = (uint32_t)std::min<uint64_t>((uint64_t)k * per, n), end = (uint32_t)std::min<uint64_t>((uint64_t)(k + 1) * per, n);
+        if (first >= end) continue;
+        cudaStream_t st = k == 0 ? c->stream : c->slice_stream[k];
+        if (k > 0) CK(cudaStreamWaitEvent(st, c->slice_fork, 0));
+#define CALL(M, CT, SO) k_fused_walks<M, CT, SO><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters)
+        DISPATCH_MCS(r->mode, c->counting, soa, CALL);
+#undef CALL
+        LAUNCHED(c);
+        if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], st));
+        ConnectScratch cs = cs_all;
+        cs.task_count = cs_all.task_count + k;
+        cs.tasks = cs_all.tasks + (size_t)first * 36;
+        int rc = launch_connect(c, st, r->mode, true, first, end, ids, store, soa, r->accel->view, r->d_materials,
+                                r->d_camera, cs, r->d_aggs, nullptr, sink, r->timing ? &r->events[ev0 + 2] : nullptr);
         if (rc != CLV_OK) return rc;
+        if (k > 0) {
+            CK(cudaEventRecord(c->slice_join[k], st));
+            CK(cudaStreamWaitEvent(c->stream, c->slice_join[k], 0));
+        }
     }
     if (r->timing) CK(cudaEventRecord(r->events[ev0 + 4], c->stream));
     k_fused_finalize<<<GRID(r->n_pixels), CLV_BLOCK, 0, c->stream>>>(r->n_pixels, r->d_aggs, r->d_camera, r->d_light_image, r->d_accum, r->d_pass_weight);
@@ -1443,6 +1490,13 @@ extern "C" int clv_counters_read(clv_ctx *c, uint64_t out[10], int reset) {
         o[4] = h[k].vertices;
     }
     if (reset) CK(cudaMemsetAsync(c->d_counters, 0, sizeof h, c->stream));
+    return CLV_OK;
+}
+extern "C" int clv_ctx_pass_slices(clv_ctx *c, int slices, int *current_out) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(slices <= CLV_MAX_SLICES, "at most 8 slices");
+    if (slices >= 0) c->pass_slices = slices;
+    if (current_out) *current_out = c->pass_slices;
     return CLV_OK;
 }
 extern "C" int clv_launch_count(clv_ctx *c, uint64_t *count) {

@@ -79,6 +79,7 @@ SIGNATURES = {
     "clv_counters_enable": [_vp, _int],
     "clv_counters_read": [_vp, C.POINTER(C.c_uint64), _int],
     "clv_launch_count": [_vp, C.POINTER(C.c_uint64)],
+    "clv_ctx_pass_slices": [_vp, _int, C.POINTER(C.c_int)],
     "clv_measure_read_bandwidth": [_vp, _sz, _int, C.POINTER(C.c_double)],
     "clv_renderer_kernel_timing": [_vp, _int],
     "clv_renderer_kernel_times": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), _int],
@@ -341,6 +342,20 @@ class Device:
         n = C.c_uint64()
         _check(self.lib.clv_launch_count(self.ctx, C.byref(n)))
         return int(n.value)
+
+    @property
+    def pass_slices(self):
+        """Number of independent sample slices (streams) a fused pass is launched as (4 * slices + 1 kernels per
+        pass); 0 = automatic (3 from one full wave of samples up, else 1)."""
+        n = C.c_int()
+        _check(self.lib.clv_ctx_pass_slices(self.ctx, -1, C.byref(n)))
+        return int(n.value)
+
+    @pass_slices.setter
+    def pass_slices(self, slices):
+        if int(slices) < 0:
+            raise ValueError("pass_slices must be >= 0 (0 = automatic)")
+        _check(self.lib.clv_ctx_pass_slices(self.ctx, int(slices), None))
 
     def traverse(self, accel, rays, mode=TRAVERSE_ORDERED):
         rays = np.ascontiguousarray(rays, dtype=T.Ray)

@@ -264,6 +264,12 @@ CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_
 CLV_API int clv_measure_read_bandwidth(clv_ctx *ctx, size_t nbytes, int iters, double *gbs_out);
 /* number of kernel launches issued on this context so far */
 CLV_API int clv_launch_count(clv_ctx *ctx, uint64_t *count);
+/* The fused pass runs the walk and connection kernels as `slices` independent slices of the samples on `slices`
+ * streams and joins them before the finalize kernel (4 * slices + 1 launches per pass): blocks of one slice's kernel
+ * fill the SMs that drain at the end of another's.  1..8 = fixed; 0 = automatic (the default; env CLV_PASS_SLICES):
+ * 3 slices when a pass has at least one full wave of samples (1024 per SM), else 1.  Results do not depend on it (the
+ * atomic summation order of the light image aside).  `slices` < 0 only queries the configured value. */
+CLV_API int clv_ctx_pass_slices(clv_ctx *ctx, int slices, int *current_out);
 
 #ifdef __cplusplus
 }

@@ -296,7 +296,9 @@ def test_full_size_properties(dev):
     for _ in range(4):
         r.run_sample()
     dev.synchronize()
-    assert dev.launch_count - n0 == 4 * len(runtime.FusedRenderer.KERNELS)  # five kernels per pass
+    # walks + three connection kernels per slice of the samples, one finalize kernel per pass
+    per_pass, rem = divmod(dev.launch_count - n0, 4)
+    assert rem == 0 and (per_pass - 1) % (len(runtime.FusedRenderer.KERNELS) - 1) == 0 and 5 <= per_pass <= 33
     assert (r.summed_sample_counts == 4).all()
     img = r.summed_image
     assert np.isfinite(img).all() and (img >= 0).all()
@@ -519,3 +521,32 @@ def test_overlapped_movie_loop_equals_frame_by_frame(dev):
     assert sorted(got) == frames
     for f in frames:
         assert np.array_equal(got[f], render_frame(dev, "bench-spheres", 64, 36, 3, frame_idx=f, total_frames=120, seed=5))
+
+
+def test_pass_slices_do_not_change_the_result(dev):
+    """The fused pass split into 1, 3 or 5 independently launched slices of the samples (ragged last slice, a slice
+    count that leaves some slices empty at this size): same RNG streams, same aggregators, same unidirectional image."""
+    w, h = 50, 37  # 1850 samples: not a multiple of the block size
+    a = arrays("bench-spheres", w, h)
+    sc = scene.scene_from_arrays(a, dev)
+    before = dev.pass_slices
+    results = []
+    try:
+        for slices in (1, 3, 5, 8):
+            dev.pass_slices = slices
+            assert dev.pass_slices == slices
+            r = Renderer(sc, seed=21)
+            for _ in range(3):
+                r.run_sample()
+            results.append((r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * w * h), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, w * h),
+                            np.array(r.unidirectional_image_buffer), np.array(r.summed_image), np.array(r.summed_sample_counts)))
+            r.release()
+    finally:
+        dev.pass_slices = before
+    for other in results[1:]:
+        assert np.array_equal(other[0], results[0][0])
+        assert_bits_equal(results[0][1], other[1], "aggregators")
+        assert np.array_equal(other[2].view(np.uint32), results[0][2].view(np.uint32))
+        assert np.array_equal(other[4], results[0][4])
+        np.testing.assert_allclose(other[3], results[0][3], rtol=5e-4, atol=1e-6)
+    sc.release()
