@@ -911,6 +911,7 @@ extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, con
                                  int32_t *pix, int32_t *path, int32_t *ray, float *w, float *shade) {
     REQUIRE(c && cp && lp && accel && mats && cam && aggs && out && pix && path && ray && w && shade, "null");
     if (!n) return CLV_OK;
+    REQUIRE(n < (1u << 26), "more than 2^26 samples per dispatch (connection tasks are sample << 6 | strategy)");
     CK(cudaSetDevice(c->device));
     LightSink sink;
     memset(&sink, 0, sizeof sink);
@@ -1074,6 +1075,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     uint32_t n_pixels = (uint32_t)cam->pixel_width * (uint32_t)cam->pixel_height;
     if (!h_sample_ids) n_local = n_pixels;
     REQUIRE(n_local > 0 && n_local <= n_pixels, "bad n_local");
+    REQUIRE(n_local < (1u << 26), "more than 2^26 samples per pass (connection tasks are sample << 6 | strategy)");
     if (h_sample_ids)
         for (uint32_t i = 0; i < n_local; i++) REQUIRE(h_sample_ids[i] < n_pixels, "sample id out of range");
 

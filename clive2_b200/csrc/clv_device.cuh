@@ -414,6 +414,9 @@ struct OccRay { /* scalars only, so that they live in registers; the node stack 
     int cur, sp;
 };
 enum { OCC_RUNNING = 0, OCC_CLEAR = 1, OCC_BLOCKED = 2 };
+#ifndef CLV_OCC_LEAF_BURST
+#define CLV_OCC_LEAF_BURST 0
+#endif
 
 template <bool COUNT>
 CLV_HD int occ_begin(const AccelView &A, OccRay &r, Cnt<COUNT> &cnt) {
@@ -533,7 +536,14 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
     int code = ~r.cur;
     int first = code >> 4, count = code & 15;
     bool blocked = false;
-    for (int i = first; i < first + count; i++) {
+#if CLV_OCC_LEAF_BURST > 0
+    /* at most CLV_OCC_LEAF_BURST triangles per step; the rest of the leaf stays in `cur` as a shorter leaf.  The lanes
+     * of a warp hold leaves of 1..15 triangles: with whole leaves per step the short ones wait for the longest */
+    const int here = count < CLV_OCC_LEAF_BURST ? count : CLV_OCC_LEAF_BURST;
+#else
+    const int here = count;
+#endif
+    for (int i = first; i < first + here; i++) {
         const V4 *tp = A.tris + 3 * (size_t)i;
         V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
         cnt.tri();
@@ -543,6 +553,7 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
             blocked = true;
     }
     if (blocked) return OCC_BLOCKED;
+    if (here < count) { r.cur = ~(((first + here) << 4) | (count - here)); return OCC_RUNNING; }
     if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
     return OCC_CLEAR;
 }

@@ -99,7 +99,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("CLV_LIBRARY") or _LIB_PATH  # CLV_LIBRARY: a differently configured build (tools/variants.sh)
     if not os.path.exists(p):
         raise CliveError(f"{p} is missing: build it with `python -m clive2_b200.build` (nvcc, sm_100a). "
                          "clive2_b200 has no CPU execution path.")
