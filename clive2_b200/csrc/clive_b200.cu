@@ -681,9 +681,6 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 /* stages 1-4: both ray generators and both random walks of one sample, RNG streams in the reference's order
  * (light gen, camera gen, light walk, camera walk; renderer.py:281-285) */
 /* measured at C2: 1.36 ms unbounded (94 regs), 1.19 ms at 6 blocks/SM (80 regs), 1.07 ms at 8 (64 regs, some spills) */
-#ifndef CLV_WALK_DECOUPLED
-#define CLV_WALK_DECOUPLED 0 /* 1: fused_walk_sample_decoupled (steps scheduled by warp votes) */
-#endif
 #ifndef CLV_WALK_MIN_BLOCKS
 #define CLV_WALK_MIN_BLOCKS (1024 / CLV_BLOCK) /* = 64 registers per thread */
 #endif
@@ -694,20 +691,6 @@ k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, cons
               AccelView A, uint32_t *seeds, PathStore store, Accum *accum, Counters *counters) {
     uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
-#if CLV_WALK_DECOUPLED
-    /* the warp schedules the steps of its 32 samples together: every lane takes part in the votes */
-    const bool valid = id < n_local;
-    Camera c = camera[0];
-    uint32_t gid = 0, seed0 = 1, seed1 = 1;
-    if (valid) {
-        gid = sample_ids ? sample_ids[id] : id;
-        uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
-        seed0 = sd.x; seed1 = sd.y;
-    }
-    fused_walk_sample_decoupled<MODE, COUNT, SOA>(valid, id, gid, light_triangles, surface_areas, light_triangle_indices,
-                                                  light_count, materials, c, A, seed0, seed1, store, accum, cnt);
-    if (valid) reinterpret_cast<uint2 *>(seeds)[id] = make_uint2(seed0, seed1);
-#else
     if (id < n_local) {
         Camera c = camera[0];
         uint32_t gid = sample_ids ? sample_ids[id] : id;
@@ -717,7 +700,6 @@ k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, cons
                                             materials, c, A, seed0, seed1, store, accum, cnt);
         reinterpret_cast<uint2 *>(seeds)[id] = make_uint2(seed0, seed1);
     }
-#endif
     flush_counters<COUNT>(cnt, counters);
 }
 

@@ -1515,314 +1515,6 @@ CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light
     a->count += 1.0f;
 }
 
-/* ---- decoupled walks --------------------------------------------------------------------------------------------- *
- * The same two random walks as fused_walk_sample, cut into steps that a warp can schedule: ONE inner node, ONE leaf,
- * or ONE vertex (everything random_walk does between two traversals: shading normal, BSDF sample, vertex store, next
- * ray).  In fused_walk_sample the 32 lanes of a warp meet after every ray, so each of the 12 traversals of a sample
- * costs the warp its longest ray (ncu: the node loop runs with 4.4 of 32 lanes, the triangle loop with 12.9).  With
- * the steps below a lane that has finished its ray goes on to its next one as soon as enough lanes want a vertex step,
- * and the warp meets only at the end of the 12 rays: a lane pays the SUM of its rays.  Every lane still executes exactly
- * the operations of random_walk in the same order on its own data, so results do not depend on the schedule.
- */
-struct WalkLane {
-    /* traversal of the current ray */
-    V3 o, d, inv;
-    float best_t, bu, bv;
-    int best_i, best_rank, cur, sp;
-    bool have; /* `cur` holds a node that still has to be processed */
-    /* the walk */
-    V3 rc, last_stored_color;
-    V4 uni;
-    float ray_tot, carry_imp;
-    int ray_hit_light, i, length;
-    int which; /* SUB_LIGHT (0), SUB_CAMERA (1), 2 = both walks done */
-    bool uni_found;
-};
-
-template <int MODE, bool COUNT>
-CLV_HD void walk_trace_begin(WalkLane &L, const AccelView &A, Cnt<COUNT> &cnt) {
-    L.best_i = -1; L.best_t = CLV_INF; L.bu = 0.0f; L.bv = 0.0f; L.best_rank = 0x7fffffff; L.sp = 0;
-    cnt.ray_ref();
-    cnt.ray_traced();
-    bool hit;
-    float te;
-    slab_test(L.o, L.inv, xyz(A.root_min), xyz(A.root_max), hit, te);
-    L.have = hit && te < L.best_t;
-    L.cur = A.root_ref;
-}
-template <int MODE>
-CLV_HD void walk_pop(WalkLane &L, const int *st_ref, const float *st_t) {
-    while (!L.have && L.sp > 0) {
-        L.sp--;
-        float t = st_t[L.sp];
-        if ((MODE == TRAVERSE_REFERENCE) ? (t < L.best_t) : (t <= L.best_t)) { L.cur = st_ref[L.sp]; L.have = true; }
-    }
-}
-/* closest_hit's inner_step / leaf_step on a WalkLane (binary nodes) */
-template <int MODE, bool COUNT>
-CLV_HD void walk_inner_step(WalkLane &L, const AccelView &A, int *st_ref, float *st_t, Cnt<COUNT> &cnt) {
-    const V4 *n = A.nodes + 4 * (size_t)L.cur;
-    V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
-    cnt.node();
-    bool hl, hr;
-    float tl, tr;
-    slab_test(L.o, L.inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
-    slab_test(L.o, L.inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
-    int lref = f2i(n3.x), rref = f2i(n3.y);
-    bool go_l, go_r, push;
-    int push_ref;
-    float push_t;
-    if (MODE == TRAVERSE_REFERENCE) {
-        go_r = hr && tr < L.best_t;
-        go_l = hl && tl < L.best_t;
-        push = go_r && hl;
-        push_ref = lref;
-        push_t = tl;
-        L.cur = go_r ? rref : lref;
-        L.have = go_r || go_l;
-    } else {
-        go_l = hl && tl <= L.best_t;
-        go_r = hr && tr <= L.best_t;
-        bool left_first = tl < tr;
-        push = go_l && go_r;
-        push_ref = left_first ? rref : lref;
-        push_t = left_first ? tr : tl;
-        L.cur = (go_l && (left_first || !go_r)) ? lref : rref;
-        L.have = go_l || go_r;
-    }
-    if (push && L.sp < CLV_STACK) { st_ref[L.sp] = push_ref; st_t[L.sp] = push_t; L.sp++; }
-    walk_pop<MODE>(L, st_ref, st_t);
-}
-template <int MODE, bool COUNT>
-CLV_HD void walk_leaf_step(WalkLane &L, const AccelView &A, const int *st_ref, const float *st_t, Cnt<COUNT> &cnt) {
-    int code = ~L.cur;
-    int first = code >> 4, count = code & 15;
-    for (int i = first; i < first + count; i++) {
-        const V4 *tp = A.tris + 3 * (size_t)i;
-        V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-        cnt.tri();
-        float t, u, v;
-        if (tri_test(L.o, L.d, xyz(a), xyz(b), xyz(c), t, u, v)) {
-            bool accept;
-            if (MODE == TRAVERSE_REFERENCE) accept = t < L.best_t;
-            else accept = t < L.best_t || (t == L.best_t && f2i(a.w) < L.best_rank);
-            if (accept) { L.best_i = i; L.best_t = t; L.bu = u; L.bv = v; L.best_rank = f2i(a.w); }
-        }
-    }
-    L.have = false;
-    walk_pop<MODE>(L, st_ref, st_t);
-}
-
-template <bool SOA> struct WalkSinkOf;
-template <> struct WalkSinkOf<true> {
-    typedef SoaSink type;
-    static CLV_HDM SoaSink make(const PathStore &store, uint32_t slot, int which) {
-        SoaSink sink;
-        sink.v = store.soa; sink.len = store.soa_len; sink.n = store.n; sink.slot = slot; sink.sub = which;
-        return sink;
-    }
-};
-template <> struct WalkSinkOf<false> {
-    typedef AosSink type;
-    static CLV_HDM AosSink make(const PathStore &store, uint32_t slot, int which) {
-        AosSink sink;
-        sink.path = (which ? store.camera_paths : store.light_paths) + slot;
-        return sink;
-    }
-};
-
-/* vertex slot i gets `ray` (speculatively, as in random_walk) and its traversal starts */
-template <int MODE, bool COUNT, typename SINK>
-CLV_HD void walk_launch(WalkLane &L, const Ray &ray, const SINK &sink, const AccelView &A, Cnt<COUNT> &cnt) {
-    sink.store(L.i, ray);
-    L.o = xyz(ray.origin); L.d = xyz(ray.direction); L.inv = xyz(ray.inv_direction); L.rc = xyz(ray.color);
-    L.ray_tot = ray.tot_importance;
-    L.ray_hit_light = ray.hit_light;
-    walk_trace_begin<MODE, COUNT>(L, A, cnt);
-}
-template <int MODE, bool COUNT, typename SINK>
-CLV_HD void walk_start(WalkLane &L, int which, const Ray &ray, const SINK &sink, const AccelView &A, Cnt<COUNT> &cnt) {
-    L.which = which;
-    L.carry_imp = which == SUB_CAMERA ? ray.c_importance : 1.0f / (2.0f * CLV_PI);
-    L.length = 0;
-    L.i = 0;
-    L.uni = v4(0, 0, 0, 0);
-    L.uni_found = false;
-    L.last_stored_color = v3(0, 0, 0);
-    walk_launch<MODE, COUNT>(L, ray, sink, A, cnt);
-}
-
-/* One vertex step of a lane whose traversal has finished: random_walk's loop body after closest_hit (trace.metal
- * :415-516).  Returns true when the walk goes on (next ray launched), false when it has ended (sink finished). */
-template <int MODE, bool COUNT, typename SINK>
-CLV_HD bool walk_vertex_step(WalkLane &L, const SINK &sink, const AccelView &A, const Material *materials, uint32_t &seed0,
-                             uint32_t &seed1, Cnt<COUNT> &cnt) {
-    const bool from_camera = L.which == SUB_CAMERA;
-    bool go_on = false;
-    do { /* `break` = the walk ends here, as in random_walk */
-        const int best_i = L.best_i;
-        if (best_i == -1) break;
-        const V3 o = L.o, d = L.d, rc = L.rc;
-        const float u = L.bu, v = L.bv;
-        const Triangle *tri = A.ref_triangles + best_i;
-        V3 tn = xyz(ld4(&tri->normal));
-        V3 n0 = xyz(ld4(&tri->n0)), n1 = xyz(ld4(&tri->n1)), n2 = xyz(ld4(&tri->n2));
-        int tri_material = tri->material, tri_is_light = tri->is_light, tri_is_camera = tri->is_camera;
-        const Material *mat = materials + tri_material;
-        V3 mat_color = xyz(ld4(&mat->color));
-        int mat_type = mat->type;
-        float alpha = mat->alpha, ior = mat->ior;
-
-        V3 n;
-        float ni, no;
-        V3 sampled_normal = normalize((n0 * (1 - u - v) + n1 * u) + n2 * v);
-        float side = dot(-d, tn);
-        if (side > 0) { n = sampled_normal; ni = 1.0f; no = ior; }
-        else if (side < 0) { n = -sampled_normal; ni = ior; no = 1.0f; }
-        else break;
-
-        Ray nr = zero_ray();
-        if (from_camera) nr.c_importance = L.carry_imp; else nr.l_importance = L.carry_imp;
-        nr.origin = pad0(o + d * L.best_t);
-        nr.material = tri_material;
-        nr.triangle = best_i;
-        nr.hit_light = (tri_is_light && dot(d, tn) < 0.0f) ? best_i : -1;
-        nr.hit_camera = tri_is_camera ? best_i : -1;
-
-        V3 wi = -d;
-        float rand_x_a = xorshift_random(seed0);
-        float rand_y_a = xorshift_random(seed1);
-        float rand_x_b = xorshift_random(seed0);
-        float rand_y_b = xorshift_random(seed1);
-
-        V3 wo = v3(0, 0, 0);
-        float f = 1.0f, c_p = 1.0f, l_p = 1.0f;
-        V3 m = GGX_sample(n, rand_x_a, rand_y_a, alpha);
-        if (dot(wi, m) < 0.0f) break;
-        if (dot(m, n) < 0.0f) break;
-        nr.normal = pad0(n);
-
-        float fresnel = degreve_fresnel(wi, m, ni, no);
-        int kind; /* 0 diffuse, 1 reflect, 2 transmit */
-        if (mat_type == 0) kind = 0;
-        else if (mat_type == 1) kind = (rand_x_b <= fresnel) ? 1 : 2;
-        else if (mat_type == 2) kind = (rand_x_b <= fresnel) ? 1 : 0;
-        else kind = 1;
-        if (kind == 0) diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
-        else if (kind == 1) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-        else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-
-        float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
-        if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);
-        else nr.color = pad0(rc * f);
-        nr.direction = pad0(wo);
-        nr.inv_direction = pad0(rcp(wo));
-
-        float next_carry;
-        if (from_camera) {
-            next_carry = c_p;
-            nr.tot_importance = L.ray_tot * nr.c_importance;
-        } else {
-            next_carry = l_p;
-            nr.tot_importance = L.ray_tot * nr.l_importance;
-        }
-        if (f == 0.0f) break;
-
-        sink.patch(L.i, from_camera, from_camera ? l_p : c_p);
-        cnt.vertex(1);
-        L.length = L.i + 1;
-        if (!L.uni_found && L.ray_hit_light >= 0) {
-            V3 c = L.last_stored_color / L.ray_tot;
-            L.uni = v4(c.x, c.y, c.z, 1.0f);
-            L.uni_found = true;
-        }
-        L.last_stored_color = rc;
-        L.carry_imp = next_carry;
-        L.i++;
-        if (L.i < CLV_MAX_BOUNCES) {
-            walk_launch<MODE, COUNT>(L, nr, sink, A, cnt);
-            go_on = true;
-        }
-    } while (false);
-    if (!go_on) sink.finish(L.length, from_camera);
-    return go_on;
-}
-
-/* one vertex step of the sample: the current walk's vertex; when the light walk ends the camera walk starts with the
- * camera ray generated up front (RNG order of renderer.py:281-285), when the camera walk ends the sample is done */
-template <int MODE, bool COUNT, bool SOA>
-CLV_HD void walk_sample_vertex_step(WalkLane &L, uint32_t slot, const Ray &cray, const PathStore &store, const AccelView &A,
-                                    const Material *materials, uint32_t &seed0, uint32_t &seed1, Cnt<COUNT> &cnt) {
-    typename WalkSinkOf<SOA>::type sink = WalkSinkOf<SOA>::make(store, slot, L.which);
-    if (walk_vertex_step<MODE, COUNT>(L, sink, A, materials, seed0, seed1, cnt)) return;
-    if (L.which == SUB_LIGHT) {
-        typename WalkSinkOf<SOA>::type csink = WalkSinkOf<SOA>::make(store, slot, SUB_CAMERA);
-        walk_start<MODE, COUNT>(L, SUB_CAMERA, cray, csink, A, cnt);
-    } else {
-        L.which = 2;
-    }
-}
-
-/* fused_walk_sample with the steps above.  On the device the 32 lanes of a warp vote on the kind of step of each
- * iteration (all lanes of the warp must call this, `valid` = the lane has a sample); on the host (tests/hostemu) a
- * sample simply runs its steps in order. */
-#ifndef CLV_WALK_VERTEX_MIN
-#define CLV_WALK_VERTEX_MIN 16 /* a vertex step runs once this many lanes wait for one (or no lane can traverse) */
-#endif
-#ifndef CLV_WALK_VOTE
-#define CLV_WALK_VOTE 8 /* inner nodes win the vote when n_inner * CLV_WALK_VOTE >= n_leaf * 4 */
-#endif
-template <int MODE, bool COUNT, bool SOA>
-CLV_HD void fused_walk_sample_decoupled(bool valid, uint32_t slot, uint32_t gid, const Triangle *light_triangles,
-                                        const float *surface_areas, const int32_t *light_triangle_indices, int light_count,
-                                        const Material *materials, const Camera &c, const AccelView &A, uint32_t &seed0,
-                                        uint32_t &seed1, const PathStore &store, Accum *accum, Cnt<COUNT> &cnt) {
-    WalkLane L;
-    int st_ref[CLV_STACK];
-    float st_t[CLV_STACK];
-    Ray cray;
-    L.which = 2;
-    L.have = false;
-    L.cur = 0;
-    L.uni = v4(0, 0, 0, 0);
-    if (valid) {
-        Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
-        cray = make_camera_ray(c, (int)gid, seed0, seed1);
-        typename WalkSinkOf<SOA>::type lsink = WalkSinkOf<SOA>::make(store, slot, SUB_LIGHT);
-        walk_start<MODE, COUNT>(L, SUB_LIGHT, lray, lsink, A, cnt);
-    }
-#if defined(__CUDA_ARCH__)
-    for (;;) {
-        const bool alive = L.which < 2;
-        const bool at_inner = alive && L.have && L.cur >= 0, at_leaf = alive && L.have && L.cur < 0;
-        const bool at_vertex = alive && !L.have;
-        const unsigned m_inner = __ballot_sync(0xffffffffu, at_inner), m_leaf = __ballot_sync(0xffffffffu, at_leaf);
-        const unsigned m_vertex = __ballot_sync(0xffffffffu, at_vertex);
-        if ((m_inner | m_leaf | m_vertex) == 0u) break;
-        if (__popc(m_vertex) >= CLV_WALK_VERTEX_MIN || (m_inner | m_leaf) == 0u) {
-            if (at_vertex) walk_sample_vertex_step<MODE, COUNT, SOA>(L, slot, cray, store, A, materials, seed0, seed1, cnt);
-        } else if (__popc(m_inner) * CLV_WALK_VOTE >= __popc(m_leaf) * 4) {
-            if (at_inner) walk_inner_step<MODE, COUNT>(L, A, st_ref, st_t, cnt);
-        } else {
-            if (at_leaf) walk_leaf_step<MODE, COUNT>(L, A, st_ref, st_t, cnt);
-        }
-    }
-#else
-    while (L.which < 2) {
-        if (!L.have) walk_sample_vertex_step<MODE, COUNT, SOA>(L, slot, cray, store, A, materials, seed0, seed1, cnt);
-        else if (L.cur >= 0) walk_inner_step<MODE, COUNT>(L, A, st_ref, st_t, cnt);
-        else walk_leaf_step<MODE, COUNT>(L, A, st_ref, st_t, cnt);
-    }
-#endif
-    if (valid) {
-        Accum *a = accum + gid;
-        a->uni[0] += nan_to_num0(L.uni.x);
-        a->uni[1] += nan_to_num0(L.uni.y);
-        a->uni[2] += nan_to_num0(L.uni.z);
-        a->count += 1.0f;
-    }
-}
-
 /* stages 6-8 for one pixel: adaptive_finalize_samples with identity bins, the light image the connect kernel
  * splatted this pass (cleared here for the next one), and process_images' accumulation (renderer.py:253-271).
  * Returns this pixel's sample weight of the pass. */

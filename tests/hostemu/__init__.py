@@ -86,10 +86,6 @@ class HostEmu:
         self.lib.emu_visibility(C.c_uint32(len(a)), _p(a), _p(b), accel, _p(out), C.c_int(mode))
         return out
 
-    def set_decoupled_walks(self, on):
-        """Walk stage of `fused_pass`: fused_walk_sample (False) or the step-wise fused_walk_sample_decoupled (True)."""
-        self.lib.emu_set_decoupled_walks(C.c_int(int(bool(on))))
-
     def fused_pass(self, arrays, accel, seeds, light_paths, camera_paths, aggs, light_image, accum, sample_ids=None,
                    mode=MODE_ORDERED, soa=None, soa_len=None):
         """One fused pass.  With `soa` (float32 (2*6*4*n_local, 4)) and `soa_len` (int32 (2*n_local,)) the renderer's compact

@@ -187,10 +187,6 @@ EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAc
     }
 }
 
-/* which form of the walk stage emu_fused_pass runs: fused_walk_sample (0) or the step-wise fused_walk_sample_decoupled (1) */
-static int g_decoupled_walks = 0;
-EXPORT void emu_set_decoupled_walks(int on) { g_decoupled_walks = on; }
-
 /* one fused pass exactly as clv_renderer_run_sample launches it: walks -> connect (splat) -> finalize+accumulate.
  * soa != NULL selects the renderer's compact SoA vertex records (soa: V4[2*6*4*n_local], soa_len: int32[2*n_local]),
  * otherwise the reference's Path records are used. */
@@ -206,12 +202,8 @@ static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Trian
         for (int64_t id = 0; id < (int64_t)n_local; id++) {
             uint32_t gid = sample_ids ? sample_ids[id] : (uint32_t)id;
             uint32_t s0 = seeds[2 * id], s1 = seeds[2 * id + 1];
-            if (g_decoupled_walks)
-                fused_walk_sample_decoupled<MODE, true, SOA>(true, (uint32_t)id, gid, lt, areas, lti, light_count, mats,
-                                                             cam[0], a->view, s0, s1, store, accum, cnt);
-            else
-                fused_walk_sample<MODE, true, SOA>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0], a->view,
-                                                   s0, s1, store, accum, cnt);
+            fused_walk_sample<MODE, true, SOA>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0], a->view, s0, s1,
+                                               store, accum, cnt);
             seeds[2 * id] = s0; seeds[2 * id + 1] = s1;
         }
         LightSink sink;

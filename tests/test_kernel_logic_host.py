@@ -313,43 +313,3 @@ def test_soa_vertex_records_give_the_same_bits_as_path_records(E, preset, w, h):
     assert_bits_equal(a0[:, 4:8].copy(), a1[:, 4:8].copy(), "unidirectional + counts")
     np.testing.assert_allclose(a1[:, 0:4], a0[:, 0:4], rtol=2e-4, atol=1e-6)
     assert np.array_equal(len1[:b], lp0["length"])  # SoA lengths: [light | camera]
-
-
-@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_ORDERED])
-@pytest.mark.parametrize("use_soa", [False, True])
-def test_decoupled_walks_give_the_same_bits(E, mode, use_soa):
-    """fused_walk_sample_decoupled (the walks cut into inner-node / leaf / vertex steps that a warp schedules) against
-    fused_walk_sample: same RNG streams, same vertex records, same aggregators and accumulators."""
-    w, h = 40, 30
-    a = arrays("bench-spheres", w, h)
-    b = w * h
-    seeds = seeds_for(b, seed=17)
-    acc = E.accel(a.boxes, a.triangles)
-    outs = []
-    try:
-        for decoupled in (False, True):
-            E.set_decoupled_walks(decoupled)
-            s = seeds.copy()
-            lp, cp = np.zeros(b, T.Path), np.zeros(b, T.Path)
-            aggs = np.zeros(b, T.WeightAggregator)
-            li = np.zeros((b, 4), np.float32)
-            accum = np.zeros((b, 8), np.float32)
-            soa = np.zeros((2 * 6 * 4 * b, 4), np.float32) if use_soa else None
-            soa_len = np.zeros(2 * b, np.int32) if use_soa else None
-            for _ in range(3):
-                E.fused_pass(a, acc, s, lp, cp, aggs, li, accum, mode=mode, soa=soa, soa_len=soa_len)
-            outs.append((s, aggs, accum, lp, cp, soa, soa_len))
-    finally:
-        E.set_decoupled_walks(False)
-        E.accel_destroy(acc)
-    x, y = outs
-    assert_bits_equal(x[0], y[0], "RNG state")
-    assert_bits_equal(x[1], y[1], "aggregators")
-    assert_bits_equal(x[2][:, 4:8].copy(), y[2][:, 4:8].copy(), "unidirectional + counts")
-    np.testing.assert_allclose(y[2][:, 0:4], x[2][:, 0:4], rtol=2e-4, atol=1e-6)  # light image: summation order of the splats
-    if use_soa:
-        assert np.array_equal(x[6], y[6])
-        assert_bits_equal(x[5], y[5], "SoA vertex records")
-    else:
-        assert_paths_equal(x[3], y[3], "light paths")
-        assert_paths_equal(x[4], y[4], "camera paths")
