@@ -53,15 +53,6 @@
 #ifndef CLV_WIDE_OCCLUSION
 #define CLV_WIDE_OCCLUSION 1
 #endif
-#ifndef CLV_TRI_TEST_BRANCHLESS
-#define CLV_TRI_TEST_BRANCHLESS 0
-#endif
-#ifndef CLV_WALK_INNER_BURST
-#define CLV_WALK_INNER_BURST 0 /* closest_hit, while-while form: 0 = walk down to the leaf, n > 0 = at most n node steps per round */
-#endif
-#ifndef CLV_WALK_SCHEDULE
-#define CLV_WALK_SCHEDULE 0    /* closest_hit: 0 = while-while, w > 0 = majority vote with weight w */
-#endif
 
 namespace clv {
 
@@ -231,16 +222,6 @@ CLV_HD bool tri_test(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float &t_out, float &u, fl
     float f = 1.0f / a;
     V3 s = o - v0;
     u = f * dot(s, h);
-#if CLV_TRI_TEST_BRANCHLESS
-    /* same predicate, evaluated at the end: the lanes of a warp test different triangles, so the early returns of the
-     * reference only add divergence (if one lane goes on, the warp pays for the rest of the test anyway) */
-    V3 q = cross(s, e1);
-    v = f * dot(d, q);
-    float t = f * dot(e2, q);
-    bool hit = !(u < 0 || u > 1) && !(v < 0 || u + v > 1) && t > CLV_DELTA;
-    if (hit) t_out = t;
-    return hit;
-#else
     if (u < 0 || u > 1) return false;
     V3 q = cross(s, e1);
     v = f * dot(d, q);
@@ -248,7 +229,6 @@ CLV_HD bool tri_test(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float &t_out, float &u, fl
     float t = f * dot(e2, q);
     if (t > CLV_DELTA) { t_out = t; return true; }
     return false;
-#endif
 }
 
 enum { TRAVERSE_REFERENCE = 0, TRAVERSE_ORDERED = 1 };
@@ -371,32 +351,13 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
             if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
         }
     };
-#if defined(__CUDA_ARCH__) && CLV_WALK_SCHEDULE > 0
-    /* majority vote (as in k_connect_rays): per iteration the converged lanes run ONE kind of step, the one more of
-     * them wait for (inner nodes win when n_inner * CLV_WALK_SCHEDULE >= n_leaf * 4).  Every lane still visits its own
-     * nodes in its own order, so results do not depend on the schedule. */
-    const unsigned lanes = __activemask();
-    for (;;) {
-        const bool at_inner = have && cur >= 0, at_leaf = have && cur < 0;
-        const unsigned m_inner = __ballot_sync(lanes, at_inner), m_leaf = __ballot_sync(lanes, at_leaf);
-        if ((m_inner | m_leaf) == 0u) break;
-        if (__popc(m_inner) * CLV_WALK_SCHEDULE >= __popc(m_leaf) * 4) { if (at_inner) inner_step(); }
-        else if (at_leaf) leaf_step();
-    }
-#else
     /* while-while: lanes at inner nodes step together until every lane has reached a leaf (or finished), then all
-     * leaves are processed together */
+     * leaves are processed together.  (Measured alternatives inside this kernel — a majority vote between node and
+     * leaf steps as in k_connect_rays, bounded bursts of node steps — were slower: profiles/r01_notes.md.) */
     while (have) {
-#if CLV_WALK_INNER_BURST > 0
-        /* bounded burst: lanes that already hold a leaf wait for at most CLV_WALK_INNER_BURST node steps of the others */
-        for (int burst = 0; burst < CLV_WALK_INNER_BURST && have && cur >= 0; burst++) inner_step();
-        if (have && cur < 0) leaf_step();
-#else
         while (have && cur >= 0) inner_step();
         if (have) leaf_step();
-#endif
     }
-#endif
 }
 
 /* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
@@ -414,9 +375,7 @@ struct OccRay { /* scalars only, so that they live in registers; the node stack 
     int cur, sp;
 };
 enum { OCC_RUNNING = 0, OCC_CLEAR = 1, OCC_BLOCKED = 2 };
-#ifndef CLV_OCC_LEAF_BURST
-#define CLV_OCC_LEAF_BURST 0
-#endif
+
 
 template <bool COUNT>
 CLV_HD int occ_begin(const AccelView &A, OccRay &r, Cnt<COUNT> &cnt) {
@@ -536,14 +495,7 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
     int code = ~r.cur;
     int first = code >> 4, count = code & 15;
     bool blocked = false;
-#if CLV_OCC_LEAF_BURST > 0
-    /* at most CLV_OCC_LEAF_BURST triangles per step; the rest of the leaf stays in `cur` as a shorter leaf.  The lanes
-     * of a warp hold leaves of 1..15 triangles: with whole leaves per step the short ones wait for the longest */
-    const int here = count < CLV_OCC_LEAF_BURST ? count : CLV_OCC_LEAF_BURST;
-#else
-    const int here = count;
-#endif
-    for (int i = first; i < first + here; i++) {
+    for (int i = first; i < first + count; i++) {
         const V4 *tp = A.tris + 3 * (size_t)i;
         V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
         cnt.tri();
@@ -553,7 +505,6 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
             blocked = true;
     }
     if (blocked) return OCC_BLOCKED;
-    if (here < count) { r.cur = ~(((first + here) << 4) | (count - here)); return OCC_RUNNING; }
     if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
     return OCC_CLEAR;
 }

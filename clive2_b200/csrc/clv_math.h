@@ -24,13 +24,7 @@
 
 #if defined(__CUDACC__)
 #define CLV_MATH_FN __host__ __device__ __forceinline__
-/* the public entry points can be kept out of line on the device (-DCLV_MATH_NOINLINE): the walk kernel evaluates ~10
- * of them per bounce and is larger than the instruction cache */
-#if defined(CLV_MATH_NOINLINE)
-#define CLV_MATH_API __host__ __device__ __noinline__
-#else
 #define CLV_MATH_API __host__ __device__ __forceinline__
-#endif
 #else
 #define CLV_MATH_FN static inline
 #define CLV_MATH_API static inline
