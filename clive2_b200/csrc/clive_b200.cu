@@ -244,6 +244,14 @@ extern "C" int clv_host_free(void *h_ptr) {
 /* ---------------------------------------------------------------------------------------------------------------
  * acceleration structure: reference Box[]/Triangle[] -> compact traversal layout (clv_device.cuh AccelView)
  * ------------------------------------------------------------------------------------------------------------- */
+/* Scenes whose traversal records (nodes + triangles) do not fit the cache hierarchy are bound by the latency of
+ * dependent record fetches, and more resident warps hide more of it even at the price of spills; cache-resident scenes
+ * are issue-bound and lose with fewer registers.  Measured (walks at 64 / 48 / 40 / 32 registers per thread): C2 (2.8 MB)
+ * 0.98 / 1.01 / - / - ms, C3 (60 MB) 6.81 / 6.32 / 6.13 / 6.17 ms, C4 (700 MB) 25.5 / 22.5 / 21.2 / 19.6 ms; occlusion
+ * rays at 63 / 48 / 40 / 32 registers: C2 0.99 / 1.00 ms, C3 6.73 / 6.60 / - / 8.71 ms, C4 14.3 / 13.5 / 13.9 / 16.4 ms. */
+#ifndef CLV_LARGE_SCENE_BYTES
+#define CLV_LARGE_SCENE_BYTES (32u << 20)
+#endif
 struct clv_accel {
     clv_ctx *ctx;
     V4 *d_nodes, *d_wnodes, *d_tris;
@@ -251,6 +259,7 @@ struct clv_accel {
     int32_t *d_camera_tris;
     AccelView view;
     uint64_t n_nodes, n_wide, n_tris;
+    int large; /* traversal records exceed CLV_LARGE_SCENE_BYTES: the fused pass uses its high-occupancy kernel flavours */
 };
 
 extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_boxes, const clv_Triangle *h_tris_,
@@ -297,6 +306,7 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     a->view.wnodes = a->d_wnodes;
     a->view.wroot_ref = H.wide_root_ref;
     a->n_wide = H.wide.size();
+    a->large = (nb_nodes + nb_wide + nb_tris) > (size_t)CLV_LARGE_SCENE_BYTES;
     a->view.tris = a->d_tris;
     a->view.ref_triangles = a->d_ref_triangles;
     a->view.root_min = boxes[0].min;
@@ -321,7 +331,7 @@ extern "C" int clv_accel_destroy(clv_accel *a) {
     return CLV_OK;
 }
 
-extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[4]) {
+extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[9]) {
     REQUIRE(a && out, "null");
     out[0] = a->n_nodes * sizeof(NodeRec); /* binary nodes */
     out[1] = a->n_tris * 3 * sizeof(V4);
@@ -331,6 +341,7 @@ extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[4]) {
     out[5] = a->n_wide;
     out[6] = CLV_WIDE_CLOSEST;             /* which of the two each search kind traverses in the ORDERED flavour */
     out[7] = CLV_WIDE_OCCLUSION;
+    out[8] = (uint64_t)a->large;
     return CLV_OK;
 }
 
@@ -489,13 +500,14 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
     flush_counters<COUNT>(cnt, counters);
 }
 
-#ifdef CLV_RAYS_MIN_BLOCKS
-#define CLV_RAYS_BOUNDS __launch_bounds__(CLV_BLOCK, CLV_RAYS_MIN_BLOCKS)
-#else
-#define CLV_RAYS_BOUNDS __launch_bounds__(CLV_BLOCK)
+#ifndef CLV_RAYS_MIN_BLOCKS
+#define CLV_RAYS_MIN_BLOCKS 1 /* no register cap: the kernel takes 63 */
 #endif
-template <int MODE, bool COUNT, bool SOA>
-__global__ void CLV_RAYS_BOUNDS
+#ifndef CLV_RAYS_MIN_BLOCKS_LARGE
+#define CLV_RAYS_MIN_BLOCKS_LARGE (1280 / CLV_BLOCK) /* = 48 registers per thread */
+#endif
+template <int MODE, bool COUNT, bool SOA, int LARGE = 0>
+__global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_RAYS_MIN_BLOCKS_LARGE : CLV_RAYS_MIN_BLOCKS)
 k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratch cs,
                Counters *counters, int refill_below, int schedule) {
     const uint32_t count = *cs.task_count;
@@ -684,8 +696,11 @@ __global__ void k_set_light_image(uint32_t n, V4 *light_image) { /* gather write
 #ifndef CLV_WALK_MIN_BLOCKS
 #define CLV_WALK_MIN_BLOCKS (1024 / CLV_BLOCK) /* = 64 registers per thread */
 #endif
-template <int MODE, bool COUNT, bool SOA>
-__global__ void __launch_bounds__(CLV_BLOCK, CLV_WALK_MIN_BLOCKS)
+#ifndef CLV_WALK_MIN_BLOCKS_LARGE
+#define CLV_WALK_MIN_BLOCKS_LARGE (2048 / CLV_BLOCK) /* = 32 registers per thread, every warp slot of the SM filled */
+#endif
+template <int MODE, bool COUNT, bool SOA, int LARGE = 0>
+__global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_WALK_MIN_BLOCKS_LARGE : CLV_WALK_MIN_BLOCKS)
 k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, const Triangle *light_triangles, const float *surface_areas,
               const int32_t *light_triangle_indices, int light_count, const Material *materials, const Camera *camera,
               AccelView A, uint32_t *seeds, PathStore store, Accum *accum, Counters *counters) {
@@ -836,7 +851,7 @@ extern "C" int clv_set_stage_traverse_mode(int mode) {
 }
 
 /* enumerate -> rays -> finish for the samples [first, n) on `stream`; `cs` holds this slice's own task list */
-static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat, uint32_t first, uint32_t n,
+static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat, bool large, uint32_t first, uint32_t n,
                           const uint32_t *sample_ids, const PathStore &store,
                           bool soa, const AccelView &view, const Material *mats, const Camera *cam,
                           ConnectScratch cs, WeightAggregator *aggs, V4 *out, const LightSink &sink,
@@ -850,9 +865,14 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
     if (mid_events) CK(cudaEventRecord(mid_events[0], stream));
     const uint64_t warps = ((uint64_t)len * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
     const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
+    if (large && mode == CLV_TRAVERSE_ORDERED && !c->counting && soa) {
+        /* the renderer's default configuration on a scene larger than the caches: high-occupancy flavour */
+        k_connect_rays<TRAVERSE_ORDERED, false, true, 1><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule);
+    } else {
 #define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
-    DISPATCH_MCS(mode, c->counting, soa, CALL);
+        DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
+    }
     LAUNCHED(c);
     if (mid_events) CK(cudaEventRecord(mid_events[1], stream));
 #define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
@@ -936,7 +956,7 @@ extern "C" int clv_connect_paths(clv_ctx *c, uint32_t n, const clv_Path *cp, con
     store.camera_paths = (Path *)cp; /* read only here */
     store.light_paths = (Path *)lp;
     store.n = n;
-    return launch_connect(c, c->stream, g_stage_mode, false, 0u, n, nullptr, store, false, accel->view,
+    return launch_connect(c, c->stream, g_stage_mode, false, false, 0u, n, nullptr, store, false, accel->view,
                           (const Material *)mats, (const Camera *)cam, cs, (WeightAggregator *)aggs, (V4 *)out, sink, nullptr);
 }
 
@@ -1176,6 +1196,8 @@ static int launch_pass(clv_renderer *r) {
     sink.splat_image = r->d_light_image;
     sink.n_pixels = (int)r->n_pixels;
     const ConnectScratch cs_all = connect_scratch_at(r->d_connect_scratch, n);
+    /* default configuration (ORDERED, SoA records, no counters) on a scene larger than the caches */
+    const bool large = r->accel->large && r->mode == CLV_TRAVERSE_ORDERED && !c->counting && soa;
     /* slices: whole blocks each; one slice (everything on the context's stream) when per-kernel events are wanted */
     int slices = c->pass_slices > 0 ? c->pass_slices : (n >= (uint32_t)c->sm_count * 1024u ? 3 : 1);
     if (r->timing) slices = 1;
@@ -1188,15 +1210,19 @@ static int launch_pass(clv_renderer *r) {
         if (first >= end) continue;
         cudaStream_t st = k == 0 ? c->stream : c->slice_stream[k];
         if (k > 0) CK(cudaStreamWaitEvent(st, c->slice_fork, 0));
+        if (large) {
+            k_fused_walks<TRAVERSE_ORDERED, false, true, 1><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters);
+        } else {
 #define CALL(M, CT, SO) k_fused_walks<M, CT, SO><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters)
-        DISPATCH_MCS(r->mode, c->counting, soa, CALL);
+            DISPATCH_MCS(r->mode, c->counting, soa, CALL);
 #undef CALL
+        }
         LAUNCHED(c);
         if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], st));
         ConnectScratch cs = cs_all;
         cs.task_count = cs_all.task_count + k;
         cs.tasks = cs_all.tasks + (size_t)first * 36;
-        int rc = launch_connect(c, st, r->mode, true, first, end, ids, store, soa, r->accel->view, r->d_materials,
+        int rc = launch_connect(c, st, r->mode, true, large, first, end, ids, store, soa, r->accel->view, r->d_materials,
                                 r->d_camera, cs, r->d_aggs, nullptr, sink, r->timing ? &r->events[ev0 + 2] : nullptr);
         if (rc != CLV_OK) return rc;
         if (k > 0) {

@@ -209,11 +209,11 @@ class Accel:
         self.n_boxes, self.n_triangles = len(b), len(t)
 
     def stats(self):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 9)()
         _check(self.device.lib.clv_accel_stats(self.handle, out))
         return {"node_bytes": int(out[0]), "triangle_bytes": int(out[1]), "nodes": int(out[2]), "triangles": int(out[3]),
                 "wide_node_bytes": int(out[4]), "wide_nodes": int(out[5]), "closest_uses_wide": bool(out[6]),
-                "occlusion_uses_wide": bool(out[7])}
+                "occlusion_uses_wide": bool(out[7]), "large_scene_tuning": bool(out[8])}
 
     def release(self):
         if getattr(self, "handle", None):

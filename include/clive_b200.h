@@ -123,8 +123,9 @@ CLV_API int clv_accel_create(clv_ctx *ctx, const clv_Box *h_boxes, int32_t n_box
 CLV_API int clv_accel_destroy(clv_accel *accel);
 /* the compact layout: [0] bytes of binary node records, [1] bytes of triangle records, [2] binary node count,
  * [3] triangle count, [4] bytes of 4-wide node records, [5] 4-wide node count, [6]/[7] 1 if closest-hit / occlusion
- * searches of the ORDERED flavour traverse the 4-wide nodes */
-CLV_API int clv_accel_stats(clv_accel *accel, uint64_t out[8]);
+ * searches of the ORDERED flavour traverse the 4-wide nodes, [8] 1 if the records exceed the cache-resident size and the
+ * fused pass therefore runs its high-occupancy kernel flavours (same results, different register budget) */
+CLV_API int clv_accel_stats(clv_accel *accel, uint64_t out[9]);
 
 /* ---- 4. the eight kernels (trace.metal entry points), reference argument order, device pointers ----------------- */
 /* generate_light_rays, trace.metal:1070-1124 / renderer.py:114-125 */

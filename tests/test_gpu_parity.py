@@ -550,3 +550,29 @@ def test_pass_slices_do_not_change_the_result(dev):
         assert np.array_equal(other[4], results[0][4])
         np.testing.assert_allclose(other[3], results[0][3], rtol=5e-4, atol=1e-6)
     sc.release()
+
+
+def test_large_scene_kernel_flavours_vs_oracle(dev):
+    """A scene whose traversal records exceed the cache-resident size (1 M-triangle terrain, BASELINE config 3's
+    geometry) runs the high-occupancy flavours of the walk and occlusion kernels (32 / 48 registers per thread): same
+    bits as the oracle, as with the default flavours."""
+    w, h = 64, 40
+    a = scene.preset_arrays("bench-terrain-1m", w, h)  # native BVH builder (byte-identical to the numpy one, tests/test_native_bvh.py)
+    b = w * h
+    seeds = seeds_for(b, seed=77)
+    sc = scene.scene_from_arrays(a, dev)
+    assert dev.accel(sc.boxes, sc.triangles).stats()["large_scene_tuning"]
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(2):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3), "uni")
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    r.release()
+    sc.release()
+    small = scene.scene_from_arrays(arrays("empty", 16, 16), dev)
+    assert not dev.accel(small.boxes, small.triangles).stats()["large_scene_tuning"]
+    small.release()
