@@ -395,6 +395,10 @@ def run_ours(args, cfg, rank, local_rank, world):
                              if (768 + 200 + 128) * batch > 126e6
                              else "per-pass working set below the 126 MB L2; steps run back to back without flush",
                        "accel_bytes": accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"],
+                       "launches_per_step": launches // K,
+                       "kernel_flavour": ("high-occupancy (walks 32 / rays 48 registers; traversal records exceed the caches)"
+                                          if accel_stats["large_scene_tuning"] else
+                                          "cache-resident (walks 64 / rays 63 registers)"),
                        "scene_build_s": t_scene, "scene_upload_s": t_up},
             "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,
             "mrays_traced_per_s": tot["rays_traced"] * world / (elapsed_ms * 1e-3) / 1e6,
