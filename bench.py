@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Benchmark of the BDPT hot path (one "step" = one sample pass = Renderer.run_sample over a full frame).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  `value` is whole-job Msamples/s with everything resident in HBM (CUDA events on the
-launch stream, max over ranks); `e2e` is the same metric through `Renderer.run_sample_e2e` with HOST buffers (seed
-upload + accumulator download inside the timed region); `roofline` is for the dominant kernel of the pass;
+launch stream, max over ranks); `e2e` is the same metric through `Renderer.run_sample_preview` with pinned HOST buffers
+(fresh seeds up, one pass, device tone map, uint8 preview image down, all inside the timed region; `e2e_accumulators`
+downloads the raw float accumulators instead); `roofline` is for the dominant kernel of the pass;
 `cpu_baseline` is the CPU transcription of the reference (oracle/, glibc build) timed on this box's host cores.
 `--impl reference` times that CPU transcription as the reference arm (the reference's Metal kernels cannot run on
 Linux and its Python needs `metalcompute`).
