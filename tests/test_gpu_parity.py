@@ -248,6 +248,21 @@ def test_end_to_end_call_with_host_buffers(dev):
     a1 = r1._accum()
     assert_bits_equal(np.ascontiguousarray(a1[..., 4:8]).reshape(b, 4), np.ascontiguousarray(h_acc.array[..., 4:8]).reshape(b, 4), "uni+count")
     np.testing.assert_allclose(h_acc.array[..., 0:4], a1[..., 0:4], rtol=5e-4, atol=1e-6)
+    # the same call with the pass cut into slices (forced: this frame is smaller than one wave)
+    before = dev.pass_slices
+    dev.pass_slices = 3
+    try:
+        r3 = Renderer(sc, seeds=seeds_for(b, seed=2))
+        h_img = runtime.PinnedArray((h, w, 3), np.uint8)
+        r3._fr.run_sample_preview(h_seeds.ptr, 4.0, h_img.ptr)
+        a3 = r3._accum()
+        assert_bits_equal(np.ascontiguousarray(a1[..., 4:8]).reshape(b, 4), np.ascontiguousarray(a3[..., 4:8]).reshape(b, 4), "uni+count, 3 slices")
+        assert np.array_equal(r1._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b), r3._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b))
+        assert np.abs(h_img.array.astype(int) - r1.image.astype(int)).max() <= 2
+        r3.release()
+        h_img.release()
+    finally:
+        dev.pass_slices = before
     for x in (r1, r2):
         x.release()
     h_seeds.release()
