@@ -335,7 +335,9 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
             if (tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v)) {
                 bool accept;
                 if (MODE == TRAVERSE_REFERENCE) accept = t < best_t;
-                else accept = t < best_t || (t == best_t && f2i(a.w) < best_rank);
+                /* a "hit" at t = +inf (ray parallel to the triangle's plane: f = 1/0, u and v NaN, which pass the
+                 * reference's range checks) is never accepted by the reference's strict t < best_t: no tie at INF */
+                else accept = t < best_t || (t == best_t && t < CLV_INF && f2i(a.w) < best_rank);
                 if (accept) {
                     best_i = i; best_t = t; bu = u; bv = v;
                     best_rank = f2i(a.w);
@@ -515,7 +517,8 @@ CLV_HD bool test_one(const AccelView &A, int tri, V3 o, V3 d, float &t, int &ran
     V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
     float u, v;
     rank = f2i(a.w);
-    return tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v);
+    /* t = +inf (parallel ray, NaN barycentrics) passes the reference's triangle test but can never be its closest hit */
+    return tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v) && t < CLV_INF;
 }
 
 /* visibility_test (trace.metal:178-197): the closest hit from a toward b must be b's triangle. */

@@ -140,3 +140,102 @@ def zoo_arrays(width, height):
              {"mesh": mesh, "offset": _np.array([-1.8, 0.2, -1.0]), "material": 0}]
     return scene.build_scene_arrays(width, height, _np.array([0, 1.5, 6]), _np.array([0, 0, -1]), specs, mats,
                                     bvh_builder="numpy")
+
+
+def fuzz_soup(seed, n_random=300):
+    """Box[]/Triangle[] of a deliberately awkward triangle soup: random triangles, EXACT duplicates (equal t on every
+    ray: the reference keeps the first in its visiting order), coplanar overlapping pairs, zero-area and collinear
+    triangles (Moeller-Trumbore divides by a = 0), large axis-aligned quads whose boxes are flat, and a far outlier."""
+    from clive2_b200.bvh import FastTreeBox, build_flat_bvh
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    base = rng.uniform(-2, 2, (n_random, 1, 3))
+    tris = [(base + rng.normal(0, 0.4, (n_random, 3, 3))).astype(f32)]
+    tris.append(tris[0][:40].copy())                                   # exact duplicates
+    shifted = tris[0][40:70].copy()
+    e = shifted[:, 1] - shifted[:, 0]
+    tris.append((shifted + 0.25 * e[:, None, :]).astype(f32))          # coplanar, overlapping their originals
+    deg = tris[0][70:80].copy(); deg[:, 1] = deg[:, 0]                 # zero area: v1 == v0
+    col = tris[0][80:90].copy(); col[:, 2] = col[:, 0] + 2 * (col[:, 1] - col[:, 0])  # collinear
+    tris += [deg, col]
+    quads = []
+    for axis in range(3):
+        for c in (-2.5, 0.0, 2.5):
+            p = np.zeros((4, 3), f32)
+            u, v = [a for a in range(3) if a != axis]
+            p[:, axis] = c
+            p[:, u] = [-3, 3, 3, -3]
+            p[:, v] = [-3, -3, 3, 3]
+            quads += [p[[0, 1, 2]], p[[0, 2, 3]]]
+    tris.append(np.array(quads, f32))
+    tris.append(np.array([[[50, 50, 50], [51, 50, 50], [50, 51, 50]]], f32))
+    corners = np.concatenate(tris).astype(f32)
+    n = len(corners)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nrm = np.cross(corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0])
+        area = np.linalg.norm(nrm, axis=1)
+        nrm = np.nan_to_num(nrm / area[:, None]).astype(f32)
+    soup = FastTreeBox(np.zeros((n, 3), np.uint32), corners, corners.min(axis=1), corners.max(axis=1), nrm,
+                       np.repeat(nrm[:, None, :], 3, axis=1), (area / 2).astype(f32), np.zeros(n, np.int32),
+                       np.zeros(n, np.bool_), np.zeros(n, np.bool_))
+    return build_flat_bvh(soup, builder="numpy")
+
+
+def fuzz_rays(triangles, n, seed):
+    """Random rays plus the awkward ones: axis-parallel directions (zero components: inv_direction = +-inf, 0 * inf = NaN
+    in the slab test), origins exactly on triangle vertices and inside triangle planes, rays along triangle edges."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    o = rng.uniform(-3.5, 3.5, (n, 3)).astype(f32)
+    d = rng.normal(size=(n, 3))
+    kind = rng.integers(0, 6, n)
+    ax = rng.integers(0, 3, n)
+    sign = rng.choice([-1.0, 1.0], n)
+    for a in range(3):                       # kind 1: one exact axis direction; kind 2: one zero component
+        m1 = (kind == 1) & (ax == a)
+        d[m1] = 0.0
+        d[m1, a] = sign[m1]
+        d[(kind == 2) & (ax == a), a] = 0.0
+    k = rng.integers(0, len(triangles), n)
+    v0, v1, v2 = (triangles[name][k, :3] for name in ("v0", "v1", "v2"))
+    m3 = kind == 3                           # origin exactly on a vertex
+    o[m3] = v0[m3]
+    m4 = kind == 4                           # origin inside a triangle's plane (barycentric point)
+    w = rng.random((n, 2)).astype(f32)
+    o[m4] = (v0 + (v1 - v0) * w[:, :1] * 0.5 + (v2 - v0) * w[:, 1:] * 0.5)[m4]
+    m5 = kind == 5                           # along an edge, from outside
+    d[m5] = (v1 - v0)[m5]
+    o[m5] = (v0 - 3 * (v1 - v0))[m5]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nd = np.linalg.norm(d, axis=1, keepdims=True)
+        d = np.where(nd > 0, d / nd, [[1.0, 0.0, 0.0]]).astype(f32)
+        rays = np.zeros(n, T.Ray)
+        rays["origin"][:, :3], rays["direction"][:, :3] = o, d
+        rays["inv_direction"][:, :3] = f32(1.0) / d
+    rays["triangle"] = -1
+    return rays
+
+
+def check_ordered_against_reference(rays, tris, tri, t, tri_o, t_o):
+    """ORDERED may leave the reference only where the reference's own hit is a rounding artefact: Moeller-Trumbore has
+    no parallel-ray guard (trace.metal:117-142), so a ray within ~1e-7 of a triangle's plane gets f = 1/a ~ 1e7 and
+    garbage (u, v, t) that can pass the range checks although o + t d is nowhere near the triangle.  Whether such a
+    'hit' is ever looked at depends on the visiting order; near-first traversal prunes its box.  Everything else — exact
+    ties between duplicates included — must resolve to the reference's triangle."""
+    mm = np.flatnonzero(tri != tri_o)
+    assert len(mm) < 0.01 * len(tri), len(mm)
+    o, d = rays["origin"][mm, :3], rays["direction"][mm, :3]
+
+    def real_hit(k, tt):  # the hit point lies inside the triangle's own (slightly inflated) bounding box
+        ok = (k >= 0) & np.isfinite(tt)
+        kk = np.where(ok, k, 0)
+        corners = np.stack([tris[name][kk, :3] for name in ("v0", "v1", "v2")], axis=1)
+        with np.errstate(invalid="ignore", over="ignore"):
+            p = o + np.where(ok, tt, 0)[:, None] * d
+        lo, hi = corners.min(axis=1) - 1e-3, corners.max(axis=1) + 1e-3
+        return ok & ((p >= lo) & (p <= hi)).all(axis=1)
+
+    ref_real, ord_real = real_hit(tri[mm], t[mm]), real_hit(tri_o[mm], t_o[mm])
+    assert not (tri_o[mm] >= 0)[~ord_real].any()               # ORDERED never reports an artefact or an infinite hit ...
+    bad = ref_real & ~(ord_real & (np.abs(t[mm] - t_o[mm]) <= 1e-3 * np.abs(t[mm])) & (t[mm] != t_o[mm]))
+    assert not bad.any(), (int(bad.sum()), mm[bad][:5])        # ... and only leaves the reference where IT does
