@@ -239,3 +239,23 @@ def check_ordered_against_reference(rays, tris, tri, t, tri_o, t_o):
     assert not (tri_o[mm] >= 0)[~ord_real].any()               # ORDERED never reports an artefact or an infinite hit ...
     bad = ref_real & ~(ord_real & (np.abs(t[mm] - t_o[mm]) <= 1e-3 * np.abs(t[mm])) & (t[mm] != t_o[mm]))
     assert not bad.any(), (int(bad.sum()), mm[bad][:5])        # ... and only leaves the reference where IT does
+
+
+AWKWARD_CAMERAS = [((0, 1.5, 30), (0, 0, -1)),      # far outside the enclosure: most camera paths have length 0 or 1
+                   ((0, 1.5, 6), (0, 0, 1)),        # looking away from the scene, at the wall behind the camera
+                   ((0, 8.5, 0), (0, -1, 0)),       # straight down from next to the light
+                   ((4.9, 0, 0), (-1, 0.2, 0.1)),   # centimetres from a wall
+                   ((40, 40, 40), (-1, -1, -1))]    # diagonal view from far away
+
+
+@functools.lru_cache(maxsize=None)
+def awkward_camera_arrays(which, width, height):
+    """Cornell box + one glossy sphere seen from AWKWARD_CAMERAS[which]: empty and one-vertex camera paths, t = 1
+    projections that land on the last pixel row/column and beyond (pixel index == W*H + ...)."""
+    from clive2_b200 import meshgen
+    from clive2_b200.load import make_materials
+    mats = make_materials({0: dict(type=1, alpha=0.05, ior=1.5), 5: dict(type=2, alpha=0.2)})
+    center, direction = AWKWARD_CAMERAS[which]
+    specs = [{"mesh": meshgen.icosphere(1, 0.8), "offset": np.array([0.5, -0.5, 0.0]), "material": 0}]
+    return scene.build_scene_arrays(width, height, np.array(center, float), np.array(direction, float), specs, mats,
+                                    bvh_builder="numpy")

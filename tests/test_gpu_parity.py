@@ -8,7 +8,8 @@ import pytest
 from clive2_b200 import runtime, scene, struct_types as T
 from clive2_b200.renderer import Renderer
 from oracle.oracle import Oracle, OracleRenderer
-from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, check_ordered_against_reference, fuzz_rays,
+from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
+                          check_ordered_against_reference, fuzz_rays,
                           fuzz_soup, oracle_stages, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 
@@ -621,3 +622,27 @@ def test_fuzzed_soups_and_degenerate_rays(dev, O, seed):
         assert np.array_equal(ref, dev.visibility(acc, A, b, runtime.TRAVERSE_REFERENCE_ORDER))
         assert (ref != dev.visibility(acc, A, b, runtime.TRAVERSE_ORDERED)).mean() < 1e-3
     acc.release()
+
+
+@pytest.mark.parametrize("which", [0, 2, 3])
+def test_awkward_cameras_fused_vs_oracle(dev, which):
+    """Camera far outside the enclosure (empty camera paths), straight down next to the light (projections beyond the
+    last pixel), centimetres from a wall: the fused renderer against the oracle renderer over three passes."""
+    w, h = 48, 36
+    a = awkward_camera_arrays(which, w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=9)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(3):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3), "uni")
+    assert np.array_equal(ref.summed_sample_counts, r.summed_sample_counts)
+    np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    r.release()
+    sc.release()

@@ -5,7 +5,8 @@ import pytest
 
 from clive2_b200 import struct_types as T
 from oracle.oracle import Oracle, OracleRenderer
-from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, check_ordered_against_reference, fuzz_rays,
+from tests.common import (AWKWARD_CAMERAS, StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
+                          check_ordered_against_reference, fuzz_rays,
                           fuzz_soup, oracle_stages, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 from tests.hostemu import MODE_ORDERED, MODE_REFERENCE, HostEmu
@@ -352,3 +353,31 @@ def test_fuzzed_soups_and_degenerate_rays(O, E, seed):
             assert (ref != E.visibility(A, b, acc, MODE_ORDERED)).mean() < 1e-3  # the artefact class again
     finally:
         E.accel_destroy(acc)
+
+
+@pytest.mark.parametrize("which", range(len(AWKWARD_CAMERAS)))
+def test_awkward_cameras_stage_buffers_bit_exact(O, E, which):
+    """Cameras outside the enclosure, facing a wall, next to a wall: empty / one-vertex camera paths, connections from
+    nothing, projections beyond the last pixel.  Every stage buffer still equals the oracle, in both traversal flavours."""
+    w, h = 32, 24
+    a = awkward_camera_arrays(which, w, h)
+    seeds = seeds_for(w * h, seed=5)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+            assert_bits_equal(R.rand, S.rand, "RNG state")
+            assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+            assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+            for name in ("pix", "pth", "ry", "w", "sh"):
+                assert_bits_equal(getattr(R, name), getattr(S, name), "light entries " + name)
+            assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+            assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+            assert_bits_equal(R.sample_weights, S.sample_weights, "sample weights")
+    finally:
+        E.accel_destroy(acc)
+    if which == 0:
+        assert (R.camera_paths["length"] == 0).mean() > 0.5       # the case this camera is here for
+    if which == 2:
+        assert R.pix.max() >= w * h                               # a projection beyond the last pixel (kept, never gathered)
