@@ -77,8 +77,17 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint8)
 
 
-def assert_bits_equal(x, y, what):
-    bx, by = bits(x), bits(y)
+def _nan_canonical(a):
+    """32-bit words with every NaN bit pattern replaced by one quiet NaN: x86 and the GPU produce different payloads /
+    signs for the same invalid operation (0/0 is 0xffc00000 on SSE, 0x7fffffff on CUDA); which NaN it is never matters
+    to the path (comparisons with NaN are false, fminf/fmaxf drop it on both)."""
+    w = np.ascontiguousarray(a).view(np.uint32).copy()
+    w[(w & 0x7f800000 == 0x7f800000) & (w & 0x007fffff != 0)] = 0x7fc00000
+    return w
+
+
+def assert_bits_equal(x, y, what, nan_equal=False):
+    bx, by = (_nan_canonical(x).view(np.uint8), _nan_canonical(y).view(np.uint8)) if nan_equal else (bits(x), bits(y))
     assert bx.shape == by.shape, (what, bx.shape, by.shape)
     if not np.array_equal(bx, by):
         rows = np.flatnonzero((bx.reshape(len(x), -1) != by.reshape(len(y), -1)).any(axis=1))
@@ -259,3 +268,21 @@ def awkward_camera_arrays(which, width, height):
     specs = [{"mesh": meshgen.icosphere(1, 0.8), "offset": np.array([0.5, -0.5, 0.0]), "material": 0}]
     return scene.build_scene_arrays(width, height, np.array(center, float), np.array(direction, float), specs, mats,
                                     bvh_builder="numpy")
+
+
+@functools.lru_cache(maxsize=None)
+def random_material_arrays(trial, width, height):
+    """Cornell box + two spheres with a random material table drawn from extreme values (alpha 0 ... 3, ior 0.7 ... 10,
+    every type on every surface): total internal reflection everywhere, GGX with alpha > 1, ior = 1, and — for some
+    tables — NaN radiance, which must then be the same NaN-ness on both sides."""
+    from clive2_b200 import meshgen
+    from clive2_b200.load import make_materials
+    rng = np.random.default_rng(1000 + trial)
+    alphas, iors = [0.0, 1e-4, 0.05, 0.5, 1.0, 3.0], [1.0, 1.0001, 1.33, 2.4, 0.7, 10.0]
+    over = {m: dict(type=int(rng.integers(0, 4)), alpha=float(rng.choice(alphas)), ior=float(rng.choice(iors))) for m in range(6)}
+    over[6] = dict(emission=[1.0, 1.0, 1.0])
+    mesh = meshgen.icosphere(2, 1.0)
+    specs = [{"mesh": mesh, "offset": np.array([1.2, -0.5, 0.5]), "material": 5},
+             {"mesh": mesh, "offset": np.array([-1.5, 0.0, -0.8]), "material": 0}]
+    return scene.build_scene_arrays(width, height, np.array([0, 1.5, 6.0]), np.array([0, 0, -1.0]), specs,
+                                    make_materials(over), bvh_builder="numpy")

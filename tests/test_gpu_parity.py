@@ -10,7 +10,7 @@ from clive2_b200.renderer import Renderer
 from oracle.oracle import Oracle, OracleRenderer
 from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
                           check_ordered_against_reference, fuzz_rays,
-                          fuzz_soup, oracle_stages, random_rays,
+                          fuzz_soup, oracle_stages, random_material_arrays, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 
 pytestmark = pytest.mark.gpu
@@ -644,5 +644,38 @@ def test_awkward_cameras_fused_vs_oracle(dev, which):
     assert np.array_equal(ref.summed_sample_counts, r.summed_sample_counts)
     np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    r.release()
+    sc.release()
+
+
+@pytest.mark.parametrize("trial", [0, 2, 3, 5])
+@pytest.mark.parametrize("mode", MODES)
+def test_random_material_tables_stage_kernels(dev, O, trial, mode):
+    """Random material tables from extreme values (alpha 0 ... 3, ior 0.7 ... 10, every type on every surface), some of
+    which produce NaN radiance: every stage buffer equals the oracle, NaNs compared as NaNs (their payload bits differ
+    between SSE and the GPU and never steer a path)."""
+    w, h = 40, 30
+    a = random_material_arrays(trial, w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=trial)
+    R = oracle_stages(O, a, StageBuffers(b, seeds), upto="finalize")
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, fused=False, seeds=seeds, traverse_mode=mode)
+    r.make_light_rays(); r.make_camera_rays(); r.trace_light_rays(); r.trace_camera_rays()
+    lp, cp = r.out_light_paths.numpy(T.Path), r.out_camera_paths.numpy(T.Path)
+    for ref, got, what in ((R.light_paths, lp, "light paths"), (R.camera_paths, cp, "camera paths")):
+        assert np.array_equal(ref["length"], got["length"]), what
+        for k in range(6):
+            m = ref["length"] > k
+            if m.any():
+                assert_bits_equal(ref["rays"][m, k], got["rays"][m, k], f"{what} vertex {k}", nan_equal=True)
+    assert_bits_equal(R.rand, r.rand_buffer.numpy(np.uint32).reshape(b, 2), "RNG state")
+    r.join_paths()
+    for name, buf in (("pix", r.out_light_indices), ("pth", r.out_light_path_indices), ("ry", r.out_light_ray_indices),
+                      ("w", r.out_light_weights), ("sh", r.out_light_shade)):
+        assert_bits_equal(getattr(R, name), buf.numpy(getattr(R, name).dtype), "light entries " + name, nan_equal=True)
+    assert_bits_equal(R.aggs, r.weight_aggregators.numpy(T.WeightAggregator), "weight aggregators", nan_equal=True)
+    r.finalize_samples()
+    assert_bits_equal(R.finalized, r.finalized_samples.numpy(np.float32).reshape(b, 4), "finalized samples", nan_equal=True)
     r.release()
     sc.release()

@@ -7,7 +7,7 @@ from clive2_b200 import struct_types as T
 from oracle.oracle import Oracle, OracleRenderer
 from tests.common import (AWKWARD_CAMERAS, StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
                           check_ordered_against_reference, fuzz_rays,
-                          fuzz_soup, oracle_stages, random_rays,
+                          fuzz_soup, oracle_stages, random_material_arrays, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 from tests.hostemu import MODE_ORDERED, MODE_REFERENCE, HostEmu
 
@@ -381,3 +381,25 @@ def test_awkward_cameras_stage_buffers_bit_exact(O, E, which):
         assert (R.camera_paths["length"] == 0).mean() > 0.5       # the case this camera is here for
     if which == 2:
         assert R.pix.max() >= w * h                               # a projection beyond the last pixel (kept, never gathered)
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_random_material_tables_bit_exact(O, E, trial):
+    """Random material tables from extreme values (tests/common.py random_material_arrays) through every stage."""
+    w, h = 40, 30
+    a = random_material_arrays(trial, w, h)
+    seeds = seeds_for(w * h, seed=trial)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+            assert_bits_equal(R.rand, S.rand, "RNG state")
+            assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+            assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+            for name in ("pix", "pth", "ry", "w", "sh"):
+                assert_bits_equal(getattr(R, name), getattr(S, name), "light entries " + name)
+            assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+            assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    finally:
+        E.accel_destroy(acc)
