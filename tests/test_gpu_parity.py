@@ -679,3 +679,30 @@ def test_random_material_tables_stage_kernels(dev, O, trial, mode):
     assert_bits_equal(R.finalized, r.finalized_samples.numpy(np.float32).reshape(b, 4), "finalized samples", nan_equal=True)
     r.release()
     sc.release()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 2), (33, 1), (1, 65)])
+def test_tiny_frames(dev, w, h):
+    """One pixel, one row, one column: the 3x3 neighbourhoods of the finalize stage at every border, warps with a
+    single live lane, a pass that is smaller than one block.  Fused renderer and stage kernels against the oracle."""
+    a = arrays("empty", w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=3)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    staged = Renderer(sc, fused=False, seeds=seeds)
+    for _ in range(3):
+        ref.run_sample()
+        r.run_sample()
+        staged.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=2e-5, atol=1e-6)
+    assert_bits_equal(ref.summed_image.reshape(-1, 3), staged.summed_image.reshape(-1, 3), "staged summed_image")
+    assert_bits_equal(ref.summed_sample_weights.reshape(-1, 1), staged.summed_sample_weights.reshape(-1, 1), "staged weights")
+    assert r.image.shape == (h, w, 3)
+    for x in (r, staged):
+        x.release()
+    sc.release()

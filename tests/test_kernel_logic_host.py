@@ -403,3 +403,20 @@ def test_random_material_tables_bit_exact(O, E, trial):
             assert_bits_equal(R.finalized, S.finalized, "finalized samples")
     finally:
         E.accel_destroy(acc)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 1), (1, 3), (3, 2), (33, 1), (1, 65)])
+def test_tiny_frames_bit_exact(O, E, w, h):
+    """One pixel, one row, one column: every border case of the 3x3 finalize neighbourhood."""
+    a = arrays("empty", w, h)
+    seeds = seeds_for(w * h, seed=3)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), MODE_ORDERED)
+    finally:
+        E.accel_destroy(acc)
+    assert_bits_equal(R.rand, S.rand, "RNG state")
+    assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+    assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    assert_bits_equal(R.sample_weights, S.sample_weights, "sample weights")
