@@ -152,10 +152,16 @@ def zoo_arrays(width, height):
 
 
 def fuzz_soup(seed, n_random=300):
-    """Box[]/Triangle[] of a deliberately awkward triangle soup: random triangles, EXACT duplicates (equal t on every
+    """Box[]/Triangle[] (numpy builder) of `fuzz_triangle_soup`."""
+    from clive2_b200.bvh import build_flat_bvh
+    return build_flat_bvh(fuzz_triangle_soup(seed, n_random), builder="numpy")
+
+
+def fuzz_triangle_soup(seed, n_random=300):
+    """A deliberately awkward triangle soup (FastTreeBox): random triangles, EXACT duplicates (equal t on every
     ray: the reference keeps the first in its visiting order), coplanar overlapping pairs, zero-area and collinear
     triangles (Moeller-Trumbore divides by a = 0), large axis-aligned quads whose boxes are flat, and a far outlier."""
-    from clive2_b200.bvh import FastTreeBox, build_flat_bvh
+    from clive2_b200.bvh import FastTreeBox
     rng = np.random.default_rng(seed)
     f32 = np.float32
     base = rng.uniform(-2, 2, (n_random, 1, 3))
@@ -184,10 +190,9 @@ def fuzz_soup(seed, n_random=300):
         nrm = np.cross(corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0])
         area = np.linalg.norm(nrm, axis=1)
         nrm = np.nan_to_num(nrm / area[:, None]).astype(f32)
-    soup = FastTreeBox(np.zeros((n, 3), np.uint32), corners, corners.min(axis=1), corners.max(axis=1), nrm,
+    return FastTreeBox(np.zeros((n, 3), np.uint32), corners, corners.min(axis=1), corners.max(axis=1), nrm,
                        np.repeat(nrm[:, None, :], 3, axis=1), (area / 2).astype(f32), np.zeros(n, np.int32),
                        np.zeros(n, np.bool_), np.zeros(n, np.bool_))
-    return build_flat_bvh(soup, builder="numpy")
 
 
 def fuzz_rays(triangles, n, seed):

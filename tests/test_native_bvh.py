@@ -63,3 +63,14 @@ def test_single_triangle_and_small_inputs():
         boxes, order = native_bvh.build_order(lo, hi)
         assert sorted(order.tolist()) == list(range(n))
         assert len(boxes) == (1 if n <= 8 else 3)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_awkward_soups_identical_with_either_builder(seed):
+    """Exact duplicates (tied centroids and tied SAH costs), coplanar overlaps, zero-area triangles, flat boxes, one far
+    outlier: the native builder still emits the numpy specification's bytes."""
+    from tests.common import fuzz_triangle_soup
+    soup = fuzz_triangle_soup(seed)
+    b1, t1 = bvh.build_flat_bvh(soup, builder="numpy")
+    b2, t2 = native_bvh.build(soup)
+    assert _same(b1, b2) and _same(t1, t2)
