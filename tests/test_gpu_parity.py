@@ -706,3 +706,45 @@ def test_tiny_frames(dev, w, h):
     for x in (r, staged):
         x.release()
     sc.release()
+
+
+def test_reset_and_sharded_host_seed_upload(dev):
+    """`reset(seeds)` restarts a render exactly (same streams, same accumulators), and the end-to-end call on a renderer
+    that owns a shard of the sample ids takes the rows of ITS samples out of the whole-frame host seed buffer."""
+    w, h = 40, 28
+    a = arrays("bench-spheres", w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=41)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(2):
+        r.run_sample()
+    first = (r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b), np.array(r.unidirectional_image_buffer), np.array(r.summed_image))
+    r._fr.reset(seeds)
+    r._cache = None
+    assert r.summed_image.sum() == 0 and r.summed_sample_counts.sum() == 0
+    for _ in range(2):
+        r.run_sample()
+    assert np.array_equal(first[0], r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b))
+    assert np.array_equal(first[1].view(np.uint32), np.array(r.unidirectional_image_buffer).view(np.uint32))
+    np.testing.assert_allclose(r.summed_image, first[2], rtol=5e-4, atol=1e-6)
+    # a shard (every third id) driven through the host-buffer call
+    ids = np.arange(1, b, 3, dtype=np.uint32)
+    part = Renderer(sc, seeds=seeds_for(b, seed=42), sample_ids=ids)  # wrong seeds on purpose: the call replaces them
+    h_seeds = runtime.PinnedArray((b, 2), np.uint32)
+    h_seeds.array[:] = seeds
+    h_acc = runtime.PinnedArray((h, w, 8), np.float32)
+    part._fr.run_sample_e2e(h_seeds.ptr, h_acc.ptr)
+    full = Renderer(sc, seeds=seeds)
+    full.run_sample()
+    after = full._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2)
+    assert np.array_equal(after[ids], part._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * len(ids)).reshape(-1, 2))
+    counts = h_acc.array[..., 7].reshape(-1)
+    assert (counts[ids] == 1).all() and counts.sum() == len(ids)
+    uni_full = np.ascontiguousarray(full._accum()[..., 4:7]).reshape(b, 3)
+    assert np.array_equal(uni_full[ids].view(np.uint32), np.ascontiguousarray(h_acc.array[..., 4:7]).reshape(b, 3)[ids].view(np.uint32))
+    for x in (r, part, full):
+        x.release()
+    h_seeds.release()
+    h_acc.release()
+    sc.release()
