@@ -433,7 +433,9 @@ __global__ void k_reset_light_indices(uint32_t n, int32_t *pix, int32_t *path, i
  *   k_connect_finish     one thread per sample: stage MIS terms in shared memory, evaluate the surviving strategies
  *                        in the reference's order, splat weights, aggregator
  */
-#define CLV_RAY_CHUNK 256 /* tasks per warp in k_connect_rays */
+#ifndef CLV_RAY_CHUNK
+#define CLV_RAY_CHUNK 512 /* tasks per warp in k_connect_rays; measured 128 / 256 / 384 / 512 / 1024: 1.068 / 0.993 / 0.980 / 0.983 / 1.120 ms at C2, 256 -> 512: 6.60 -> 6.44 ms at C3 */
+#endif
 #define CLV_WARPS_PER_BLOCK (CLV_BLOCK / 32)
 
 struct ConnectScratch { /* device buffers shared by the three kernels */
