@@ -173,16 +173,22 @@ def read_obj(path):
     vs, fs = [], []
     with open(path, "r") as fh:
         for line in fh:
-            if line.startswith("v "):
-                vs.append(line.split()[1:4])
-            elif line.startswith("f "):
-                toks = line.split()[1:]
-                if len(toks) != 3:
-                    raise ValueError(f"{path}: only triangular faces are supported, got {len(toks)} corners")
-                fs.append([t.split("/", 1)[0] for t in toks])
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "v":
+                vs.append(tok[1:4])
+            elif tok[0] == "f":
+                if len(tok) != 4:
+                    raise ValueError(f"{path}: only triangular faces are supported, got {len(tok) - 1} corners")
+                face = [int(t.split("/", 1)[0]) for t in tok[1:]]
+                # a negative index counts back from the vertices defined SO FAR (relative indexing), not from the end of the file
+                fs.append([i + len(vs) if i < 0 else i - 1 for i in face])
     vertices = np.array(vs, dtype=np.float64).reshape(-1, 3)
     faces = np.array(fs, dtype=np.int64).reshape(-1, 3)
-    faces = np.where(faces < 0, faces + len(vertices), faces - 1).astype(np.int32)
+    if len(faces) and (faces.min() < 0 or faces.max() >= len(vertices)):
+        raise ValueError(f"{path}: face index out of range")
+    faces = faces.astype(np.int32)
     return vertices, faces
 
 

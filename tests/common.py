@@ -291,3 +291,29 @@ def random_material_arrays(trial, width, height):
              {"mesh": mesh, "offset": np.array([-1.5, 0.0, -0.8]), "material": 0}]
     return scene.build_scene_arrays(width, height, np.array([0, 1.5, 6.0]), np.array([0, 0, -1.0]), specs,
                                     make_materials(over), bvh_builder="numpy")
+
+
+@functools.lru_cache(maxsize=None)
+def many_lights_arrays(n_extra, width, height):
+    """Cornell box + two spheres where `n_extra` faces of one sphere are emitters too (n_extra = 0: ONE light, the
+    second ceiling triangle switched off): light pick, pdf 1 / (count * area) and hit_light on mesh lights."""
+    import dataclasses
+    from clive2_b200 import meshgen
+    from clive2_b200.load import make_materials
+    from clive2_b200.scene import surface_area
+    mesh = meshgen.icosphere(1, 0.7)
+    specs = [{"mesh": mesh, "offset": np.array([1.0, 0.5, 0.0]), "material": 5},
+             {"mesh": mesh, "offset": np.array([-1.5, -0.8, 0.5]), "material": 0}]
+    a = scene.build_scene_arrays(width, height, np.array([0, 1.5, 6.0]), np.array([0, 0, -1.0]), specs,
+                                 make_materials({0: dict(type=2, alpha=0.2)}), bvh_builder="numpy")
+    tris = a.triangles.copy()
+    extra = np.flatnonzero(tris["material"] == 5)[:n_extra]
+    tris["is_light"][extra] = 1
+    tris["material"][extra] = 6
+    if n_extra == 0:
+        tris["is_light"][np.flatnonzero(tris["is_light"] != 0)[1]] = 0
+    idx = np.flatnonzero(tris["is_light"] != 0).astype(np.int32)
+    lights = np.ascontiguousarray(tris[idx])
+    return dataclasses.replace(a, triangles=tris, light_triangles=lights, light_counts=np.array(len(lights), np.int32),
+                               light_surface_areas=np.array([surface_area(t) for t in lights], np.float32),
+                               light_triangle_indices=idx)

@@ -10,7 +10,7 @@ from clive2_b200.renderer import Renderer
 from oracle.oracle import Oracle, OracleRenderer
 from tests.common import (StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
                           check_ordered_against_reference, fuzz_rays,
-                          fuzz_soup, oracle_stages, random_material_arrays, random_rays,
+                          fuzz_soup, many_lights_arrays, oracle_stages, random_material_arrays, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 
 pytestmark = pytest.mark.gpu
@@ -747,4 +747,25 @@ def test_reset_and_sharded_host_seed_upload(dev):
         x.release()
     h_seeds.release()
     h_acc.release()
+    sc.release()
+
+
+@pytest.mark.parametrize("n_extra", [0, 9])
+def test_light_counts_fused_vs_oracle(dev, n_extra):
+    """One light and eleven lights (nine of them faces of a mesh): fused renderer against the oracle renderer."""
+    w, h = 48, 36
+    a = many_lights_arrays(n_extra, w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=8 + n_extra)
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(3):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), "aggregators")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3), "uni")
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=5e-4, atol=1e-6)
+    r.release()
     sc.release()

@@ -89,3 +89,27 @@ def test_render_movie_pipeline_keeps_frame_order_and_surfaces_writer_errors(monk
         raise OSError("disk full")
     with pytest.raises(OSError):
         movie.render_movie(None, "x", 2, 2, 1, [0, 1], 120, sink=bad_sink)
+
+
+def test_obj_relative_indices_interleaved_blocks_and_slashes(tmp_path):
+    """Negative OBJ indices count back from the vertices defined so far; `v/vt/vn` corners, tabs, comments, other records."""
+    import pytest
+    from clive2_b200.load import read_obj
+    p = tmp_path / "blocks.obj"
+    p.write_text("# two blocks\n"
+                 "v 0 0 0\nv 1 0 0\nv 0 1 0\n"
+                 "vn 0 0 1\nvt 0 0\n"
+                 "f -3/1/1 -2/1/1 -1/1/1\n"
+                 "v\t0 0 1\nv 1 0 1\n  v 0 1 1\n"
+                 "f -3//1 -2//1 -1//1\n"
+                 "f 1 5 6\n")
+    v, f = read_obj(str(p))
+    assert v.shape == (6, 3) and f.tolist() == [[0, 1, 2], [3, 4, 5], [0, 4, 5]]
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n")
+    with pytest.raises(ValueError):
+        read_obj(str(bad))
+    quad = tmp_path / "quad.obj"
+    quad.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    with pytest.raises(ValueError):
+        read_obj(str(quad))

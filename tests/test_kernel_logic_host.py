@@ -7,7 +7,7 @@ from clive2_b200 import struct_types as T
 from oracle.oracle import Oracle, OracleRenderer
 from tests.common import (AWKWARD_CAMERAS, StageBuffers, arrays, assert_bits_equal, assert_paths_equal, awkward_camera_arrays,
                           check_ordered_against_reference, fuzz_rays,
-                          fuzz_soup, oracle_stages, random_material_arrays, random_rays,
+                          fuzz_soup, many_lights_arrays, oracle_stages, random_material_arrays, random_rays,
                           rel_rmse, seeds_for, zoo_arrays)
 from tests.hostemu import MODE_ORDERED, MODE_REFERENCE, HostEmu
 
@@ -420,3 +420,26 @@ def test_tiny_frames_bit_exact(O, E, w, h):
     assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
     assert_bits_equal(R.finalized, S.finalized, "finalized samples")
     assert_bits_equal(R.sample_weights, S.sample_weights, "sample weights")
+
+
+@pytest.mark.parametrize("n_extra", [0, 1, 9])
+def test_light_counts_bit_exact(O, E, n_extra):
+    """1, 3 and 11 light triangles (the reference's scenes always have 2): light pick, light pdf, emitters on a mesh."""
+    w, h = 40, 30
+    a = many_lights_arrays(n_extra, w, h)
+    assert int(a.light_counts) == (1 if n_extra == 0 else 2 + n_extra)
+    seeds = seeds_for(w * h, seed=8 + n_extra)
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+            assert_bits_equal(R.rand, S.rand, "RNG state")
+            assert_bits_equal(R.light_rays, S.light_rays, "light rays")
+            assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+            assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+            assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+            assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    finally:
+        E.accel_destroy(acc)
+    assert len(np.unique(R.light_rays["triangle"])) == int(a.light_counts)  # every light gets picked
