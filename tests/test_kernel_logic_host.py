@@ -443,3 +443,43 @@ def test_light_counts_bit_exact(O, E, n_extra):
     finally:
         E.accel_destroy(acc)
     assert len(np.unique(R.light_rays["triangle"])) == int(a.light_counts)  # every light gets picked
+
+
+def _fused_vs_oracle_renderer(E, a, seeds, passes=3):
+    b = a.pixel_width * a.pixel_height
+    ref = OracleRenderer(a, seeds, shared_math=True)
+    s = seeds.copy()
+    aggs = np.zeros(b, T.WeightAggregator)
+    light_image = np.zeros((b, 4), np.float32)
+    accum = np.zeros((b, 8), np.float32)
+    soa = np.zeros((2 * 6 * 4 * b, 4), np.float32)
+    soa_len = np.zeros(2 * b, np.int32)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for _ in range(passes):
+            ref.run_sample()
+            E.fused_pass(a, acc, s, None, None, aggs, light_image, accum, soa=soa, soa_len=soa_len)
+    finally:
+        E.accel_destroy(acc)
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), s, "RNG state")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), aggs, "aggregators")
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), accum[:, 4:7].copy(), "unidirectional image")
+    assert np.array_equal(ref.summed_sample_counts.reshape(b), accum[:, 7].astype(np.int32))
+    assert (light_image == 0).all()
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_allclose(accum[:, 3], ref.summed_sample_weights.reshape(b), rtol=5e-5, atol=1e-6)
+        np.testing.assert_allclose(accum[:, 0:3], ref.summed_image.reshape(b, 3), rtol=5e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("which", range(len(AWKWARD_CAMERAS)))
+def test_fused_pass_awkward_cameras(E, which):
+    """The fused pass (atomic splats instead of sort + bins + gather) where light-image entries fall beyond the last
+    pixel or do not exist at all: dropped / absent exactly as in the reference's gather."""
+    w, h = 32, 24
+    _fused_vs_oracle_renderer(E, awkward_camera_arrays(which, w, h), seeds_for(w * h, seed=5))
+
+
+@pytest.mark.parametrize("n_extra", [0, 9])
+def test_fused_pass_light_counts(E, n_extra):
+    w, h = 32, 24
+    _fused_vs_oracle_renderer(E, many_lights_arrays(n_extra, w, h), seeds_for(w * h, seed=6))
