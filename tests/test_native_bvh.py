@@ -74,3 +74,22 @@ def test_awkward_soups_identical_with_either_builder(seed):
     b1, t1 = bvh.build_flat_bvh(soup, builder="numpy")
     b2, t2 = native_bvh.build(soup)
     assert _same(b1, b2) and _same(t1, t2)
+
+
+def test_thread_count_does_not_change_the_tree():
+    """The builder splits subtrees across OpenMP tasks; the emitted arrays must not depend on how many threads ran them."""
+    import subprocess
+    import sys
+    code = ("import hashlib, sys; sys.path.insert(0, %r)\n"
+            "from clive2_b200 import meshgen, native_bvh\n"
+            "from clive2_b200.load import fast_load\n"
+            "v, f = meshgen.terrain(120, 120)\n"
+            "b, t = native_bvh.build(fast_load(v, f, material=3))\n"
+            "print(hashlib.sha1(b.tobytes() + t.tobytes()).hexdigest())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = set()
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-500:]
+        digests.add(out.stdout.strip())
+    assert len(digests) == 1
