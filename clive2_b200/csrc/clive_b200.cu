@@ -112,7 +112,9 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     c->counting = 0;
     c->launches = 0;
     c->sm_count = prop.multiProcessorCount;
-    c->refill_below = getenv("CLV_REFILL_BELOW") ? atoi(getenv("CLV_REFILL_BELOW")) : 24;
+    /* measured with 512-task chunks at C2: 8 / 12 / 16 / 20 / 24 / 28 / 32 -> 1.028 / 0.968 / 0.953 / 0.956 / 0.983 / 0.992 /
+     * 1.093 ms for k_connect_rays; C3: 12 / 16 / 24 -> 6.70 / 6.44 / 6.44 ms */
+    c->refill_below = getenv("CLV_REFILL_BELOW") ? atoi(getenv("CLV_REFILL_BELOW")) : 16;
     c->ray_schedule = getenv("CLV_RAY_SCHEDULE") ? atoi(getenv("CLV_RAY_SCHEDULE")) : 8; /* measured: C2 1.15 -> 1.10 ms, C3 8.07 -> 7.10 ms */
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
