@@ -43,6 +43,8 @@ struct Node {
 
 template <typename T>
 struct Builder {
+    static const int64_t PARALLEL_AXES_MIN = 1 << 15; /* nodes at least this large sweep their three axes as tasks */
+    static const int64_t PARALLEL_SORT_MIN = 1 << 17; /* ranges at least this large are sorted as two task halves + merge */
     const T *mins, *maxes; /* [n][3] */
     int64_t n;
     int max_members, max_depth;
@@ -61,50 +63,89 @@ struct Builder {
 
     struct Scratch {
         std::vector<int64_t> order[3];
-        std::vector<T> left_area, right_area;
+        std::vector<T> left_area[3], right_area[3];
+        std::vector<int64_t> merge_buffer[3];
     };
 
+    /* stable sort of ord[0, count) by centroid along `axis`.  Large ranges are cut in two halves sorted as OpenMP tasks
+     * and merged stably: the same permutation std::stable_sort gives (a stable merge of stably sorted halves IS the
+     * stable sort), so the tree does not depend on the thread count. */
+    void sort_axis(int64_t *ord, int64_t count, int axis, int64_t *buffer) {
+        const T *c = centers.data();
+        auto less = [c, axis](int64_t a, int64_t b) { return c[3 * a + axis] < c[3 * b + axis]; };
+        if (count < PARALLEL_SORT_MIN) {
+            std::stable_sort(ord, ord + count, less);
+            return;
+        }
+        const int64_t half = count / 2;
+#pragma omp task default(shared) firstprivate(ord, half, axis, buffer)
+        sort_axis(ord, half, axis, buffer);
+#pragma omp task default(shared) firstprivate(ord, half, count, axis, buffer)
+        sort_axis(ord + half, count - half, axis, buffer + half);
+#pragma omp taskwait
+        std::merge(ord, ord + half, ord + half, ord + count, buffer, less); /* stable: ties take the left range first */
+        std::copy(buffer, buffer + count, ord);
+    }
+
+    /* SAH sweep along one axis of perm[first, first+count): cost and position of the axis' first minimum (km < 0: none) */
+    void sweep_axis(int64_t first, int64_t count, int axis, Scratch &S, double &m_out, int64_t &km_out) {
+        std::vector<int64_t> &ord = S.order[axis];
+        ord.assign(perm.begin() + first, perm.begin() + first + count);
+        if (count >= PARALLEL_SORT_MIN) S.merge_buffer[axis].resize(count);
+        sort_axis(ord.data(), count, axis, S.merge_buffer[axis].data());
+        std::vector<T> &left_area = S.left_area[axis], &right_area = S.right_area[axis];
+        left_area.resize(count);
+        right_area.resize(count);
+        T lo[3], hi[3];
+        for (int64_t k = 0; k < count; k++) { /* prefix boxes */
+            const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
+            for (int d = 0; d < 3; d++) {
+                lo[d] = (k == 0) ? mn[d] : std::min(lo[d], mn[d]);
+                hi[d] = (k == 0) ? mx[d] : std::max(hi[d], mx[d]);
+            }
+            left_area[k] = half_area_x2(lo, hi);
+        }
+        for (int64_t k = count - 1; k >= 0; k--) { /* suffix boxes */
+            const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
+            for (int d = 0; d < 3; d++) {
+                lo[d] = (k == count - 1) ? mn[d] : std::min(lo[d], mn[d]);
+                hi[d] = (k == count - 1) ? mx[d] : std::max(hi[d], mx[d]);
+            }
+            right_area[k] = half_area_x2(lo, hi);
+        }
+        /* cost[k] = left_area[k] * k + right_area[k+1] * ((n-1) - k), k = 0 .. n-2; first minimum (numpy argmin
+         * returns the first NaN if there is one) */
+        double m = 0.0;
+        int64_t km = -1;
+        for (int64_t k = 0; k + 1 < count; k++) {
+            double cost = (double)left_area[k] * (double)k + (double)right_area[k + 1] * (double)((count - 1) - k);
+            if (cost != cost) { m = cost; km = k; break; }
+            if (km < 0 || cost < m) { m = cost; km = k; }
+        }
+        m_out = m;
+        km_out = km;
+    }
+
     /* best SAH object split of perm[first, first+count); returns n_left (0 = no valid split) and leaves the chosen
-     * order in perm */
+     * order in perm.  The three axes of a large node are swept as parallel tasks (near the root there are no sibling
+     * subtrees to keep the other threads busy); the choice between them is made afterwards in x, y, z order. */
     int64_t split(int64_t first, int64_t count, Scratch &S) {
+        double m[3];
+        int64_t km[3];
+        if (count >= PARALLEL_AXES_MIN) {
+            for (int axis = 0; axis < 3; axis++) {
+#pragma omp task default(shared) firstprivate(axis, first, count)
+                sweep_axis(first, count, axis, S, m[axis], km[axis]);
+            }
+#pragma omp taskwait
+        } else {
+            for (int axis = 0; axis < 3; axis++) sweep_axis(first, count, axis, S, m[axis], km[axis]);
+        }
         double best_cost = std::numeric_limits<double>::infinity();
         int best_axis = -1;
         int64_t best_left = 0;
-        S.left_area.resize(count);
-        S.right_area.resize(count);
-        for (int axis = 0; axis < 3; axis++) {
-            std::vector<int64_t> &ord = S.order[axis];
-            ord.assign(perm.begin() + first, perm.begin() + first + count);
-            const T *c = centers.data();
-            std::stable_sort(ord.begin(), ord.end(), [c, axis](int64_t a, int64_t b) { return c[3 * a + axis] < c[3 * b + axis]; });
-            T lo[3], hi[3];
-            for (int64_t k = 0; k < count; k++) { /* prefix boxes */
-                const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
-                for (int d = 0; d < 3; d++) {
-                    lo[d] = (k == 0) ? mn[d] : std::min(lo[d], mn[d]);
-                    hi[d] = (k == 0) ? mx[d] : std::max(hi[d], mx[d]);
-                }
-                S.left_area[k] = half_area_x2(lo, hi);
-            }
-            for (int64_t k = count - 1; k >= 0; k--) { /* suffix boxes */
-                const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
-                for (int d = 0; d < 3; d++) {
-                    lo[d] = (k == count - 1) ? mn[d] : std::min(lo[d], mn[d]);
-                    hi[d] = (k == count - 1) ? mx[d] : std::max(hi[d], mx[d]);
-                }
-                S.right_area[k] = half_area_x2(lo, hi);
-            }
-            /* cost[k] = left_area[k] * k + right_area[k+1] * ((n-1) - k), k = 0 .. n-2; first minimum (numpy argmin
-             * returns the first NaN if there is one) */
-            double m = 0.0;
-            int64_t km = -1;
-            for (int64_t k = 0; k + 1 < count; k++) {
-                double cost = (double)S.left_area[k] * (double)k + (double)S.right_area[k + 1] * (double)((count - 1) - k);
-                if (cost != cost) { m = cost; km = k; break; }
-                if (km < 0 || cost < m) { m = cost; km = k; }
-            }
-            if (km >= 0 && m < best_cost) { best_cost = m; best_axis = axis; best_left = km + 1; }
-        }
+        for (int axis = 0; axis < 3; axis++)
+            if (km[axis] >= 0 && m[axis] < best_cost) { best_cost = m[axis]; best_axis = axis; best_left = km[axis] + 1; }
         if (best_axis < 0) return 0;
         std::copy(S.order[best_axis].begin(), S.order[best_axis].end(), perm.begin() + first);
         return best_left;
@@ -227,4 +268,47 @@ int64_t clv_bvh_build(const void *mins, const void *maxes, int is_double, int64_
                                       (FlatBox *)out_boxes, box_capacity, out_order);
     return run<float>((const float *)mins, (const float *)maxes, n, max_members, max_depth, (FlatBox *)out_boxes,
                       box_capacity, out_order);
+}
+
+/* struct_types.Triangle records for soup members `order` (bvh.py:361-370 of the reference, bvh.emit_triangles here):
+ * corners / smoothed corner normals [n][3][3] and face normals [n][3] of float (is_double = 0) or double, narrowed to
+ * float32 by a plain conversion (round to nearest even, what numpy's astype does); material int32, emitter / camera
+ * bool bytes.  A memory-bound gather: one OpenMP loop. */
+namespace {
+struct FlatTriangle { /* struct_types.Triangle, 128 bytes */
+    float v[3][4], n[3][4], normal[4];
+    int32_t material, is_light, is_camera, pad;
+};
+static_assert(sizeof(FlatTriangle) == 128, "Triangle");
+
+template <typename T>
+void emit(const int64_t *order, int64_t count, const T *corners, const T *smooth, const T *face_normals,
+          const int32_t *material, const uint8_t *emitter, const uint8_t *camera, FlatTriangle *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < count; k++) {
+        const int64_t i = order[k];
+        FlatTriangle t;
+        memset(&t, 0, sizeof t);
+        for (int c = 0; c < 3; c++)
+            for (int d = 0; d < 3; d++) {
+                t.v[c][d] = (float)corners[9 * i + 3 * c + d];
+                t.n[c][d] = (float)smooth[9 * i + 3 * c + d];
+            }
+        for (int d = 0; d < 3; d++) t.normal[d] = (float)face_normals[3 * i + d];
+        t.material = material[i];
+        t.is_light = emitter[i] ? 1 : 0;
+        t.is_camera = camera[i] ? 1 : 0;
+        out[k] = t;
+    }
+}
+} /* namespace */
+
+extern "C" __attribute__((visibility("default")))
+void clv_emit_triangles(const int64_t *order, int64_t count, int is_double, const void *corners, const void *smooth,
+                        const void *face_normals, const int32_t *material, const uint8_t *emitter,
+                        const uint8_t *camera, void *out) {
+    if (is_double) emit<double>(order, count, (const double *)corners, (const double *)smooth, (const double *)face_normals,
+                                material, emitter, camera, (FlatTriangle *)out);
+    else emit<float>(order, count, (const float *)corners, (const float *)smooth, (const float *)face_normals, material,
+                     emitter, camera, (FlatTriangle *)out);
 }

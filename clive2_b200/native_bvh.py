@@ -35,6 +35,8 @@ def _load():
         lib.clv_bvh_build.restype = C.c_int64
         lib.clv_bvh_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                       C.c_int64, C.c_void_p]
+        lib.clv_emit_triangles.restype = None
+        lib.clv_emit_triangles.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7
         _lib = lib
     return _lib
 
@@ -57,8 +59,26 @@ def build_order(mins, maxes, max_members=MAX_MEMBERS, max_depth=MAX_DEPTH):
     return boxes[:nb].copy(), order
 
 
+def emit_triangles(soup, order):
+    """`bvh.emit_triangles` as one native gather (numpy's fancy indexing of the ten soup arrays is as slow as the build
+    itself at a million triangles); falls back to the numpy version for soups whose arrays it cannot take as they are."""
+    from .bvh import emit_triangles as numpy_emit
+    from .struct_types import Triangle
+    f = soup.triangles.dtype
+    same = all(a.dtype == f for a in (soup.smoothed_normals, soup.face_normals))
+    if f not in (np.float32, np.float64) or not same or soup.material.dtype != np.int32:
+        return numpy_emit(soup, order)
+    lib = _load()
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    arrays = [np.ascontiguousarray(a) for a in (soup.triangles, soup.smoothed_normals, soup.face_normals, soup.material,
+                                                soup.emitter.astype(np.uint8), soup.camera.astype(np.uint8))]
+    out = np.empty(len(order), dtype=Triangle)
+    lib.clv_emit_triangles(order.ctypes.data_as(C.c_void_p), len(order), int(f == np.float64),
+                           *[a.ctypes.data_as(C.c_void_p) for a in arrays], out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def build(soup):
     """Soup (bvh.FastTreeBox) -> (Box[], Triangle[]) like bvh.np_flatten_bvh(bvh.construct_BVH(soup))."""
-    from .bvh import emit_triangles
     boxes, order = build_order(soup.mins, soup.maxes)
     return boxes, emit_triangles(soup, order)
