@@ -4,7 +4,8 @@
  * src/bvh.py:132-191, 288-389) emits with a stable sort: greedy top-down SAH object split on centroid-sorted triangles,
  * leaves of <= max_members triangles, breadth-first flat layout with "right == 0 => inner node, children at left and
  * left + 1".  The reference needs ~55 us per triangle and an O(n^2) flatten (minutes at 1 M triangles, tens of minutes
- * at 10 M); this one is O(n log^2 n) and runs subtrees as OpenMP tasks.
+ * at 10 M); this one sorts the triangles three times at the root and then only partitions (O(n log n)), and runs
+ * subtrees, the three sweeps of large nodes and the halves of the root's sorts as OpenMP tasks.
  *
  * Reference behaviours that shape the tree and are therefore kept:
  *   - arithmetic in the soup's own dtype T (float32 for the Cornell-only scene, float64 once a mesh joins): centroid
@@ -61,44 +62,46 @@ struct Builder {
         return (T)2 * sum;
     }
 
-    struct Scratch {
-        std::vector<int64_t> order[3];
-        std::vector<T> left_area[3], right_area[3];
-        std::vector<int64_t> merge_buffer[3];
-    };
+    struct Keyed { T key; int64_t idx; }; /* centroid coordinate next to the index: sorts and sweeps read memory in order */
+    typedef std::vector<Keyed> Order;
 
-    /* stable sort of ord[0, count) by centroid along `axis`.  Large ranges are cut in two halves sorted as OpenMP tasks
-     * and merged stably: the same permutation std::stable_sort gives (a stable merge of stably sorted halves IS the
-     * stable sort), so the tree does not depend on the thread count. */
-    void sort_axis(int64_t *ord, int64_t count, int axis, int64_t *buffer) {
-        const T *c = centers.data();
-        auto less = [c, axis](int64_t a, int64_t b) { return c[3 * a + axis] < c[3 * b + axis]; };
+    /* One node's work: its triangles in three orders, each the STABLE sort of the node's current order P by the centroid
+     * coordinate of that axis (what bvh.py's `argsort(kind="stable")` of the node's member list gives).  P itself is the
+     * order along `cur_axis`, the axis the parent was split on (the root's P is the input order). */
+    struct Work {
+        int64_t id, first, count;
+        int left_turns, cur_axis;
+        Order K[3];
+    };
+    std::vector<int64_t> pos;   /* [n] position of a triangle in the order of the split axis of the node being split */
+    std::vector<uint8_t> side;  /* [n] 0 = goes left, 1 = goes right */
+
+    /* stable sort of a[0, count) by key.  Large ranges are cut in two halves sorted as OpenMP tasks and merged stably:
+     * the same permutation std::stable_sort gives (a stable merge of stably sorted halves IS the stable sort), so the
+     * tree does not depend on the thread count. */
+    static void sort_keyed(Keyed *a, int64_t count, Keyed *buffer) {
+        auto less = [](const Keyed &x, const Keyed &y) { return x.key < y.key; };
         if (count < PARALLEL_SORT_MIN) {
-            std::stable_sort(ord, ord + count, less);
+            std::stable_sort(a, a + count, less);
             return;
         }
         const int64_t half = count / 2;
-#pragma omp task default(shared) firstprivate(ord, half, axis, buffer)
-        sort_axis(ord, half, axis, buffer);
-#pragma omp task default(shared) firstprivate(ord, half, count, axis, buffer)
-        sort_axis(ord + half, count - half, axis, buffer + half);
+#pragma omp task default(shared) firstprivate(a, half, buffer)
+        sort_keyed(a, half, buffer);
+#pragma omp task default(shared) firstprivate(a, half, count, buffer)
+        sort_keyed(a + half, count - half, buffer + half);
 #pragma omp taskwait
-        std::merge(ord, ord + half, ord + half, ord + count, buffer, less); /* stable: ties take the left range first */
-        std::copy(buffer, buffer + count, ord);
+        std::merge(a, a + half, a + half, a + count, buffer, less); /* stable: ties take the left range first */
+        std::copy(buffer, buffer + count, a);
     }
 
-    /* SAH sweep along one axis of perm[first, first+count): cost and position of the axis' first minimum (km < 0: none) */
-    void sweep_axis(int64_t first, int64_t count, int axis, Scratch &S, double &m_out, int64_t &km_out) {
-        std::vector<int64_t> &ord = S.order[axis];
-        ord.assign(perm.begin() + first, perm.begin() + first + count);
-        if (count >= PARALLEL_SORT_MIN) S.merge_buffer[axis].resize(count);
-        sort_axis(ord.data(), count, axis, S.merge_buffer[axis].data());
-        std::vector<T> &left_area = S.left_area[axis], &right_area = S.right_area[axis];
-        left_area.resize(count);
-        right_area.resize(count);
+    /* SAH sweep along one order: cost and position of its first minimum (km < 0: none) */
+    void sweep(const Order &ord, double &m_out, int64_t &km_out) const {
+        const int64_t count = (int64_t)ord.size();
+        std::vector<T> left_area(count), right_area(count);
         T lo[3], hi[3];
         for (int64_t k = 0; k < count; k++) { /* prefix boxes */
-            const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
+            const T *mn = mins + 3 * ord[k].idx, *mx = maxes + 3 * ord[k].idx;
             for (int d = 0; d < 3; d++) {
                 lo[d] = (k == 0) ? mn[d] : std::min(lo[d], mn[d]);
                 hi[d] = (k == 0) ? mx[d] : std::max(hi[d], mx[d]);
@@ -106,7 +109,7 @@ struct Builder {
             left_area[k] = half_area_x2(lo, hi);
         }
         for (int64_t k = count - 1; k >= 0; k--) { /* suffix boxes */
-            const T *mn = mins + 3 * ord[k], *mx = maxes + 3 * ord[k];
+            const T *mn = mins + 3 * ord[k].idx, *mx = maxes + 3 * ord[k].idx;
             for (int d = 0; d < 3; d++) {
                 lo[d] = (k == count - 1) ? mn[d] : std::min(lo[d], mn[d]);
                 hi[d] = (k == count - 1) ? mx[d] : std::max(hi[d], mx[d]);
@@ -126,35 +129,10 @@ struct Builder {
         km_out = km;
     }
 
-    /* best SAH object split of perm[first, first+count); returns n_left (0 = no valid split) and leaves the chosen
-     * order in perm.  The three axes of a large node are swept as parallel tasks (near the root there are no sibling
-     * subtrees to keep the other threads busy); the choice between them is made afterwards in x, y, z order. */
-    int64_t split(int64_t first, int64_t count, Scratch &S) {
-        double m[3];
-        int64_t km[3];
-        if (count >= PARALLEL_AXES_MIN) {
-            for (int axis = 0; axis < 3; axis++) {
-#pragma omp task default(shared) firstprivate(axis, first, count)
-                sweep_axis(first, count, axis, S, m[axis], km[axis]);
-            }
-#pragma omp taskwait
-        } else {
-            for (int axis = 0; axis < 3; axis++) sweep_axis(first, count, axis, S, m[axis], km[axis]);
-        }
-        double best_cost = std::numeric_limits<double>::infinity();
-        int best_axis = -1;
-        int64_t best_left = 0;
-        for (int axis = 0; axis < 3; axis++)
-            if (km[axis] >= 0 && m[axis] < best_cost) { best_cost = m[axis]; best_axis = axis; best_left = km[axis] + 1; }
-        if (best_axis < 0) return 0;
-        std::copy(S.order[best_axis].begin(), S.order[best_axis].end(), perm.begin() + first);
-        return best_left;
-    }
-
-    void bounds(int64_t first, int64_t count, double lo[3], double hi[3]) const {
+    void bounds_of(const Keyed *a, int64_t count, double lo[3], double hi[3]) const {
         T l[3], h[3];
         for (int64_t k = 0; k < count; k++) {
-            const T *mn = mins + 3 * perm[first + k], *mx = maxes + 3 * perm[first + k];
+            const T *mn = mins + 3 * a[k].idx, *mx = maxes + 3 * a[k].idx;
             for (int d = 0; d < 3; d++) {
                 l[d] = (k == 0) ? mn[d] : std::min(l[d], mn[d]);
                 h[d] = (k == 0) ? mx[d] : std::max(h[d], mx[d]);
@@ -163,49 +141,109 @@ struct Builder {
         for (int d = 0; d < 3; d++) { lo[d] = (double)l[d]; hi[d] = (double)h[d]; }
     }
 
-    int64_t new_node(int64_t first, int64_t count) {
-        int64_t id;
-#pragma omp critical(clv_bvh_nodes)
-        {
-            id = (int64_t)nodes.size();
-            nodes.emplace_back();
+    /* `src` (one of the node's orders, axis != split axis) cut into the members of the two children, each again the
+     * stable sort of the CHILD's current order by this axis.  A stable partition keeps the sort; what changes is the
+     * tie order: equal keys must follow the child's current order, which is the order along the split axis (`pos`),
+     * no longer the node's own.  When the node was itself split along the same axis as its parent the two agree. */
+    void partition(const Order &src, int64_t n_left, bool fix_ties, Order &left, Order &right) const {
+        const int64_t count = (int64_t)src.size();
+        left.resize(n_left);
+        right.resize(count - n_left);
+        int64_t nl = 0, nr = 0;
+        for (int64_t k = 0; k < count; k++) {
+            if (side[src[k].idx]) right[nr++] = src[k];
+            else left[nl++] = src[k];
         }
-        return id;
+        if (!fix_ties) return;
+        for (Order *o : {&left, &right}) {
+            Keyed *a = o->data();
+            const int64_t m = (int64_t)o->size();
+            for (int64_t k = 0; k < m;) {
+                int64_t e = k + 1;
+                while (e < m && !(a[k].key < a[e].key) && !(a[e].key < a[k].key)) e++;
+                if (e - k > 1) {
+                    const int64_t *p = pos.data();
+                    std::sort(a + k, a + e, [p](const Keyed &x, const Keyed &y) { return p[x.idx] < p[y.idx]; });
+                }
+                k = e;
+            }
+        }
     }
 
-    /* builds the subtree of node `id` (range and box already set) */
-    void build(int64_t id, int left_turns) {
-        int64_t first, count;
-#pragma omp critical(clv_bvh_nodes)
-        { first = nodes[id].first; count = nodes[id].count; }
-        if (count <= max_members || left_turns > max_depth) return;
-        Scratch S;
-        int64_t n_left = split(first, count, S);
-        if (n_left <= 0 || n_left >= count) return;
-        Node l, r;
-        l.first = first; l.count = n_left;
-        r.first = first + n_left; r.count = count - n_left;
-        bounds(l.first, l.count, l.lo, l.hi);
-        bounds(r.first, r.count, r.lo, r.hi);
-        int64_t li, ri;
-#pragma omp critical(clv_bvh_nodes)
-        {
-            li = (int64_t)nodes.size();
-            nodes.push_back(l);
-            ri = (int64_t)nodes.size();
-            nodes.push_back(r);
-            nodes[id].left = li;
-            nodes[id].right = ri;
-        }
-        if (count > 8192) {
-#pragma omp task default(shared) firstprivate(li, left_turns)
-            build(li, left_turns + 1);
-#pragma omp task default(shared) firstprivate(ri, left_turns)
-            build(ri, left_turns);
+    void write_leaf(const Work &w) {
+        /* the leaf keeps its triangles in the node's current order (the root's is the input order, already in perm) */
+        if (w.cur_axis < 0) return;
+        const Order &p = w.K[w.cur_axis];
+        for (int64_t k = 0; k < w.count; k++) perm[w.first + k] = p[k].idx;
+    }
+
+    /* builds the subtree of the node described by `w` (range and box already set in nodes[w.id]); owns and frees w */
+    void build(Work *wp) {
+        Work &w = *wp;
+        if (w.count <= max_members || w.left_turns > max_depth) { write_leaf(w); delete wp; return; }
+        double m[3];
+        int64_t km[3];
+        if (w.count >= PARALLEL_AXES_MIN) { /* near the root there are no sibling subtrees to keep the other threads busy */
+            for (int axis = 0; axis < 3; axis++) {
+#pragma omp task default(shared) firstprivate(axis)
+                sweep(w.K[axis], m[axis], km[axis]);
+            }
 #pragma omp taskwait
         } else {
-            build(li, left_turns + 1);
-            build(ri, left_turns);
+            for (int axis = 0; axis < 3; axis++) sweep(w.K[axis], m[axis], km[axis]);
+        }
+        /* first minimum inside an axis, strict improvement across axes x -> y -> z */
+        double best_cost = std::numeric_limits<double>::infinity();
+        int split_axis = -1;
+        int64_t n_left = 0;
+        for (int axis = 0; axis < 3; axis++)
+            if (km[axis] >= 0 && m[axis] < best_cost) { best_cost = m[axis]; split_axis = axis; n_left = km[axis] + 1; }
+        if (split_axis < 0 || n_left <= 0 || n_left >= w.count) { write_leaf(w); delete wp; return; }
+
+        const Order &along = w.K[split_axis];
+        for (int64_t k = 0; k < w.count; k++) {
+            pos[along[k].idx] = k;
+            side[along[k].idx] = k < n_left ? 0 : 1;
+        }
+        Work *l = new Work(), *r = new Work();
+        l->first = w.first; l->count = n_left;
+        r->first = w.first + n_left; r->count = w.count - n_left;
+        l->left_turns = w.left_turns + 1; r->left_turns = w.left_turns;
+        l->cur_axis = r->cur_axis = split_axis;
+        for (int axis = 0; axis < 3; axis++) {
+            if (axis == split_axis) {
+                l->K[axis].assign(along.begin(), along.begin() + n_left);
+                r->K[axis].assign(along.begin() + n_left, along.end());
+            } else {
+                partition(w.K[axis], n_left, split_axis != w.cur_axis, l->K[axis], r->K[axis]);
+            }
+            Order().swap(w.K[axis]); /* the parent's copy is not needed any more */
+        }
+        Node ln, rn;
+        ln.first = l->first; ln.count = l->count;
+        rn.first = r->first; rn.count = r->count;
+        bounds_of(l->K[split_axis].data(), l->count, ln.lo, ln.hi);
+        bounds_of(r->K[split_axis].data(), r->count, rn.lo, rn.hi);
+#pragma omp critical(clv_bvh_nodes)
+        {
+            l->id = (int64_t)nodes.size();
+            nodes.push_back(ln);
+            r->id = (int64_t)nodes.size();
+            nodes.push_back(rn);
+            nodes[w.id].left = l->id;
+            nodes[w.id].right = r->id;
+        }
+        const bool parallel = w.count > 8192;
+        delete wp;
+        if (parallel) {
+#pragma omp task default(shared) firstprivate(l)
+            build(l);
+#pragma omp task default(shared) firstprivate(r)
+            build(r);
+#pragma omp taskwait
+        } else {
+            build(l);
+            build(r);
         }
     }
 };
@@ -219,15 +257,34 @@ int64_t run(const T *mins, const T *maxes, int64_t n, int max_members, int max_d
     for (int64_t i = 0; i < n * 3; i++) B.centers[i] = (mins[i] + maxes[i]) / (T)2;
     B.perm.resize(n);
     for (int64_t i = 0; i < n; i++) B.perm[i] = i;
+    B.pos.assign((size_t)n, 0);
+    B.side.assign((size_t)n, 0);
     B.nodes.reserve((size_t)std::max<int64_t>(16, n / 2));
     Node root;
     root.first = 0; root.count = n;
-    B.bounds(0, n, root.lo, root.hi);
+    typename Builder<T>::Work *w = new typename Builder<T>::Work();
+    w->id = 0; w->first = 0; w->count = n; w->left_turns = 0; w->cur_axis = -1;
+    for (int axis = 0; axis < 3; axis++) {
+        w->K[axis].resize((size_t)n);
+        for (int64_t i = 0; i < n; i++) { w->K[axis][i].key = B.centers[3 * i + axis]; w->K[axis][i].idx = i; }
+    }
     if (n == 0) for (int d = 0; d < 3; d++) { root.lo[d] = INFINITY; root.hi[d] = -INFINITY; }
+    else B.bounds_of(w->K[0].data(), n, root.lo, root.hi);
     B.nodes.push_back(root);
 #pragma omp parallel
 #pragma omp single
-    B.build(0, 0);
+    {
+        /* the only sorts of the whole build: the root's three orders (stable, so ties keep the input order) */
+        for (int axis = 0; axis < 3; axis++) {
+#pragma omp task default(shared) firstprivate(axis)
+            {
+                typename Builder<T>::Order buffer(n >= Builder<T>::PARALLEL_SORT_MIN ? (size_t)n : 0);
+                Builder<T>::sort_keyed(w->K[axis].data(), n, buffer.data());
+            }
+        }
+#pragma omp taskwait
+        B.build(w);
+    }
 
     /* breadth-first flatten (bvh.py:329-389) */
     if ((int64_t)B.nodes.size() > box_capacity) return -(int64_t)B.nodes.size();
