@@ -93,3 +93,21 @@ def test_thread_count_does_not_change_the_tree():
         assert out.returncode == 0, out.stderr[-500:]
         digests.add(out.stdout.strip())
     assert len(digests) == 1
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("n,levels", [(300, 2), (1000, 3), (2000, 1)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_massive_centroid_ties(seed, n, levels, dtype):
+    """Coordinates quantised to a handful of values: almost every centroid ties on every axis and many SAH costs tie too.
+    The native builder sorts once at the root and then partitions, repairing the order inside runs of equal keys; the
+    numpy specification re-sorts every node.  Same bytes."""
+    rng = np.random.default_rng(seed)
+    corners = (rng.integers(0, levels, (n, 1, 3)) + rng.integers(0, 2, (n, 3, 3)) * 0.5).astype(dtype)
+    zeros = np.zeros((n, 3), dtype)
+    soup = bvh.FastTreeBox(np.zeros((n, 3), np.uint32), corners, corners.min(axis=1), corners.max(axis=1), zeros,
+                           np.repeat(zeros[:, None, :], 3, axis=1), np.zeros(n, dtype), np.zeros(n, np.int32),
+                           np.zeros(n, np.bool_), np.zeros(n, np.bool_))
+    b1, t1 = bvh.build_flat_bvh(soup, builder="numpy")
+    b2, t2 = native_bvh.build(soup)
+    assert _same(b1, b2) and _same(t1, t2)
