@@ -533,6 +533,9 @@ class FusedRenderer:
                          _host_ptr(keep[4]), len(keep[2]))
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32).reshape(self.n_pixels, 2)
         ids = None if sample_ids is None else np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        if ids is not None and len(ids) == 0:
+            raise ValueError("empty shard: this rank owns no sample ids (frame smaller than world_size tiles?); "
+                             "render with fewer ranks or smaller tiles")
         if ids is not None and len(np.unique(ids)) != len(ids):
             # every pixel's accumulator is updated without atomics by the one sample that owns it
             raise ValueError("sample_ids must not contain duplicates")

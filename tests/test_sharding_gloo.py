@@ -96,3 +96,13 @@ def test_tiled_order_is_a_permutation_of_compact_blocks():
     assert xs.max() - xs.min() == 7 and ys.max() - ys.min() == 3  # one warp = one 8x4 pixel block
     o2 = sharding.tiled_order(70, 33, 8, 4)  # ragged edges
     assert np.array_equal(np.sort(o2), np.arange(70 * 33, dtype=np.uint32))
+
+
+def test_more_ranks_than_tiles_leaves_empty_shards():
+    """A 16x16 frame is ONE 16x16 tile: ranks 1.. own nothing (the renderer refuses an empty shard with a clear message;
+    the caller picks a smaller tile)."""
+    from clive2_b200 import sharding
+    assert len(sharding.tile_ids(16, 16, 0, 4, 16)) == 256
+    assert all(len(sharding.tile_ids(16, 16, r, 4, 16)) == 0 for r in (1, 2, 3))
+    parts = [sharding.tile_ids(16, 16, r, 4, 4) for r in range(4)]
+    assert all(len(p) == 64 for p in parts) and len(np.unique(np.concatenate(parts))) == 256
