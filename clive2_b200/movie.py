@@ -3,6 +3,7 @@
 
     python -m clive2_b200.movie render --scene bench-spheres --width 512 --height 512 --samples 64 --out out.png
     torchrun --nproc-per-node 8 -m clive2_b200.movie movie --scene bench-spheres --movie-frames 120 --samples 32
+    torchrun --nproc-per-node 8 -m clive2_b200.movie render --scene bench-terrain-10m --width 1920 --height 1080 --samples 256
 
 Frames of a movie are independent (the reference rebuilds scene + BVH + renderer per frame, movie.py:29-55), so frame f
 goes to rank f mod world_size and no collective is needed; within a rank the host work of neighbouring frames (scene
@@ -68,6 +69,36 @@ def render_frame(device, preset, width, height, samples, frame_idx=None, total_f
     return render_arrays(device, frame_arrays(preset, width, height, frame_idx, total_frames), samples, seed)
 
 
+def passes_for_rank(samples, rank, world):
+    """How many of the `samples` passes of one image `rank` renders (pass sharding: the first `samples % world` ranks
+    take one more)."""
+    return samples // world + (1 if rank < samples % world else 0)
+
+
+def render_frame_sharded(device, preset, width, height, samples, rank, world, local_rank, seed=None):
+    """One image on `world` GPUs (BASELINE config 4): every rank renders its share of the passes over the
+    full frame from its own RNG streams (`sharding.rank_seeds`), ONE NCCL reduce sums the packed accumulators on rank 0,
+    which tone-maps.  Returns the image on rank 0 and None elsewhere.  torch.distributed must be initialised (nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import sharding
+    arrays = frame_arrays(preset, width, height)
+    sc = scene.scene_from_arrays(arrays, device)
+    base = 20240928 if seed is None else int(seed)
+    r = Renderer(sc, seeds=sharding.rank_seeds(width * height, base, rank))
+    for _ in range(passes_for_rank(samples, rank, world)):
+        r.run_sample()
+    device.synchronize()
+    acc = torch.as_tensor(r.accumulator_buffer(), device=torch.device("cuda", local_rank))
+    sharding.reduce_accumulators(acc, dst=0)
+    torch.cuda.synchronize(local_rank)
+    image = r.image if rank == 0 else None  # accumulator_buffer() dropped the host cache: this reads the reduced sums
+    r.release()
+    sc.release()
+    return image
+
+
 def render_movie(device, preset, width, height, samples, frames, total_frames, seed=None, sink=None, overlap=True):
     """Frames `frames` of the orbit movie, in order; `sink(frame_idx, image)` receives each image (e.g. the PNG
     writer).  The reference does scene + BVH + render + imwrite serially per frame (movie.py:29-55); here the host
@@ -117,9 +148,22 @@ def main(argv=None):
     dev = runtime.Device(int(os.environ.get("LOCAL_RANK", 0)))
     if args.cmd == "render":
         t0 = time.time()
-        img = render_frame(dev, args.scene, args.width, args.height, args.samples, seed=args.seed)
+        if world > 1:  # torchrun: the passes of the one image are dealt to the ranks, one NCCL reduce at the end
+            import torch
+            import torch.distributed as dist
+            local_rank = int(os.environ.get("LOCAL_RANK", 0))
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            img = render_frame_sharded(dev, args.scene, args.width, args.height, args.samples, rank, world, local_rank,
+                                       seed=args.seed)
+            dist.barrier()
+            dist.destroy_process_group()
+            if rank != 0:
+                return
+        else:
+            img = render_frame(dev, args.scene, args.width, args.height, args.samples, seed=args.seed)
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
-        print(f"{write_image(args.out, img)}: {args.samples} passes in {time.time() - t0:.2f} s")
+        print(f"{write_image(args.out, img)}: {args.samples} passes on {world} GPU(s) in {time.time() - t0:.2f} s")
         return
     out_dir = os.path.join(args.out_dir, args.movie_name)
     os.makedirs(out_dir, exist_ok=True)

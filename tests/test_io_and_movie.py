@@ -113,3 +113,11 @@ def test_obj_relative_indices_interleaved_blocks_and_slashes(tmp_path):
     quad.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
     with pytest.raises(ValueError):
         read_obj(str(quad))
+
+
+def test_passes_are_dealt_to_ranks_completely():
+    from clive2_b200.movie import passes_for_rank
+    for samples in (0, 1, 7, 8, 256, 1001):
+        for world in (1, 2, 3, 8):
+            shares = [passes_for_rank(samples, r, world) for r in range(world)]
+            assert sum(shares) == samples and max(shares) - min(shares) <= 1 and shares == sorted(shares, reverse=True)
