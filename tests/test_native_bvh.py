@@ -111,3 +111,18 @@ def test_massive_centroid_ties(seed, n, levels, dtype):
     b1, t1 = bvh.build_flat_bvh(soup, builder="numpy")
     b2, t2 = native_bvh.build(soup)
     assert _same(b1, b2) and _same(t1, t2)
+
+
+def test_bench_trees_stay_far_below_the_reference_stack():
+    """trace.metal:144-176 stops traversing when its 64-entry stack fills (one entry per level of the path being
+    descended); the kernels do not reproduce that abort, so the trees in use must be much shallower than 62 levels."""
+    def depth(boxes):
+        d = np.zeros(len(boxes), np.int32)
+        for b in range(len(boxes)):  # breadth-first layout: parents come before their children
+            if boxes["right"][b] == 0:
+                d[boxes["left"][b]] = d[boxes["left"][b] + 1] = d[b] + 1
+        return int(d.max())
+    assert depth(scene.preset_arrays("empty", 32, 32).boxes) <= 4
+    assert depth(scene.preset_arrays("bench-spheres", 32, 32).boxes) <= 24
+    v, f = meshgen.terrain(200, 200)
+    assert depth(native_bvh.build(fast_load(v, f, material=3))[0]) <= 30
