@@ -483,3 +483,34 @@ def test_fused_pass_awkward_cameras(E, which):
 def test_fused_pass_light_counts(E, n_extra):
     w, h = 32, 24
     _fused_vs_oracle_renderer(E, many_lights_arrays(n_extra, w, h), seeds_for(w * h, seed=6))
+
+
+def test_random_number_exactly_one(O, E):
+    """xorshift states >= 0xffffff80 convert to exactly 1.0: the light pick `(int)(r * count)`
+    then equals `count` (out of bounds in the reference; clamped here and in the oracle), a barycentric draw of 1.0
+    lands on a vertex, a roll of 1.0 never passes `<= fresnel`.  Seeds are chosen so that the FIRST draw of either stream
+    of some samples is 1.0 (0x5e6cfce7, 0x4a4d939f, 0x55935ce6 are the xorshift32 pre-images of 0xffffffff, 0xffffff80,
+    0xffffffc1)."""
+    w, h = 24, 16
+    a = arrays("bench-spheres", w, h)
+    seeds = seeds_for(w * h, seed=12)
+    pre = np.array([0x5E6CFCE7, 0x4A4D939F, 0x55935CE6], np.uint32)
+    seeds[0:3, 0] = pre          # light pick r == 1.0
+    seeds[3:6, 1] = pre          # second stream: barycentric / direction draws of 1.0
+    seeds[6:9, 0] = pre
+    seeds[6:9, 1] = pre[::-1]
+    R = oracle_stages(O, a, StageBuffers(w * h, seeds), upto="finalize")
+    assert (R.light_rays["triangle"][:3] == a.light_triangle_indices[-1]).all()  # clamped to the last light
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            S = emu_stages(E, acc, a, StageBuffers(w * h, seeds), mode)
+            assert_bits_equal(R.rand, S.rand, "RNG state")
+            assert_bits_equal(R.light_rays, S.light_rays, "light rays")
+            assert_bits_equal(R.camera_rays, S.camera_rays, "camera rays")
+            assert_paths_equal(R.light_paths, S.light_paths, "light paths")
+            assert_paths_equal(R.camera_paths, S.camera_paths, "camera paths")
+            assert_bits_equal(R.aggs, S.aggs, "weight aggregators")
+            assert_bits_equal(R.finalized, S.finalized, "finalized samples")
+    finally:
+        E.accel_destroy(acc)
