@@ -514,3 +514,12 @@ def test_random_number_exactly_one(O, E):
             assert_bits_equal(R.finalized, S.finalized, "finalized samples")
     finally:
         E.accel_destroy(acc)
+
+
+@pytest.mark.parametrize("trial", [0, 2, 3])
+def test_fused_pass_scrubs_nan_radiance_like_the_reference(E, trial):
+    """Material tables that produce NaN / inf radiance for some samples: the reference zeroes them
+    per pass with np.nan_to_num before accumulating (renderer.py:269-271); the fused finalize does it on the device."""
+    w, h = 32, 24
+    a = random_material_arrays(trial, w, h)
+    _fused_vs_oracle_renderer(E, a, seeds_for(w * h, seed=trial))
