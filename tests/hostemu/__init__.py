@@ -81,6 +81,13 @@ class HostEmu:
         self.lib.emu_traverse(C.c_uint32(n), _p(rays), accel, _p(tri), _p(t), _p(u), _p(v), C.c_int(mode))
         return tri, t, u, v
 
+    def traverse_counts(self, rays, accel):
+        """Node and triangle records each ray's ORDERED closest-hit search fetches (work model for tools/lane_model.py)."""
+        n = len(rays)
+        nodes, tris = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        self.lib.emu_traverse_counts(C.c_uint32(n), _p(rays), accel, _p(nodes), _p(tris))
+        return nodes, tris
+
     def visibility(self, a, b, accel, mode=MODE_ORDERED):
         out = np.empty(len(a), np.int32)
         self.lib.emu_visibility(C.c_uint32(len(a)), _p(a), _p(b), accel, _p(out), C.c_int(mode))

@@ -168,6 +168,20 @@ EXPORT void emu_traverse(uint32_t n, const Ray *rays, const EmuAccel *a, int32_t
     else traverse<TRAVERSE_ORDERED>(n, rays, a, tri, t, u, v);
 }
 
+/* per-ray work of the ORDERED closest-hit search: node records and triangle records fetched (tools/lane_model.py) */
+EXPORT void emu_traverse_counts(uint32_t n, const Ray *rays, const EmuAccel *a, uint32_t *nodes, uint32_t *tris) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t id = 0; id < (int64_t)n; id++) {
+        Cnt<true> cnt;
+        int best_i = -1;
+        float best_t = CLV_INF, u = 0.0f, v = 0.0f;
+        closest_hit<TRAVERSE_ORDERED, true>(a->view, xyz(rays[id].origin), xyz(rays[id].direction),
+                                            xyz(rays[id].inv_direction), best_i, best_t, u, v, cnt, -CLV_INF, -1);
+        nodes[id] = cnt.nf;
+        tris[id] = cnt.tf;
+    }
+}
+
 EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAccel *a, int32_t *visible, int mode) {
 #pragma omp parallel
     {

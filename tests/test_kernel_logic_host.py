@@ -523,3 +523,19 @@ def test_fused_pass_scrubs_nan_radiance_like_the_reference(E, trial):
     w, h = 32, 24
     a = random_material_arrays(trial, w, h)
     _fused_vs_oracle_renderer(E, a, seeds_for(w * h, seed=trial))
+
+
+def test_per_ray_work_counts(E):
+    """The per-ray node / triangle counts the lane model (tools/lane_model.py) is built on add up to the global counters."""
+    a = arrays("bench-spheres", 32, 24)
+    rays = random_rays(5000, [-9, -1.9, -9], [9, 9, 9], seed=4)
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        E.counters(reset=True)
+        E.traverse(rays, acc, MODE_ORDERED)
+        total = E.counters(reset=True)
+        nodes, tris = E.traverse_counts(rays, acc)
+    finally:
+        E.accel_destroy(acc)
+    assert nodes.sum() == total["node_fetches"] and tris.sum() == total["tri_fetches"]
+    assert nodes.max() > 4 * nodes.mean() or tris.max() > 3 * tris.mean()  # the heavy tail the model is about
