@@ -12,6 +12,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD_DIR = os.path.join(HERE, "_build")
+REF_DIR = os.path.join(HERE, "_ref")  # the reference's own trace.metal compiled as C++ (git-ignored build output)
+REFERENCE_TREE = os.environ.get("CLV_REFERENCE_TREE", "/root/reference")
 STAGES = ("make_light_rays", "make_camera_rays", "trace_light_rays", "trace_camera_rays", "join_paths",
           "finalize_samples", "gather_light_image", "process_images")
 
@@ -19,9 +21,31 @@ STAGES = ("make_light_rays", "make_camera_rays", "trace_light_rays", "trace_came
 def build(force=False):
     """Compile both oracle variants with oracle/Makefile (gcc -O3 -fopenmp -ffp-contract=off)."""
     libs = [os.path.join(BUILD_DIR, n) for n in ("libclive_oracle.so", "libclive_oracle_sm.so")]
-    if force or not all(os.path.exists(p) for p in libs):
+    srcs = [os.path.join(HERE, n) for n in ("trace_ref.c", "ref_glue.c", "ref_types.h", "Makefile")]
+    newest = max(os.path.getmtime(p) for p in srcs)
+    if force or not all(os.path.exists(p) and os.path.getmtime(p) >= newest for p in libs):
         subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True, capture_output=True)
     return libs
+
+
+def ref_libs():
+    return [os.path.join(REF_DIR, n) for n in ("libclive_ref.so", "libclive_ref_sm.so")]
+
+
+def build_ref(force=False):
+    """Compile the reference's src/trace.metal, unmodified and where it lies, as C++ (`make -C oracle ref`) into
+    oracle/_ref/.  Possible only where the reference tree exists (the build container); on the GPU box the prebuilt
+    files that travelled with the snapshot are used.  Returns the library paths, or [] when neither is available."""
+    libs = ref_libs()
+    have_tree = os.path.exists(os.path.join(REFERENCE_TREE, "src", "trace.metal"))
+    if have_tree and (force or not all(os.path.exists(p) for p in libs)):
+        subprocess.run(["make", "-C", HERE, "ref", f"REFERENCE={REFERENCE_TREE}"] + (["-B"] if force else []),
+                       check=True, capture_output=True)
+    return libs if all(os.path.exists(p) for p in libs) else []
+
+
+def have_ref():
+    return all(os.path.exists(p) for p in ref_libs())
 
 
 def _ptr(a):
@@ -32,11 +56,20 @@ def _ptr(a):
 
 
 class Oracle:
-    def __init__(self, shared_math=False):
-        build()
-        name = "libclive_oracle_sm.so" if shared_math else "libclive_oracle.so"
-        self.lib = C.CDLL(os.path.join(BUILD_DIR, name))
+    """One of four builds: the C restatement (oracle/trace_ref.c) or, with reference=True, the reference's own
+    trace.metal compiled as C++ (oracle/_ref); each with glibc libm or with the shared clv_math.h functions."""
+
+    def __init__(self, shared_math=False, reference=False):
+        if reference:
+            if not build_ref():
+                raise FileNotFoundError("oracle/_ref is not built (needs /root/reference: `make -C oracle ref`)")
+            name = os.path.join(REF_DIR, "libclive_ref_sm.so" if shared_math else "libclive_ref.so")
+        else:
+            build()
+            name = os.path.join(BUILD_DIR, "libclive_oracle_sm.so" if shared_math else "libclive_oracle.so")
+        self.lib = C.CDLL(name)
         self.shared_math = bool(shared_math)
+        self.reference = bool(reference)
         L = self.lib
         L.ref_renderer_create.restype = C.c_void_p
         L.ref_renderer_buffer.restype = C.c_void_p
@@ -135,10 +168,10 @@ class Oracle:
 class OracleRenderer:
     """renderer.py's per-pass dispatcher restated in C (ref_renderer_*): same buffers, same stage order."""
 
-    def __init__(self, arrays, seeds, shared_math=False, oracle=None):
+    def __init__(self, arrays, seeds, shared_math=False, oracle=None, reference=False):
         from clive2_b200 import struct_types as T
         self.T = T
-        self.oracle = oracle or Oracle(shared_math)
+        self.oracle = oracle or Oracle(shared_math, reference=reference)
         self.arrays = arrays  # keeps the borrowed numpy arrays alive
         self.width, self.height = arrays.pixel_width, arrays.pixel_height
         self.batch = self.width * self.height
