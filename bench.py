@@ -1,19 +1,29 @@
 #!/usr/bin/env python
-"""Benchmark of the BDPT hot path (one "step" = one sample pass = Renderer.run_sample over a full frame).
+"""Benchmark of the BDPT hot path.  One "step" = one sample pass (Renderer.run_sample) over the FULL frame of the
+configuration; `value` = samples of all steps / device time, whole job.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4] [--impl ours|reference]
 
-Prints ONE JSON line (rank 0).  `value` is whole-job Msamples/s with everything resident in HBM (CUDA events on the
-launch stream, max over ranks); `e2e` is the same metric through `Renderer.run_sample_preview` with pinned HOST buffers
-(fresh seeds up, one pass, device tone map, uint8 preview image down, all inside the timed region; `e2e_accumulators`
-downloads the raw float accumulators instead); `roofline` is for the dominant kernel of the pass;
-`cpu_baseline` is the CPU transcription of the reference (oracle/, glibc build) timed on this box's host cores.
-`--impl reference` times that CPU transcription as the reference arm (the reference's Metal kernels cannot run on
-Linux and its Python needs `metalcompute`).
+Default configuration: **c4** — BASELINE.json's north-star workload (1920x1080, ~10 M-triangle PLY mesh), the largest
+configuration that fits one GPU.  c1-c3 are the other BASELINE configs (parity-test cases; selectable for profiling).
 
-Multi-GPU (torchrun, one rank per GPU): every rank renders full-frame passes with its own RNG streams (the work
-shards by sample pass, no data-path collective), and ONE NCCL reduce of the packed float accumulators closes the timed
-region.  Per-GPU work is fixed => "scaling": "weak".
+Prints ONE JSON line (rank 0):
+  value            Msamples/s, scene + accumulators resident in HBM, CUDA events on the launch stream, max over ranks
+  e2e              the same through the public call with pinned HOST buffers every step (seeds up, preview image down)
+  roofline         dominant kernel of the pass: algorithmic bytes (device counters of an instrumented run of the same
+                   passes) / its CUDA-event time, against the HBM peak of MEASURED_PEAKS.json when the traversal
+                   records exceed the L2, against the L2 read peak measured in this run when they are L2 resident;
+                   `traffic` = DRAM bytes of that kernel from ncu (profiles/dram_traffic.json, regenerated per round)
+  rel_rmse         relative RMSE of the GPU image against the CPU reference (glibc build) at equal spp and against a
+                   high-spp CPU image, on a reduced frame of the same scene (stated)
+  cpu_baseline     the CPU reference on this box's host cores: oracle/_ref (the reference's own trace.metal compiled as
+                   C++, kind "reference") when it was built, else oracle/trace_ref.c (kind "port")
+`--impl reference` times that CPU code as the reference arm (same config / metric / unit).
+
+N > 1 (torchrun, one rank per GPU): STRONG scaling of one frame.  The K passes of the frame are split over the GPUs by
+sample pass and by image tile (clive2_b200.sharding.shard_plan: pass groups = largest divisor of N that divides K, the
+rest by 16x16 tiles), replicated scene, and ONE NCCL reduce of the packed float accumulators closes the timed region.
+Extra keys carry the pure tile-sharded and the weak pass-sharded figures measured in the same run.
 """
 import argparse
 import json
@@ -29,21 +39,23 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+L2_BYTES = 126 << 20
 CONFIGS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable case
-    "c1": dict(preset="empty", width=256, height=256,
+    "c1": dict(preset="empty", width=256, height=256, mesh=None,
                workload="C1: Cornell box (preset 'empty', 16 triangles), 256x256, diffuse, max path length 6+6"),
-    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
-    "c2": dict(preset="bench-spheres", width=512, height=512,
+    "c2": dict(preset="bench-spheres", width=512, height=512, mesh=None,
                workload="C2: Cornell box + two icospheres (2 x 20480 triangles), rough-dielectric (GGX transmission) "
                         "and coated-diffuse (GGX specular) materials, 512x512"),
-    # BASELINE.json configs[2]
-    "c3": dict(preset="bench-terrain-1m", width=1024, height=1024,
-               workload="C3: Cornell enclosure + procedural terrain mesh (1 002 528 triangles), 1024x1024"),
+    "c3": dict(preset="bench-terrain-1m", width=1024, height=1024, mesh=("obj", 708),
+               workload="C3: Cornell enclosure + procedural terrain mesh (1 002 528 triangles, OBJ), 1024x1024"),
+    # BASELINE.json configs[3]: the north-star configuration, quoted at N = 1, 2, 4, 8
+    "c4": dict(preset="bench-terrain-10m", width=1920, height=1080, mesh=("ply", 2236),
+               workload="C4: Cornell enclosure + procedural terrain mesh (9 999 392 triangles, PLY), 1920x1080"),
 }
-CONFIGS["c4"] = dict(preset="bench-terrain-10m", width=1920, height=1080,
-                     workload="C4: Cornell enclosure + procedural terrain mesh (9 999 392 triangles), 1920x1080")
 SEED = 20240928
+RMSE_FRAME = {"c1": (128, 128), "c2": (128, 128), "c3": (128, 128), "c4": (160, 90)}  # reduced frames of rel_rmse
+RMSE_SPP, RMSE_HI_SPP = 16, 128
 
 
 def env_int(name, default):
@@ -110,85 +122,196 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+            # median over the samples taken under load (the sampler also sees the idle gaps between timed regions)
+            busy = [x for x in sm if x >= 0.6 * max(sm)]
+            out.update(sm_mhz=statistics.median(busy or sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
-def build_arrays(cfg, width=None, height=None):
-    from clive2_b200 import scene
-    return scene.preset_arrays(cfg["preset"], width or cfg["width"], height or cfg["height"])
+# ---------------------------------------------------------------------------------------------------------------------
+# scenes
+# ---------------------------------------------------------------------------------------------------------------------
+def build_arrays(cfg, width=None, height=None, via_file=True, bvh_builder="auto"):
+    """Scene arrays of a configuration.  C3 / C4 go through the file path BASELINE names (load.py:76-95 of the reference):
+    the procedural mesh is written as OBJ / PLY and read back by the package's own readers (`via_file=False`: the
+    in-memory mesh of the scene preset)."""
+    from clive2_b200 import load, meshgen, scene
+    w, h = width or cfg["width"], height or cfg["height"]
+    if not (via_file and cfg.get("mesh")):
+        return scene.preset_arrays(cfg["preset"], w, h, bvh_builder=bvh_builder)
+    kind, quads = cfg["mesh"]
+    p = scene.scene_presets[cfg["preset"]]
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(tmp, f"clv_bench_terrain_{quads}_{os.getuid()}.{kind}")
+    if not os.path.exists(path):
+        v, f = meshgen.terrain(quads, quads)
+        part = path + f".{os.getpid()}.tmp." + kind
+        (load.write_ply if kind == "ply" else load.write_obj)(part, v, f)
+        os.replace(part, path)
+    return scene.build_scene_arrays(w, h, p["cam_center"], p["cam_direction"],
+                                    [{"file_path": path, "material": p["file_specs"][0]["material"]}], None, bvh_builder)
 
 
-def seeds_for(batch, rank):
-    s = np.random.RandomState(SEED + 7919 * rank).randint(0, 2 ** 32, size=(batch, 2), dtype=np.uint32)
+ARRAY_FIELDS = ("camera", "boxes", "triangles", "materials", "light_triangles", "light_counts", "light_surface_areas",
+                "light_triangle_indices", "camera_triangle_indices")
+
+
+def shared_arrays(cfg, rank, world, via_file):
+    """Rank 0 builds the scene (mesh, normals, BVH: ~40 s at C4) and hands the arrays to the other ranks through
+    /dev/shm instead of eight ranks building the same 10 M-triangle BVH on the same host cores."""
+    if world == 1:
+        return build_arrays(cfg, via_file=via_file)
+    import torch.distributed as dist
+    from clive2_b200.scene import SceneArrays
+    base = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                        f"clv_bench_scene_{os.environ.get('MASTER_PORT', '0')}_")
+    if rank == 0:
+        a = build_arrays(cfg, via_file=via_file)
+        for f in ARRAY_FIELDS:
+            np.save(base + f + ".npy", getattr(a, f))
+    dist.barrier()
+    if rank != 0:
+        a = SceneArrays(pixel_width=cfg["width"], pixel_height=cfg["height"],
+                        **{f: np.load(base + f + ".npy", mmap_mode="r" if f in ("boxes", "triangles") else None)
+                           for f in ARRAY_FIELDS})
+        a.boxes, a.triangles = np.ascontiguousarray(a.boxes), np.ascontiguousarray(a.triangles)
+    dist.barrier()
+    if rank == 0:
+        for f in ARRAY_FIELDS:
+            try:
+                os.unlink(base + f + ".npy")
+            except OSError:
+                pass
+    return a
+
+
+def seeds_for(batch, stream):
+    s = np.random.RandomState(SEED + 7919 * stream).randint(0, 2 ** 32, size=(batch, 2), dtype=np.uint32)
     s[s == 0] = 1
     return s
 
 
+def config_dict(cfg, arrays_or_none, world, plan):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    tile_groups, pass_groups = plan
+    if world == 1:
+        par = "single GPU"
+    else:
+        par = (f"one frame on {world} GPUs: {pass_groups} pass group(s) x {tile_groups} tile group(s) (16x16 tiles, rows "
+               f"rotated), replicated scene, one NCCL reduce of the float accumulators")
+    batch = cfg["width"] * cfg["height"]
+    work = (768 + 200 + 128) * batch
+    return {"workload": cfg["workload"], "width": cfg["width"], "height": cfg["height"], "samples_per_step": batch,
+            "parallelism": par,
+            "l2": (f"per-pass working set {work / 1e6:.0f} MB (path vertex records, connection scratch, aggregators, "
+                   f"accumulators) is rewritten every step and exceeds the 126 MB L2; no explicit flush" if work > 126e6 else
+                   "per-pass working set below the 126 MB L2; steps run back to back without flush")}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU transcription (oracle) legs
+# CPU reference legs
 # ---------------------------------------------------------------------------------------------------------------------
-def oracle_passes(arrays, seeds, n_passes):
-    """Seconds per pass of the C transcription (glibc build, all host threads) over `n_passes` passes."""
+def cpu_kind():
+    from oracle import oracle as oracle_mod
+    return ("reference", True) if oracle_mod.have_ref() else ("port", False)
+
+
+def cpu_renderer(arrays, seeds):
+    """The CPU reference, glibc build, all host threads: oracle/_ref (trace.metal compiled as C++) when built."""
     from oracle.oracle import OracleRenderer
-    r = OracleRenderer(arrays, seeds, shared_math=False)
-    r.oracle.use_all_cores()
+    kind, use_ref = cpu_kind()
+    r = OracleRenderer(arrays, seeds, shared_math=False, reference=use_ref)
+    threads = r.oracle.use_all_cores()
+    return r, threads, kind
+
+
+CPU_WHAT = {"reference": "oracle/_ref: the reference's src/trace.metal compiled unmodified as C++ (g++ -O3 -fopenmp, glibc "
+                         "libm) under the restated per-pass dispatcher of renderer.py (oracle/ref_glue.c)",
+            "port": "oracle/trace_ref.c: C restatement of trace.metal + renderer.py's dispatcher (gcc -O3 -fopenmp, glibc libm)"}
+
+
+def cpu_passes(arrays, n_passes, seed_stream=0):
+    r, threads, kind = cpu_renderer(arrays, seeds_for(arrays.pixel_width * arrays.pixel_height, seed_stream))
     times = []
     for _ in range(n_passes):
         t0 = time.perf_counter()
         r.run_sample()
         times.append(time.perf_counter() - t0)
-    threads = r.oracle.num_threads
+    est = np.nan_to_num(r.summed_image / r.summed_sample_weights)
     r.close()
-    return times, threads
+    return times, threads, kind, est
 
 
-def cpu_baseline(cfg, budget_s=20.0):
-    arrays = build_arrays(cfg)
-    batch = cfg["width"] * cfg["height"]
-    seeds = seeds_for(batch, 0)
-    t1, threads = oracle_passes(arrays, seeds, 1)
-    n_more = int(max(1, min(6, (budget_s - t1[0]) // max(t1[0], 1e-3))))
-    tn, _ = oracle_passes(arrays, seeds, n_more)
-    per_pass = min(statistics.median(tn), t1[0])
-    return {"value": batch / per_pass / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
-            "sample": f"{n_more} full passes of the same workload ({batch} samples each) after 1 warm-up pass; "
-                      f"oracle/trace_ref.c (gcc -O3 -fopenmp, glibc libm), {per_pass:.3f} s/pass"}
+def bounded_cpu_frame(cfg, arrays_full, budget_s, n_steps):
+    """(arrays, width, height, note): the full frame when `n_steps` passes of it fit the budget, else the same scene at a
+    frame reduced by a power of two per axis (per-sample cost does not depend on the frame size)."""
+    width, height = cfg["width"], cfg["height"]
+    probe_w, probe_h = (width // 8, height // 8) if width % 8 == 0 and height % 8 == 0 else (width, height)
+    probe = build_arrays_like(arrays_full, cfg, probe_w, probe_h)
+    t, _, _, _ = cpu_passes(probe, 2)
+    per_sample = min(t) / (probe_w * probe_h)
+    shrink = 1
+    while (per_sample * (width // shrink) * (height // shrink) * n_steps > budget_s and min(width, height) // (2 * shrink) >= 32
+           and width % (2 * shrink) == 0 and height % (2 * shrink) == 0):
+        shrink *= 2
+    if shrink == 1:
+        return arrays_full, width, height, ""
+    w, h = width // shrink, height // shrink
+    return (build_arrays_like(arrays_full, cfg, w, h), w, h,
+            f"frame reduced {shrink}x per axis from {width}x{height} to {w}x{h} to bound the run (same scene and BVH)")
 
 
-def run_reference(args, cfg, rank):
+def build_arrays_like(arrays_full, cfg, width, height):
+    """The same scene at another frame size WITHOUT rebuilding mesh and BVH: only the camera record depends on the
+    resolution... except that the two sensor triangles are part of the BVH and scale with the aspect ratio, so the
+    aspect ratio is kept (all reduced frames are the full frame divided by an integer)."""
+    import copy
+    from clive2_b200.camera import Camera
+    from clive2_b200 import scene
+    p = scene.scene_presets[cfg["preset"]]
+    assert abs(width / height - cfg["width"] / cfg["height"]) < 1e-9, "reduced frames keep the aspect ratio"
+    cam = Camera(center=p["cam_center"], direction=p["cam_direction"], pixel_width=width, pixel_height=height,
+                 phys_width=width / height, phys_height=1)
+    a = copy.copy(arrays_full)
+    a.pixel_width, a.pixel_height = width, height
+    a.camera = np.array([cam.to_struct()]).reshape(1)
+    return a
+
+
+def cpu_baseline(cfg, arrays_full, budget_s=20.0):
+    arrays, w, h, note = bounded_cpu_frame(cfg, arrays_full, budget_s, 3)
+    t, threads, kind, _ = cpu_passes(arrays, 3)
+    per_pass = min(t[1:])
+    batch = w * h
+    return {"value": batch / per_pass / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+            "sample": f"2 timed passes of {batch} samples each after 1 warm-up pass ({per_pass:.3f} s/pass)"
+                      + (f"; {note}" if note else "; the full frame of the workload") + f"; {CPU_WHAT[kind]}"}
+
+
+def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    width, height = cfg["width"], cfg["height"]
-    arrays = build_arrays(cfg)
-    probe, threads = oracle_passes(arrays, seeds_for(width * height, 0), 1)
-    shrink = 1
-    while probe[0] / (shrink * shrink) * (args.steps + args.warmup) > 240.0 and min(width, height) // (2 * shrink) >= 64:
-        shrink *= 2
-    if shrink > 1:
-        width, height = width // shrink, height // shrink
-        arrays = build_arrays(cfg, width, height)
+    full = build_arrays(cfg, via_file=not args.mesh_in_memory)
+    arrays, width, height, note = bounded_cpu_frame(cfg, full, 150.0, args.steps + args.warmup)
     batch = width * height
-    from oracle.oracle import OracleRenderer
-    r = OracleRenderer(arrays, seeds_for(batch, 0), shared_math=False)
-    threads = r.oracle.use_all_cores()
+    r, threads, kind = cpu_renderer(arrays, seeds_for(batch, 0))
     for _ in range(args.warmup):
         r.run_sample()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r.run_sample()
     dt = time.perf_counter() - t0
+    r.close()
     value = batch * args.steps / dt / 1e6
-    sample = (f"each step = one full pass of the {width}x{height} frame ({batch} samples)"
-              + (f", frame reduced {shrink}x per axis from {cfg['width']}x{cfg['height']} to bound the run" if shrink > 1 else ""))
+    sample = (f"each step = one pass of {batch} samples" + (f"; {note}" if note else " = the full frame of the workload")
+              + f"; {CPU_WHAT[kind]}")
+    from clive2_b200 import sharding
     line = {
         "impl": "reference", "metric": "bdpt_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "width": width, "height": height, "samples_per_step": batch,
-                   "what": "CPU transcription of the reference's trace.metal + renderer.py pass (oracle/trace_ref.c, "
-                           "glibc build, OpenMP over all host threads); the reference's Metal kernels cannot run on Linux"},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(cfg, full, world, sharding.shard_plan(world, args.steps)),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,113 +325,164 @@ def run_ours(args, cfg, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from clive2_b200 import runtime, scene
+    from clive2_b200 import runtime, scene, sharding
     from clive2_b200.renderer import Renderer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; clive2_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    tdev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=tdev)
 
     width, height = cfg["width"], cfg["height"]
     batch = width * height
+    K, W = args.steps, args.warmup
     t_scene = time.perf_counter()
-    arrays = build_arrays(cfg)
+    arrays = shared_arrays(cfg, rank, world, via_file=not args.mesh_in_memory)
     t_scene = time.perf_counter() - t_scene
     dev = runtime.Device(local_rank)
     t_up = time.perf_counter()
     sc = scene.scene_from_arrays(arrays, dev)
-    tile_sharded = args.shard == "tile" and world > 1
-    seeds = seeds_for(batch, 0 if tile_sharded else rank)
-    ids = None
-    if tile_sharded:
-        # strong scaling of ONE frame: this rank traces its 16x16 tiles with the global RNG rows (same streams as 1 GPU)
-        from clive2_b200 import sharding
-        ids = sharding.tile_ids(width, height, rank, world, 16)
-    elif args.tile:
-        from clive2_b200 import sharding
-        tw, th = (int(x) for x in args.tile.lower().split("x"))
-        ids = sharding.tiled_order(width, height, tw, th)
+
+    # ---- how this rank takes part in the frame ----------------------------------------------------------------------
+    if world == 1:
+        ids, seed_stream, my_passes, plan = None, 0, K, (1, 1)
+        if args.tile:
+            tw, th = (int(x) for x in args.tile.lower().split("x"))
+            ids = sharding.tiled_order(width, height, tw, th)
+    elif args.shard == "tile":
+        ids, seed_stream, my_passes, plan = sharding.tile_ids(width, height, rank, world, 16), 0, K, (world, 1)
+    elif args.shard == "pass":
+        if K % world:
+            raise SystemExit(f"--shard pass needs --steps divisible by the number of GPUs ({K} % {world})")
+        ids, seed_stream, my_passes, plan = None, rank, K // world, (1, world)
+    else:
+        ids, seed_stream, my_passes, tg, pg = sharding.hybrid_shard(width, height, rank, world, K, 16)
+        plan = (tg, pg)
+    seeds = seeds_for(batch, seed_stream)
     r = Renderer(sc, seeds=seeds, sample_ids=ids)
     dev.synchronize()
     t_up = time.perf_counter() - t_up
-    accel_stats = dev.accel(sc.boxes, sc.triangles).stats()
-    l2_read_gbs = dev.read_bandwidth(32 << 20, 5) if rank == 0 else None     # 32 MB: L2 resident
-    hbm_read_gbs = dev.read_bandwidth(2 << 30, 5) if rank == 0 else None      # 2 GB: streams from HBM
-    K, W = args.steps, args.warmup
+    accel = dev.accel(sc.boxes, sc.triangles)
+    accel_stats = accel.stats()
+    n_local = batch if ids is None else len(ids)
+    extras_err = {}
+    l2_read_gbs = hbm_read_gbs = None
+    if rank == 0:
+        try:
+            l2_read_gbs = dev.read_bandwidth(32 << 20, 5)   # 32 MB: L2 resident
+            hbm_read_gbs = dev.read_bandwidth(2 << 30, 5)   # 2 GB: streams from HBM
+        except Exception as e:  # noqa: BLE001
+            extras_err["read_bandwidth"] = repr(e)
 
     # ---- 1. instrumented run: work counters of exactly the passes that will be timed (same seeds => same work) ----
     dev.counters_enable(True)
     for _ in range(W):
         r.run_sample()
     dev.counters(reset=True)
-    for _ in range(K):
+    for _ in range(my_passes):
         r.run_sample()
     counters = dev.counters(reset=True, per_class=True)
     dev.counters_enable(False)
     r._fr.reset(seeds)
 
-    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(dev.stream, device=tdev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
 
-    # ---- 2. device-resident timed run -------------------------------------------------------------------------------
-    for _ in range(W):
-        r.run_sample()
-    dev.synchronize()
-    if world > 1:
-        # warm-up of the collective too: the first reduce on a communicator sets up its channels (the timed region's
-        # reduce is then the steady-state one); a scratch tensor of the accumulators' size, not the accumulators
-        with torch.cuda.stream(stream):
-            warm = torch.zeros(height * width * 8, dtype=torch.float32, device=torch.device("cuda", local_rank))
-            dist.reduce(warm, dst=0)
+    def timed_passes(rend, n_passes, with_reduce):
+        """(ms of this rank's passes, ms of the reduce, launches): `n_passes` passes + one reduce between CUDA events on the
+        launch stream after W warm-up passes."""
+        for _ in range(W):
+            rend.run_sample()
+        dev.synchronize()
+        if world > 1 and with_reduce:
+            with torch.cuda.stream(stream):  # the first reduce on a communicator sets up its channels: not timed
+                warm = torch.zeros(height * width * 8, dtype=torch.float32, device=tdev)
+                dist.reduce(warm, dst=0)
+            torch.cuda.synchronize()
+            del warm
         torch.cuda.synchronize()
-        del warm
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = dev.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        r.run_sample()
-    if world > 1:
-        # the reduce is issued with the renderer's stream as torch's current stream: NCCL's stream waits for the passes
-        # and the renderer's stream for the reduce, all on the device (no host synchronisation inside the timed region)
-        with torch.cuda.stream(stream):
-            acc = torch.as_tensor(r.accumulator_buffer(), device=torch.device("cuda", local_rank))
-            dist.reduce(acc, dst=0)
-    e1.record(stream)
-    dev.synchronize()
-    torch.cuda.synchronize()
-    launches = dev.launch_count - launches0
-    elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        dist.barrier()
-    # per-kernel durations for the roofline: K more passes of the same work with CUDA events between the kernels on the
+        if world > 1:
+            dist.barrier()
+        n0 = dev.launch_count
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        for _ in range(n_passes):
+            rend.run_sample()
+        e1.record(stream)
+        if world > 1 and with_reduce:
+            # issued with the renderer's stream as torch's current stream: NCCL's stream waits for the passes and the
+            # renderer's stream for the reduce, all on the device (no host synchronisation inside the timed region)
+            with torch.cuda.stream(stream):
+                acc = torch.as_tensor(rend.accumulator_buffer(), device=tdev)
+                dist.reduce(acc, dst=0)
+        e2.record(stream)
+        dev.synchronize()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), dev.launch_count - n0
+
+    def over_ranks(x):
+        """(max, mean) of a per-rank number."""
+        if world == 1:
+            return float(x), float(x)
+        t = torch.tensor([float(x)], device=tdev, dtype=torch.float64)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        v = [float(q.item()) for q in g]
+        return max(v), sum(v) / len(v)
+
+    # ---- 2. device-resident timed run -------------------------------------------------------------------------------
+    pass_ms, reduce_ms, launches = timed_passes(r, my_passes, True)
+    elapsed_ms, _ = over_ranks(pass_ms + reduce_ms)
+    pass_ms_max, pass_ms_mean = over_ranks(pass_ms)
+    reduce_ms_max, _ = over_ranks(reduce_ms)
+
+    # per-kernel durations for the roofline: more passes of the same work with CUDA events between the kernels on the
     # launch stream.  With events requested the pass runs as ONE slice on ONE stream (in the timed region above the
     # slices of a pass overlap on several streams, where "the duration of a kernel" is not defined).
     r._fr.kernel_timing(True)
-    for _ in range(K):
+    for _ in range(my_passes):
         r.run_sample()
-    kernel_ms, timed_passes = r._fr.kernel_times(reset=True)
+    kernel_ms, timed = r._fr.kernel_times(reset=True)
     r._fr.kernel_timing(False)
+
+    # ---- 2b. N > 1: the two pure shardings, for the record ----------------------------------------------------------------
+    alt = {}
+    if world > 1 and args.shard == "auto" and not args.no_alternatives:
+        try:
+            if plan != (world, 1):
+                rt = Renderer(sc, seeds=seeds_for(batch, 0), sample_ids=sharding.tile_ids(width, height, rank, world, 16))
+                p_ms, r_ms, _ = timed_passes(rt, K, True)
+                t_max, _ = over_ranks(p_ms + r_ms)
+                pm, pa = over_ranks(p_ms)
+                alt["tile_sharded"] = {"value": batch * K / (t_max * 1e-3) / 1e6, "unit": "Msamples/s", "scaling": "strong",
+                                       "ms_per_step": t_max / K, "rank_pass_ms_max_over_mean": pm / pa,
+                                       "what": f"every pass of the frame split over {world} GPUs by 16x16 tile "
+                                               f"({batch // world} samples per GPU and pass), same RNG streams as 1 GPU"}
+                rt.release()
+            rp = Renderer(sc, seeds=seeds_for(batch, 100 + rank))
+            p_ms, r_ms, _ = timed_passes(rp, K, True)
+            t_max, _ = over_ranks(p_ms + r_ms)
+            alt["pass_sharded_weak"] = {"value": batch * K * world / (t_max * 1e-3) / 1e6, "unit": "Msamples/s",
+                                        "scaling": "weak", "ms_per_step": t_max / K,
+                                        "what": f"every GPU renders {K} full-frame passes from its own RNG streams "
+                                                f"({world}x the samples of the headline run), one reduce"}
+            rp.release()
+        except Exception as e:  # noqa: BLE001
+            extras_err["alternative_shardings"] = repr(e)
 
     # ---- 3. end-to-end timed runs through the public API, HOST buffers in and out every step ---------------------------
     # (a) Renderer.run_sample_preview: seeds in, tone-mapped uint8 preview out = the loop body of the reference's
     #     render.py:31-37 (pass + `renderer.image`); (b) Renderer.run_sample_e2e: seeds in, raw float accumulators out.
-    h_seeds = runtime.PinnedArray((batch, 2), np.uint32)
     h_accum = runtime.PinnedArray((height, width, 8), np.float32)
     h_image = runtime.PinnedArray((height, width, 3), np.uint8)
-
+    h_seeds = runtime.PinnedArray((batch, 2), np.uint32)
     h_seeds_b = runtime.PinnedArray((batch, 2), np.uint32)
     h_seeds.array[:] = seeds
-    h_seeds_b.array[:] = seeds_for(batch, rank + 1000)
+    h_seeds_b.array[:] = seeds_for(batch, seed_stream + 1000)
     host_seed_buffers = (h_seeds, h_seeds_b)  # fresh host-side RNG state every step, no host arithmetic in the loop
 
     def timed_e2e(step):
@@ -319,31 +493,34 @@ def run_ours(args, cfg, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for k in range(K):
+        for k in range(my_passes):
             step(host_seed_buffers[k & 1])
         dev.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+        return over_ranks(time.perf_counter() - t0)[0]
 
     e2e_s = timed_e2e(lambda hs: r.run_sample_preview(hs, h_image))
     checksum = int(h_image.array.astype(np.int64).sum())
     e2e_acc_s = timed_e2e(lambda hs: r.run_sample_e2e(hs, h_accum))
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- 4. image error against the CPU reference (N = 1) -----------------------------------------------------------------
+    rel_rmse = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rel_rmse = image_error(args, cfg, arrays, dev)
+        except Exception as e:  # noqa: BLE001
+            extras_err["rel_rmse"] = repr(e)
+
     if rank == 0:
-        samples = batch * K * (1 if tile_sharded else world)
+        samples = batch * K
         value = samples / (elapsed_ms * 1e-3) / 1e6
         e2e_value = samples / e2e_s / 1e6
         tot = {k: counters["walk"][k] + counters["connect"][k] for k in counters["walk"]}
-        rays_ref_per_pass = tot["rays_ref"] / K
-        peak, peak_src = measured_peaks()
+        peak_hbm, peak_src = measured_peaks()
+        np_ = max(timed, 1)
         # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
-        cw, cc = ({k: v / K for k, v in counters[x].items()} for x in ("walk", "connect"))
+        cw, cc = ({k: v / max(my_passes, 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
         VB = 64  # bytes of one stored path vertex in the renderer's SoA records (four 16-byte parts)
@@ -351,81 +528,100 @@ def run_ours(args, cfg, rank, local_rank, world):
             # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record
             # (80 B of the reference Triangle) + path vertices written (64 B) + seeds RMW (16 B) + accumulator RMW (64 B)
             "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * VB
-                             + batch * (16 + 64),
+                             + n_local * (16 + 64),
             # node + triangle records fetched + per task: 4 B task word, origin + triangle parts of two vertices (4 x 16 B)
             "k_connect_rays": cc["node_fetches"] * NBR + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 64),
             # path vertices staged (64 B each), visibility bits + projection record (8 + 48 B), aggregator written (80 B)
-            "k_connect_finish": cc["vertices"] * VB + batch * (8 + 48 + 80),
+            "k_connect_finish": cc["vertices"] * VB + n_local * (8 + 48 + 80),
             # origin / normal / material parts of every vertex (48 B), task words + projection record written
-            "k_connect_enumerate": cc["vertices"] * 48 + cc["rays_ref"] * 4 + batch * (48 + 8),
+            "k_connect_enumerate": cc["vertices"] * 48 + cc["rays_ref"] * 4 + n_local * (48 + 8),
             # 9 aggregators read (80 B), light image RMW (32 B), accumulator RMW (64 B) per pixel
             "k_fused_finalize": batch * (9 * 80 + 32 + 64),
         }
-        alg_bytes = alg[dom]
-        dom_ms = kernel_ms[dom] / max(timed_passes, 1)
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom,
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": dom_ms,
+        for k in list(kernel_ms):
+            alg.setdefault(k, 0.0)
+        accel_bytes = accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"]
+        resident = accel_bytes < L2_BYTES * 0.8
+        dom_ms = kernel_ms[dom] / np_
+        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+        if resident and l2_read_gbs:
+            bound, peak, src = "l2", l2_read_gbs, ("L2 read peak measured in this run (clv_measure_read_bandwidth, 32 MB "
+                                                   "resident buffer); MEASURED_PEAKS.json has no L2 figure")
+        else:
+            bound, peak, src = "hbm", peak_hbm, peak_src
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
+            traffic = tj.get(args.config, {}).get(dom)
+            traffic_note = tj.get("_note")
+        except Exception:
+            pass
+        roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": dom_ms,
+                    "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak_hbm) if traffic else None,
+                    "traffic_source": traffic_note,
+                    "traversal_records_bytes": accel_bytes, "traversal_records_l2_resident": bool(resident),
                     "l2_read_peak_gbs_measured_here": l2_read_gbs, "hbm_read_peak_gbs_measured_here": hbm_read_gbs,
-                    "frac_of_l2_read_peak": achieved / l2_read_gbs if l2_read_gbs else None,
-                    "kernel_ms_per_pass": {k: v / max(timed_passes, 1) for k, v in kernel_ms.items()},
-                    "algorithmic_gbs_per_kernel": {k: alg[k] / (kernel_ms[k] / max(timed_passes, 1) * 1e-3) / 1e9
-                                                   for k in kernel_ms if kernel_ms[k] > 0},
-                    "note": "algorithmic bytes = node (64 B) and triangle (48 B) records the kernel fetches (device "
-                            "counters of an instrumented run of the same passes) + the per-sample / per-ray records it "
-                            "reads and writes (DESIGN.md §7); BVH records of this configuration are cache resident, so "
-                            "DRAM traffic (`traffic`, from ncu) is far below the algorithmic figure"}
-        traffic_file = os.path.join(REPO, "profiles", "dram_traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(roofline["kernel"])
-            except Exception:
-                pass
+                    "kernel_ms_per_pass": {k: v / np_ for k, v in kernel_ms.items()},
+                    "algorithmic_gbs_per_kernel": {k: alg[k] / (kernel_ms[k] / np_ * 1e-3) / 1e9
+                                                   for k in kernel_ms if kernel_ms[k] > 0 and alg.get(k)},
+                    "per_ray": {"node_records_walk": cw["node_fetches"] / max(cw["rays_traced"], 1),
+                                "triangle_records_walk": cw["tri_fetches"] / max(cw["rays_traced"], 1),
+                                "node_records_connect": cc["node_fetches"] / max(cc["rays_traced"], 1),
+                                "triangle_records_connect": cc["tri_fetches"] / max(cc["rays_traced"], 1)},
+                    "note": "achieved = algorithmic bytes / CUDA-event time of the kernel; algorithmic bytes = node (64 B; "
+                            "128 B 4-wide) and triangle (48 B) records the kernel fetches (device counters of an "
+                            "instrumented run of the same passes) + the per-sample / per-ray records it reads and writes "
+                            "(DESIGN.md §7).  dram_frac = ncu DRAM bytes of the kernel / its time / HBM peak: part of "
+                            "the algorithmic bytes is served by L1/L2"}
         line = {
             "metric": "bdpt_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong" if tile_sharded else "weak",
-            "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "width": width, "height": height, "samples_per_step_per_gpu": batch,
-                       "triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)),
-                       "parallelism": (f"tile-sharded x{world} (16x16 tiles round-robin, one NCCL reduce)" if tile_sharded else
-                                       f"pass-sharded x{world} (one NCCL reduce)") if world > 1 else "single GPU",
-                       "l2": f"per-pass working set {(768 + 200 + 128) * batch / 1e6:.0f} MB (path vertex records, connection "
-                             f"scratch, aggregators + accumulators) is rewritten every step (> 126 MB L2); no explicit flush"
-                             if (768 + 200 + 128) * batch > 126e6
-                             else "per-pass working set below the 126 MB L2; steps run back to back without flush",
-                       "accel_bytes": accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"],
-                       "launches_per_step": launches // K,
-                       "kernel_flavour": ("high-occupancy (walks 32 / rays 48 registers; traversal records exceed the caches)"
-                                          if accel_stats["large_scene_tuning"] else
-                                          "cache-resident (walks 64 / rays 63 registers)"),
-                       "scene_build_s": t_scene, "scene_upload_s": t_up},
-            "mrays_per_s": rays_ref_per_pass * K * world / (elapsed_ms * 1e-3) / 1e6,
-            "mrays_traced_per_s": tot["rays_traced"] * world / (elapsed_ms * 1e-3) / 1e6,
-            "rays_per_sample": rays_ref_per_pass / (len(ids) if ids is not None else batch),
-            "rays_definition": "mrays_per_s counts traverse_bvh invocations the reference makes for the same paths "
-                               "(SURVEY.md 8d); mrays_traced_per_s counts traversals this implementation starts "
-                               "(connection rays whose target test fails first are skipped)",
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(cfg, arrays, world, plan),
+            "run": {"triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)), "accel_bytes": accel_bytes,
+                    "samples_per_pass_per_gpu": n_local, "passes_per_gpu": my_passes,
+                    "launches_per_pass": launches // max(my_passes, 1),
+                    "kernel_flavour": ("high-occupancy (traversal records exceed the caches)"
+                                       if accel_stats["large_scene_tuning"] else "cache-resident"),
+                    "mesh_source": "in-memory" if (args.mesh_in_memory or not cfg.get("mesh")) else
+                                   f"{cfg['mesh'][0].upper()} file written and read back (load.write_{cfg['mesh'][0]} / read_{cfg['mesh'][0]})",
+                    "scene_build_s": t_scene, "scene_upload_s": t_up, "excluded_from_timed_region": "scene build + upload",
+                    "rank_pass_ms_max": pass_ms_max, "rank_pass_ms_mean": pass_ms_mean,
+                    "rank_pass_ms_max_over_mean": pass_ms_max / max(pass_ms_mean, 1e-9),
+                    "reduce_ms": reduce_ms_max, "reduce_bytes": batch * 32 if world > 1 else 0},
+            "mrays_per_s": value * tot["rays_ref"] / max(my_passes, 1) / n_local,
+            "rays_per_sample": tot["rays_ref"] / max(my_passes, 1) / n_local,
+            "rays_definition": "a ray = one traverse_bvh invocation the reference makes for the same paths (SURVEY.md 8d: "
+                               "closest hits of the walks, shadow rays, projections), counted by device counters of an "
+                               "instrumented run of the same passes (rank 0's share at N > 1); mrays_per_s = value x "
+                               "rays_per_sample",
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": batch * 8,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": n_local * 8,
                     "d2h_bytes_per_step": batch * 3, "ms_per_step": e2e_s / K * 1e3, "checksum": checksum,
                     "api": "Renderer.run_sample_preview -> clv_renderer_run_sample_preview: pinned host seeds in, one "
                            "pass, device tone map, uint8 preview image out (render.py:31-37)"},
             "e2e_accumulators": {"value": samples / e2e_acc_s / 1e6, "unit": "Msamples/s",
-                                 "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": batch * 32,
+                                 "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": batch * 32,
                                  "api": "Renderer.run_sample_e2e: seeds in, packed float accumulators [H][W][8] out"},
             "gpu_launches": launches,
             "roofline": roofline,
         }
+        if world > 1:
+            line.update(alt)
+        if rel_rmse is not None:
+            line["rel_rmse"] = rel_rmse
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg)
+            try:
+                line["cpu_baseline"] = cpu_baseline(cfg, arrays)
+            except Exception as e:  # noqa: BLE001
+                extras_err["cpu_baseline"] = repr(e)
+        if extras_err:
+            line["errors_in_extras"] = extras_err
         print(json.dumps(line), flush=True)
 
-    h_seeds.release()
-    h_seeds_b.release()
-    h_accum.release()
-    h_image.release()
+    for x in (h_seeds, h_seeds_b, h_accum, h_image):
+        x.release()
     r.release()
     sc.release()
     dev.release()
@@ -433,19 +629,54 @@ def run_ours(args, cfg, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def image_error(args, cfg, arrays_full, dev):
+    """Relative RMSE (sqrt(mean((a-b)^2)) / mean(b)) of the estimate `summed_image / summed_sample_weights`
+    (renderer.py:293-300) on a reduced frame of the same scene: GPU at RMSE_SPP vs CPU reference (glibc build) at the
+    same spp (different RNG streams and elementary functions: this is Monte-Carlo noise of two independent renders), and
+    each of them against a CPU image at RMSE_HI_SPP."""
+    from clive2_b200 import scene
+    from clive2_b200.renderer import Renderer
+    w, h = RMSE_FRAME[args.config]
+    a = build_arrays_like(arrays_full, cfg, w, h)
+
+    def err(img, ref):
+        img, ref = np.asarray(img, np.float64), np.asarray(ref, np.float64)
+        return float(np.sqrt(np.mean((img - ref) ** 2)) / max(np.mean(ref), 1e-30))
+
+    _, threads, kind, cpu_hi = cpu_passes(a, RMSE_HI_SPP, seed_stream=501)
+    _, _, _, cpu_eq = cpu_passes(a, RMSE_SPP, seed_stream=502)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds_for(w * h, 503))
+    for _ in range(RMSE_SPP):
+        r.run_sample()
+    gpu_eq = r.estimate()
+    for _ in range(RMSE_HI_SPP - RMSE_SPP):
+        r.run_sample()
+    gpu_hi = r.estimate()
+    r.release()
+    sc.release()
+    return {"gpu_vs_cpu_equal_spp": err(gpu_eq, cpu_eq), "gpu_vs_hi_spp": err(gpu_eq, cpu_hi), "cpu_vs_hi_spp": err(cpu_eq, cpu_hi),
+            "gpu_hi_vs_cpu_hi": err(gpu_hi, cpu_hi), "mean_ratio_gpu_over_cpu_hi": float(gpu_hi.mean() / cpu_hi.mean()),
+            "spp": RMSE_SPP, "hi_spp": RMSE_HI_SPP, "frame": f"{w}x{h}", "cpu_kind": kind,
+            "what": f"same scene and BVH as the workload at a {w}x{h} frame; independent RNG streams per image; the two "
+                    f"equal-spp errors against the high-spp CPU image should agree (same estimator, same noise)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default=os.environ.get("CLV_BENCH_CONFIG", "c4"))
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", choices=("pass", "tile"), default="pass",
-                    help="N > 1: 'pass' = every rank renders full-frame passes from its own seeds (weak scaling, default); "
-                         "'tile' = the ranks split every pass of ONE frame by 16x16 tiles (strong scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline and rel_rmse (profiling runs)")
+    ap.add_argument("--no-alternatives", action="store_true", help="N > 1: skip the pure tile / weak pass measurements")
+    ap.add_argument("--mesh-in-memory", action="store_true", help="c3/c4: do not round-trip the mesh through OBJ/PLY")
+    ap.add_argument("--shard", choices=("auto", "pass", "tile"), default="auto",
+                    help="N > 1: 'auto' = pass groups x tile groups (sharding.shard_plan, default), 'tile' = every pass split "
+                         "by 16x16 tiles, 'pass' = passes dealt to the GPUs (needs steps % N == 0); all strong scaling")
     ap.add_argument("--tile", default=os.environ.get("CLV_BENCH_TILE", ""),
-                    help="WxH: trace samples in tiles of WxH pixels per warp-sized group (e.g. 8x4); default row-major")
+                    help="N = 1: trace samples in tiles of WxH pixels per warp-sized group (e.g. 8x4); default row-major")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     args.steps = max(args.steps, 1)
@@ -454,14 +685,14 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
-    if args.impl == "reference":
-        run_reference(args, cfg, rank)
-        return
     if args.gpus > 1 and world == 1:
         # launched without torchrun: re-launch one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
     run_ours(args, cfg, rank, local_rank, world)
 
 

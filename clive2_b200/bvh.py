@@ -22,6 +22,8 @@ platform.  On tie-free input all variants agree exactly.
 """
 from collections import deque
 
+import subprocess
+
 import numpy as np
 
 from .constants import MAX_DEPTH, MAX_MEMBERS
@@ -219,7 +221,7 @@ def build_flat_bvh(soup, builder="auto", sort_kind="stable"):
         try:
             from . import native_bvh
             return native_bvh.build(soup)
-        except (ImportError, OSError):
+        except (ImportError, OSError, subprocess.CalledProcessError):
             if builder == "native":
                 raise
     return np_flatten_bvh(construct_BVH(soup, sort_kind=sort_kind))

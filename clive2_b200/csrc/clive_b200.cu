@@ -256,6 +256,8 @@ extern "C" int clv_host_free(void *h_ptr) {
 #endif
 struct clv_accel {
     clv_ctx *ctx;
+    int refs; /* 1 for the creator + 1 per renderer built on it: clv_accel_destroy only frees at zero, so releasing the
+               * scene (or its buffers) before a renderer that still traverses the structure is harmless */
     V4 *d_nodes, *d_wnodes, *d_tris;
     Triangle *d_ref_triangles;
     int32_t *d_camera_tris;
@@ -264,6 +266,7 @@ struct clv_accel {
     int large; /* traversal records exceed CLV_LARGE_SCENE_BYTES: the fused pass uses its high-occupancy kernel flavours */
 };
 
+extern "C" int clv_accel_destroy(clv_accel *a);
 extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_boxes, const clv_Triangle *h_tris_,
                                 int32_t n_tris, clv_accel **out) {
     REQUIRE(c && out && h_boxes_ && h_tris_, "null");
@@ -286,24 +289,30 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     if (!a) return fail(CLV_ERR_NOMEM, "host allocation");
     memset(a, 0, sizeof *a);
     a->ctx = c;
+    a->refs = 1;
     a->n_nodes = nodes.size();
     a->n_tris = (uint64_t)n_tris;
     size_t nb_nodes = std::max<size_t>(nodes.size(), 1) * sizeof(NodeRec);
     size_t nb_tris = ctris.size() * sizeof(V4);
     size_t nb_ref = (size_t)n_tris * sizeof(Triangle);
     size_t nb_cam = std::max<size_t>(camera_tris.size(), 1) * sizeof(int32_t);
-    CK(dev_alloc(c, &a->d_nodes, nb_nodes));
+    /* on failure free what was allocated so far: the pool never trims, a half-built 10 M-triangle structure would strand
+     * its blocks for the life of the process */
+#define CKA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { clv_accel_destroy(a); \
+        return fail(e_ == cudaErrorMemoryAllocation ? CLV_ERR_NOMEM : CLV_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+    CKA(dev_alloc(c, &a->d_nodes, nb_nodes));
     size_t nb_wide = std::max<size_t>(H.wide.size(), 1) * sizeof(WideRec);
-    CK(dev_alloc(c, &a->d_wnodes, nb_wide));
-    if (!H.wide.empty()) CK(cudaMemcpyAsync(a->d_wnodes, H.wide.data(), H.wide.size() * sizeof(WideRec), cudaMemcpyHostToDevice, c->stream));
-    CK(dev_alloc(c, &a->d_tris, nb_tris));
-    CK(dev_alloc(c, &a->d_ref_triangles, nb_ref));
-    CK(dev_alloc(c, &a->d_camera_tris, nb_cam));
-    if (!nodes.empty()) CK(cudaMemcpyAsync(a->d_nodes, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(a->d_tris, ctris.data(), nb_tris, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(a->d_ref_triangles, tris, nb_ref, cudaMemcpyHostToDevice, c->stream));
-    if (!camera_tris.empty()) CK(cudaMemcpyAsync(a->d_camera_tris, camera_tris.data(), camera_tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CKA(dev_alloc(c, &a->d_wnodes, nb_wide));
+    if (!H.wide.empty()) CKA(cudaMemcpyAsync(a->d_wnodes, H.wide.data(), H.wide.size() * sizeof(WideRec), cudaMemcpyHostToDevice, c->stream));
+    CKA(dev_alloc(c, &a->d_tris, nb_tris));
+    CKA(dev_alloc(c, &a->d_ref_triangles, nb_ref));
+    CKA(dev_alloc(c, &a->d_camera_tris, nb_cam));
+    if (!nodes.empty()) CKA(cudaMemcpyAsync(a->d_nodes, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, c->stream));
+    CKA(cudaMemcpyAsync(a->d_tris, ctris.data(), nb_tris, cudaMemcpyHostToDevice, c->stream));
+    CKA(cudaMemcpyAsync(a->d_ref_triangles, tris, nb_ref, cudaMemcpyHostToDevice, c->stream));
+    if (!camera_tris.empty()) CKA(cudaMemcpyAsync(a->d_camera_tris, camera_tris.data(), camera_tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CKA(cudaStreamSynchronize(c->stream));
+#undef CKA
     a->view.nodes = a->d_nodes;
     a->view.wnodes = a->d_wnodes;
     a->view.wroot_ref = H.wide_root_ref;
@@ -322,6 +331,7 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
 
 extern "C" int clv_accel_destroy(clv_accel *a) {
     if (!a) return CLV_OK;
+    if (--a->refs > 0) return CLV_OK; /* a renderer still uses it: freed when the last user lets go */
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
     dev_free(a->ctx, a->d_nodes);
@@ -1066,6 +1076,7 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     dev_free(r->ctx, r->d_tone_sum);
     dev_free(r->ctx, r->d_tone_image);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
+    clv_accel_destroy(const_cast<clv_accel *>(r->accel)); /* drops the renderer's reference */
     delete r;
     return CLV_OK;
 }
@@ -1111,6 +1122,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     clv_renderer *r = new (std::nothrow) clv_renderer();
     if (!r) return fail(CLV_ERR_NOMEM, "host allocation");
     r->ctx = c; r->accel = accel;
+    const_cast<clv_accel *>(accel)->refs++;
     r->width = cam->pixel_width; r->height = cam->pixel_height; r->n_pixels = n_pixels; r->n_local = n_local;
     r->light_count = s->n_lights;
     r->mode = CLV_TRAVERSE_ORDERED;
@@ -1158,9 +1170,16 @@ extern "C" int clv_renderer_set_path_records(clv_renderer *r, int enabled) {
     clv_ctx *c = r->ctx;
     CK(cudaSetDevice(c->device));
     if (enabled && !r->d_light_paths) {
-        CK(dev_alloc(c, &r->d_light_paths, (size_t)r->n_local * sizeof(Path)));
+        Path *lp = nullptr, *cp = nullptr;
+        CK(dev_alloc(c, &lp, (size_t)r->n_local * sizeof(Path)));
+        cudaError_t e2 = dev_alloc(c, &cp, (size_t)r->n_local * sizeof(Path));
+        if (e2 != cudaSuccess) { /* all or nothing: a renderer with one of the two records would read a null pointer */
+            dev_free(c, lp);
+            return fail(e2 == cudaErrorMemoryAllocation ? CLV_ERR_NOMEM : CLV_ERR_CUDA, "path records: %s", cudaGetErrorString(e2));
+        }
+        r->d_light_paths = lp;
+        r->d_camera_paths = cp;
         CK(cudaMemsetAsync(r->d_light_paths, 0, (size_t)r->n_local * sizeof(Path), c->stream));
-        CK(dev_alloc(c, &r->d_camera_paths, (size_t)r->n_local * sizeof(Path)));
         CK(cudaMemsetAsync(r->d_camera_paths, 0, (size_t)r->n_local * sizeof(Path), c->stream));
     }
     r->path_records = enabled ? 1 : 0;

@@ -27,13 +27,16 @@ def frames_for_rank(start_frame, total_frames, rank, world):
 
 
 def write_image(path, image_bgr_u8):
+    """PNG through cv2 (movie.py:52); only when cv2 itself is missing does the frame go out as .npy instead.  A failed
+    write (unwritable path, unknown extension: cv2.imwrite returns False) is an error, not a silently missing frame."""
     try:
         import cv2
-        cv2.imwrite(path, image_bgr_u8)
-        return path
-    except Exception:
+    except ImportError:
         np.save(path + ".npy", image_bgr_u8)
         return path + ".npy"
+    if not cv2.imwrite(path, image_bgr_u8):
+        raise OSError(f"cv2.imwrite could not write {path!r}")
+    return path
 
 
 def frame_arrays(preset, width, height, frame_idx=None, total_frames=None):

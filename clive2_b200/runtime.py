@@ -13,6 +13,7 @@ no B200-class GPU is visible.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -138,6 +139,7 @@ class Buffer:
         self.nbytes = int(nbytes)
         self.dtype = np.dtype(dtype) if dtype is not None else None
         self.shape = shape
+        self.version = 0  # bumped whenever the contents change: invalidates acceleration structures built from them
         p = C.c_void_p()
         _check(device.lib.clv_mem_alloc(device.ctx, self.nbytes, C.byref(p)))
         self.ptr = p.value
@@ -147,7 +149,12 @@ class Buffer:
         if a.nbytes > self.nbytes:
             raise ValueError("array larger than buffer")
         _check(self.device.lib.clv_mem_upload(self.device.ctx, self.ptr, _host_ptr(a), a.nbytes))
+        self._changed()
         return self
+
+    def _changed(self):
+        self.version += 1
+        self.device._forget_accels(self)
 
     def numpy(self, dtype=None, count=None):
         """Download (waits for pending launches).  `dtype` defaults to the dtype the buffer was created from."""
@@ -161,6 +168,7 @@ class Buffer:
 
     def fill32(self, value):
         _check(self.device.lib.clv_mem_fill32(self.device.ctx, self.ptr, int(value) & 0xFFFFFFFF, self.nbytes // 4))
+        self._changed()
 
     @property
     def __cuda_array_interface__(self):
@@ -168,9 +176,10 @@ class Buffer:
         return {"shape": (self.nbytes // 4,), "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
 
     def release(self):
+        # drop the cache entry of an acceleration structure built from this buffer (the structure itself is reference
+        # counted in the library: a renderer that still uses it keeps it alive until the renderer is released)
+        self.device._forget_accels(self)
         if getattr(self, "ptr", None):
-            # an acceleration structure cached for this buffer must not outlive it: the allocator reuses addresses
-            self.device._forget_accels(self.ptr)
             self.device.lib.clv_mem_free(self.device.ctx, self.ptr)
             self.ptr = None
 
@@ -179,6 +188,83 @@ class Buffer:
             self.release()
         except Exception:
             pass
+
+
+class LazyBuffer(Buffer):
+    """A Buffer whose device copy is made on first use of `.ptr`.  The scene's `boxes` / `triangles` are such buffers:
+    the fused renderer traverses the acceleration structure (built from the host arrays, with its own compact device
+    records) and never touches them, so a 10 M-triangle scene does not hold a second 1.3 GB copy of its Triangle[] in
+    HBM; the stage-level kernels, which take them as arguments, trigger the upload."""
+
+    def __init__(self, device, array):
+        a = np.ascontiguousarray(array)
+        self.device = device
+        self.nbytes = max(int(a.nbytes), 16)
+        self.dtype, self.shape = a.dtype, a.shape
+        self.version = 0
+        self._host = a
+        self._ptr = None
+
+    @property
+    def ptr(self):
+        if self._ptr is None and self._host is not None:
+            p = C.c_void_p()
+            _check(self.device.lib.clv_mem_alloc(self.device.ctx, self.nbytes, C.byref(p)))
+            self._ptr = p.value
+            if self._host.nbytes:
+                _check(self.device.lib.clv_mem_upload(self.device.ctx, self._ptr, _host_ptr(self._host), self._host.nbytes))
+        return self._ptr
+
+    @ptr.setter
+    def ptr(self, value):
+        self._ptr = value
+        if value is None:
+            self._host = None
+
+    @property
+    def resident(self):
+        return self._ptr is not None
+
+    def host_array(self):
+        """The host copy the buffer was created from (None once its contents were changed on the device)."""
+        return self._host
+
+    def upload(self, array):
+        a = np.ascontiguousarray(array)
+        if a.nbytes > self.nbytes:
+            raise ValueError("array larger than buffer")
+        if self._ptr is None:
+            self._host = a.copy() if a.nbytes == self._host.nbytes else None
+            if self._host is None:
+                raise ValueError("partial upload into a lazy buffer that is not resident yet")
+            self._changed()
+            return self
+        self._host = None
+        return Buffer.upload(self, a)
+
+    def fill32(self, value):
+        _ = self.ptr
+        self._host = None
+        Buffer.fill32(self, value)
+
+    def numpy(self, dtype=None, count=None):
+        if self._ptr is None and self._host is not None:
+            out = self._host.reshape(-1).view(np.uint8)
+            dt = np.dtype(dtype) if dtype is not None else self.dtype
+            out = out.view(dt).copy()
+            if count is not None:
+                out = out[:int(count)]
+            elif dtype is None:
+                out = out.reshape(self.shape)
+            return out
+        return Buffer.numpy(self, dtype, count)
+
+    def release(self):
+        self.device._forget_accels(self)
+        if self._ptr:
+            self.device.lib.clv_mem_free(self.device.ctx, self._ptr)
+        self._ptr = None
+        self._host = None
 
 
 class _ForeignBuffer:
@@ -293,20 +379,49 @@ class Device:
         return KernelLibrary(self)
 
     # --- extras ---------------------------------------------------------------------------------------------------
-    def accel(self, boxes, triangles):
-        """Acceleration structure for a (boxes, triangles) pair of Buffers or arrays; cached per buffer pair so that
-        the reference's call sites, which pass both buffers to every traversal kernel, build it once."""
-        key = (getattr(boxes, "ptr", id(boxes)), getattr(triangles, "ptr", id(triangles)))
-        acc = self._accels.get(key)
-        if acc is None:
-            b = boxes.numpy(T.Box) if isinstance(boxes, Buffer) else boxes
-            t = triangles.numpy(T.Triangle) if isinstance(triangles, Buffer) else triangles
-            acc = self._accels[key] = Accel(self, b, t)
-        return acc
+    def lazy_buffer(self, data):
+        """Like `buffer(array)`, but the device copy is made when a kernel first asks for it (see LazyBuffer)."""
+        return LazyBuffer(self, data)
 
-    def _forget_accels(self, ptr):
-        for key in [k for k in getattr(self, "_accels", {}) if ptr in k]:
-            self._accels.pop(key).release()
+    def accel(self, boxes, triangles):
+        """Acceleration structure for a (boxes, triangles) pair.
+
+        For a pair of Buffers it is cached — the reference's call sites pass both buffers to every traversal kernel —
+        under the identity AND the content version of the two buffers: `upload()` / `fill32()` / `release()` of either
+        drops the entry, so a kernel never traverses a stale BVH.  Host arrays are not cached (CPython reuses `id()`s and
+        nothing says when an array's contents change): the caller gets a fresh `Accel` and owns it."""
+        if isinstance(boxes, Buffer) and isinstance(triangles, Buffer):
+            key = (id(boxes), id(triangles))
+            ent = self._accels.get(key)
+            if ent is not None:
+                rb, rt, acc, versions = ent
+                if rb() is boxes and rt() is triangles and versions == (boxes.version, triangles.version) and acc.handle:
+                    return acc
+                self._accels.pop(key)
+                acc.release()
+            # host copies when the buffers still have them (no 1.3 GB device-to-host copy at 10 M triangles)
+            hb = boxes.host_array() if isinstance(boxes, LazyBuffer) else None
+            ht = triangles.host_array() if isinstance(triangles, LazyBuffer) else None
+            acc = Accel(self, boxes.numpy(T.Box) if hb is None else hb, triangles.numpy(T.Triangle) if ht is None else ht)
+            self._accels[key] = (weakref.ref(boxes), weakref.ref(triangles), acc, (boxes.version, triangles.version))
+            return acc
+        b = boxes.numpy(T.Box) if isinstance(boxes, Buffer) else boxes
+        t = triangles.numpy(T.Triangle) if isinstance(triangles, Buffer) else triangles
+        return Accel(self, b, t)
+
+    def _accel_for_call(self, boxes, triangles):
+        """(accel, owned): `owned` structures were built for this one call and are released by the caller."""
+        cached = isinstance(boxes, Buffer) and isinstance(triangles, Buffer)
+        return self.accel(boxes, triangles), not cached
+
+    def _forget_accels(self, buf):
+        """Drop cache entries built from `buf` (and entries whose buffers are gone).  Dropping releases the cache's
+        reference only: the library keeps a structure alive while a renderer uses it (clv_accel is reference counted)."""
+        for key in list(getattr(self, "_accels", {})):
+            rb, rt, acc, _ = self._accels[key]
+            if rb() is buf or rt() is buf or rb() is None or rt() is None:
+                self._accels.pop(key)
+                acc.release()
 
     def synchronize(self):
         _check(self.lib.clv_ctx_synchronize(self.ctx))
@@ -384,8 +499,8 @@ class Device:
         A.done()
 
     def release(self):
-        for acc in list(getattr(self, "_accels", {}).values()):
-            acc.release()
+        for ent in list(getattr(self, "_accels", {}).values()):
+            ent[2].release()
         self._accels = {}
         if getattr(self, "ctx", None):
             self.lib.clv_ctx_destroy(self.ctx)
@@ -453,10 +568,14 @@ def _k_generate_camera_rays(dev, n, camera, rand, indices, out):
 
 def _k_generate_paths(dev, n, rays, boxes, triangles, materials, rand, out, paths, debug):
     A = _Args(dev)
-    acc = dev.accel(boxes, triangles)
-    _check(dev.lib.clv_generate_paths(dev.ctx, n, A.ptr(rays), acc.handle, A.ptr(materials), A.ptr(rand), A.ptr(out),
-                                      A.ptr(paths), A.ptr(debug)))
-    A.done()
+    acc, owned = dev._accel_for_call(boxes, triangles)
+    try:
+        _check(dev.lib.clv_generate_paths(dev.ctx, n, A.ptr(rays), acc.handle, A.ptr(materials), A.ptr(rand), A.ptr(out),
+                                          A.ptr(paths), A.ptr(debug)))
+        A.done()
+    finally:
+        if owned:
+            acc.release()  # waits for the launch
 
 
 def _k_reset_light_indices(dev, n, pix, path, ray, w, shade):
@@ -468,11 +587,15 @@ def _k_reset_light_indices(dev, n, pix, path, ray, w, shade):
 def _k_connect_paths(dev, n, camera_paths, light_paths, triangles, materials, boxes, camera, aggregators, out, pix, path,
                      ray, w, shade):
     A = _Args(dev)
-    acc = dev.accel(boxes, triangles)
-    _check(dev.lib.clv_connect_paths(dev.ctx, n, A.ptr(camera_paths), A.ptr(light_paths), acc.handle, A.ptr(materials),
-                                     A.ptr(camera), A.ptr(aggregators), A.ptr(out), A.ptr(pix), A.ptr(path), A.ptr(ray),
-                                     A.ptr(w), A.ptr(shade)))
-    A.done()
+    acc, owned = dev._accel_for_call(boxes, triangles)
+    try:
+        _check(dev.lib.clv_connect_paths(dev.ctx, n, A.ptr(camera_paths), A.ptr(light_paths), acc.handle, A.ptr(materials),
+                                         A.ptr(camera), A.ptr(aggregators), A.ptr(out), A.ptr(pix), A.ptr(path), A.ptr(ray),
+                                         A.ptr(w), A.ptr(shade)))
+        A.done()
+    finally:
+        if owned:
+            acc.release()
 
 
 def _k_adaptive_finalize_samples(dev, n, aggregators, camera, out, counts, bin_offsets, weights):

@@ -147,7 +147,9 @@ def scene_from_arrays(arrays, device=None):
     up = dev.buffer
     return Scene(
         device=dev, pixel_width=arrays.pixel_width, pixel_height=arrays.pixel_height,
-        camera=up(arrays.camera), triangles=up(arrays.triangles), boxes=up(arrays.boxes),
+        # boxes / triangles: device copies are made only if a stage-level kernel asks for them (runtime.LazyBuffer); the
+        # fused renderer traverses the acceleration structure built from the host arrays
+        camera=up(arrays.camera), triangles=dev.lazy_buffer(arrays.triangles), boxes=dev.lazy_buffer(arrays.boxes),
         materials=up(arrays.materials),
         light_triangles=up(arrays.light_triangles), light_counts=up(arrays.light_counts),
         light_surface_areas=up(arrays.light_surface_areas),

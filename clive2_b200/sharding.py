@@ -12,14 +12,53 @@ on GPUs; the same call runs on gloo/CPU tensors in the tests).
 import numpy as np
 
 
+def _row_step(world):
+    """Per-row rotation of the tile owners: the smallest odd step that is coprime with `world`."""
+    for step in (3, 5, 7, 11, 13, 17):
+        if np.gcd(step, world) == 1:
+            return step
+    return 1
+
+
+def tile_owner(width, height, world, tile=16):
+    """Owner rank of every pixel: tiles of `tile` x `tile` pixels dealt round-robin along a row, each row of tiles
+    rotated by a step coprime with `world`.  (Plain row-major round-robin degenerates into vertical stripes whenever the
+    number of tiles per row is a multiple of `world` — 1920 / 16 = 120 tiles on 8 ranks — and a column's cost then
+    decides a rank's time.)  Every `world` consecutive tiles of a row, and every `world` consecutive rows of a column,
+    go to `world` different ranks."""
+    ys, xs = np.divmod(np.arange(width * height, dtype=np.int64), width)
+    return ((xs // tile) + (ys // tile) * _row_step(world)) % world
+
+
 def tile_ids(width, height, rank, world, tile=16):
-    """Sample ids (= pixel indices) of `rank`: tiles of `tile` x `tile` pixels dealt round-robin in row-major order."""
+    """Sample ids (= pixel indices) of `rank`, ascending: its tiles of `tile` x `tile` pixels (see `tile_owner`)."""
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
-    ys, xs = np.divmod(np.arange(width * height, dtype=np.int64), width)
-    tiles_x = (width + tile - 1) // tile
-    owner = ((ys // tile) * tiles_x + (xs // tile)) % world
-    return np.flatnonzero(owner == rank).astype(np.uint32)
+    return np.flatnonzero(tile_owner(width, height, world, tile) == rank).astype(np.uint32)
+
+
+def shard_plan(world, steps):
+    """How `world` GPUs split `steps` sample passes of ONE frame (strong scaling): (tile_groups, pass_groups) with
+    tile_groups * pass_groups == world.  A GPU in tile group t and pass group p traces the tiles of group t for the passes
+    p, p + pass_groups, ... from pass group p's own RNG streams; one reduce sums everything.
+
+    Passes are the cheaper axis to split — a GPU keeps whole frames, i.e. as many resident warps per pass as a single-GPU
+    render — so pass_groups is the largest divisor of `world` that divides `steps` (every GPU then renders exactly
+    steps / pass_groups passes); what is left is split by tile."""
+    world, steps = int(world), int(steps)
+    best = 1
+    for p in range(1, world + 1):
+        if world % p == 0 and steps % p == 0:
+            best = p
+    return world // best, best
+
+
+def hybrid_shard(width, height, rank, world, steps, tile=16):
+    """(sample ids or None, pass group, passes of this rank, tile_groups, pass_groups) for `shard_plan(world, steps)`."""
+    tile_groups, pass_groups = shard_plan(world, steps)
+    t, p = rank % tile_groups, rank // tile_groups
+    ids = None if tile_groups == 1 else tile_ids(width, height, t, tile_groups, tile)
+    return ids, p, steps // pass_groups, tile_groups, pass_groups
 
 
 def rank_seeds(batch, base_seed, rank):

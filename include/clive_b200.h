@@ -120,6 +120,8 @@ CLV_API int clv_host_free(void *h_ptr);
 typedef struct clv_accel clv_accel;
 CLV_API int clv_accel_create(clv_ctx *ctx, const clv_Box *h_boxes, int32_t n_boxes, const clv_Triangle *h_triangles,
                              int32_t n_triangles, clv_accel **out);
+/* Reference counted: clv_renderer_create takes a reference and clv_renderer_destroy drops it, so destroying the
+ * structure (or the scene that owns it) while a renderer still traverses it only defers the free. */
 CLV_API int clv_accel_destroy(clv_accel *accel);
 /* the compact layout: [0] bytes of binary node records, [1] bytes of triangle records, [2] binary node count,
  * [3] triangle count, [4] bytes of 4-wide node records, [5] 4-wide node count, [6]/[7] 1 if closest-hit / occlusion

@@ -1,0 +1,200 @@
+"""Parity at BASELINE.json's own configurations and frame sizes (round-1 tests used 64x64 / 64x48 frames).
+
+Every test renders the configuration's scene at the configuration's resolution with the fused CUDA renderer (through
+the C ABI) and with the CPU oracle in its shared-math build on the same seeds, and compares RNG state, MIS aggregators
+and the unidirectional image bit for bit and the accumulated image within the float-summation-order tolerance of the
+atomically splatted light image (rtol 5e-4).  Where oracle/_ref exists (the reference's own trace.metal compiled as
+C++, prebuilt in the build container and shipped with the snapshot) the checker is THAT, not the restatement.
+
+A second group renders each configuration at bench size with the reference's visiting order (REFERENCE_ORDER: unordered
+DFS, right child first, trace.metal:144-176) and with the product's ordered traversal and requires IDENTICAL path
+records, RNG state and aggregators: zero rays with a different hit, not "few".
+"""
+import numpy as np
+import pytest
+
+from clive2_b200 import runtime, scene, struct_types as T
+from clive2_b200.renderer import Renderer
+from oracle import oracle as oracle_mod
+from oracle.oracle import OracleRenderer
+from tests.common import arrays, assert_bits_equal, assert_paths_equal, rel_rmse, seeds_for
+
+pytestmark = pytest.mark.gpu
+
+USE_REF = oracle_mod.have_ref()  # checker = the compiled reference when it is available
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = runtime.Device(0)
+    yield d
+    d.release()
+
+
+def checker(a, seeds):
+    r = OracleRenderer(a, seeds, shared_math=True, reference=USE_REF)
+    r.oracle.use_all_cores()
+    return r
+
+
+def compare_with_checker(dev, a, passes, seed=20240928, rtol=5e-4):
+    w, h = a.pixel_width, a.pixel_height
+    b = w * h
+    seeds = seeds_for(b, seed=seed)
+    ref = checker(a, seeds)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds)
+    for _ in range(passes):
+        ref.run_sample()
+        r.run_sample()
+    assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b).reshape(b, 2), "RNG state")
+    assert_bits_equal(ref.buffer("aggregators", T.WeightAggregator), r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b),
+                      "aggregators of the last pass", nan_equal=True)
+    assert_bits_equal(ref.unidirectional_image_buffer.reshape(b, 3), np.ascontiguousarray(r.unidirectional_image_buffer).reshape(b, 3),
+                      "unidirectional image", nan_equal=True)
+    assert np.array_equal(ref.summed_sample_counts, r.summed_sample_counts)
+    np.testing.assert_allclose(r.summed_sample_weights, ref.summed_sample_weights, rtol=5e-5, atol=1e-6)
+    np.testing.assert_allclose(r.summed_image, ref.summed_image, rtol=rtol, atol=1e-6)
+    est_ref = np.nan_to_num(ref.summed_image / ref.summed_sample_weights)
+    err = rel_rmse(r.estimate(), est_ref)
+    assert err < 1e-4, err
+    ref.close()
+    r.release()
+    sc.release()
+    return err
+
+
+def test_c1_cornell_256x256_16spp_vs_checker(dev):
+    """BASELINE.json configs[0]: built-in Cornell box, 256x256, 16 spp — the whole configuration."""
+    compare_with_checker(dev, arrays("empty", 256, 256), passes=16)
+
+
+def test_c2_ggx_transmission_512x512_vs_checker(dev):
+    """BASELINE.json configs[1] at its frame size: GGX specular + dielectric transmission, 512x512, 4 of its 64 passes."""
+    a = arrays("bench-spheres", 512, 512)
+    compare_with_checker(dev, a, passes=4)
+
+
+def test_c3_terrain_1m_256x256_vs_checker(dev):
+    """BASELINE.json configs[2]'s scene (1 002 528-triangle mesh, high-occupancy kernel flavours) at 256x256, 2 passes."""
+    a = scene.preset_arrays("bench-terrain-1m", 256, 256)
+    compare_with_checker(dev, a, passes=2, seed=5)
+
+
+def test_c4_terrain_10m_160x90_vs_checker(dev):
+    """BASELINE.json configs[3]'s scene — the north-star configuration's 9 999 392 triangles, i.e. the kernels, tree depth
+    and leaf chains the headline number runs on — at 160x90 (1080p / 12), 2 passes."""
+    a = scene.preset_arrays("bench-terrain-10m", 160, 90)
+    assert len(a.triangles) > 9_900_000
+    sc_stats_dev = runtime.Accel(dev, a.boxes, a.triangles)
+    assert sc_stats_dev.stats()["large_scene_tuning"]
+    sc_stats_dev.release()
+    compare_with_checker(dev, a, passes=2, seed=11)
+
+
+def both_orders(dev, a, passes, seed):
+    w, h = a.pixel_width, a.pixel_height
+    b = w * h
+    seeds = seeds_for(b, seed=seed)
+    sc = scene.scene_from_arrays(a, dev)
+    out = []
+    for mode in (runtime.TRAVERSE_REFERENCE_ORDER, runtime.TRAVERSE_ORDERED):
+        r = Renderer(sc, seeds=seeds, traverse_mode=mode, path_records=True)
+        for _ in range(passes):
+            r.run_sample()
+        out.append(dict(seeds=r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b),
+                        cam=r._fr.read(runtime.BUF_CAMERA_PATHS, T.Path, b), lig=r._fr.read(runtime.BUF_LIGHT_PATHS, T.Path, b),
+                        aggs=r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), acc=r._accum().copy()))
+        r.release()
+    sc.release()
+    return out
+
+
+@pytest.mark.parametrize("preset,w,h,passes,native", [
+    ("empty", 256, 256, 4, False),              # C1 at bench size
+    ("bench-spheres", 512, 512, 2, False),      # C2 at bench size
+    ("bench-terrain-1m", 1024, 1024, 1, True),  # C3 at bench size
+])
+def test_ordered_traversal_equals_reference_order_at_bench_size(dev, preset, w, h, passes, native):
+    """Every ray of the pass — closest hits of both walks, shadow rays, projections — decides the same way under the
+    product's ordered traversal as under the reference's visiting order: identical Path records (hit triangle of every
+    vertex included), RNG state and aggregators.  north_star: 'bit-exact ... ray-triangle hit indices for identical rays'."""
+    a = scene.preset_arrays(preset, w, h) if native else arrays(preset, w, h)
+    ref_order, ordered = both_orders(dev, a, passes, seed=31)
+    assert np.array_equal(ref_order["seeds"], ordered["seeds"])
+    assert_paths_equal(ref_order["cam"], ordered["cam"], "camera paths, reference order vs ordered")
+    assert_paths_equal(ref_order["lig"], ordered["lig"], "light paths, reference order vs ordered")
+    assert_bits_equal(ref_order["aggs"], ordered["aggs"], "aggregators (every shadow ray decided identically)", nan_equal=True)
+    # accumulators: unidirectional + count exact, image up to the splat's summation order
+    assert np.array_equal(ref_order["acc"][..., 4:8].view(np.uint32), ordered["acc"][..., 4:8].view(np.uint32))
+    np.testing.assert_allclose(ordered["acc"][..., 0:4], ref_order["acc"][..., 0:4], rtol=5e-4, atol=1e-6)
+
+
+def test_c4_scene_ordered_equals_reference_order(dev):
+    a = scene.preset_arrays("bench-terrain-10m", 320, 180)
+    ref_order, ordered = both_orders(dev, a, 1, seed=41)
+    assert np.array_equal(ref_order["seeds"], ordered["seeds"])
+    assert_paths_equal(ref_order["cam"], ordered["cam"], "camera paths")
+    assert_paths_equal(ref_order["lig"], ordered["lig"], "light paths")
+    assert_bits_equal(ref_order["aggs"], ordered["aggs"], "aggregators", nan_equal=True)
+
+
+def test_c2_image_against_glibc_transcription_within_noise(dev):
+    """GGX / transmission scene against the canonical glibc build of the checker (different elementary functions, so
+    paths diverge after the first bounce: statistical agreement).  Tolerance: 1.5 x the transcription's own seed-to-seed
+    relative RMSE at equal spp against a 128-spp transcription image, plus agreement of the image means within 3 %."""
+    w, h = 96, 96
+    a = arrays("bench-spheres", w, h)
+    b = w * h
+
+    def cpu_est(seed, spp):
+        r = OracleRenderer(a, seeds_for(b, seed=seed), shared_math=False, reference=USE_REF)
+        r.oracle.use_all_cores()
+        for _ in range(spp):
+            r.run_sample()
+        est = np.nan_to_num(r.summed_image / r.summed_sample_weights)
+        r.close()
+        return est
+
+    hi = cpu_est(201, 128)
+    noise = rel_rmse(cpu_est(202, 16), hi)
+    sc = scene.scene_from_arrays(a, dev)
+    r = Renderer(sc, seeds=seeds_for(b, seed=203))
+    for _ in range(16):
+        r.run_sample()
+    e16 = rel_rmse(r.estimate(), hi)
+    for _ in range(112):
+        r.run_sample()
+    e128 = rel_rmse(r.estimate(), hi)
+    assert e16 < 1.5 * noise, (e16, noise)
+    assert e128 < e16
+    assert abs(r.estimate().mean() - hi.mean()) / hi.mean() < 0.03
+    r.release()
+    sc.release()
+
+
+def test_accel_cache_follows_buffer_contents_and_renderer_outlives_scene(dev):
+    """a cached acceleration structure must not survive an upload into its buffers, and releasing the scene
+    before a renderer that still uses its structure must be harmless (clv_accel is reference counted)."""
+    a = arrays("empty", 32, 32)
+    sc = scene.scene_from_arrays(a, dev)
+    acc1 = dev.accel(sc.boxes, sc.triangles)
+    assert dev.accel(sc.boxes, sc.triangles) is acc1
+    assert not sc.triangles.resident  # the fused path never needs the reference-layout device copy
+    sc.triangles.upload(a.triangles)
+    acc2 = dev.accel(sc.boxes, sc.triangles)
+    assert acc2 is not acc1 and acc1.handle is None
+    fresh = dev.accel(a.boxes, a.triangles)  # host arrays: never cached, caller owns
+    assert fresh is not acc2 and dev.accel(a.boxes, a.triangles) is not fresh
+    fresh.release()
+    seeds = seeds_for(32 * 32)
+    r = Renderer(sc, seeds=seeds)
+    keep = Renderer(sc, seeds=seeds)
+    r.run_sample()
+    sc.release()      # scene (and the cache's reference) gone first ...
+    r.run_sample()    # ... the renderer still traverses a live structure
+    keep.run_sample()
+    keep.run_sample()
+    assert np.array_equal(r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * 32 * 32), keep._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * 32 * 32))
+    r.release()
+    keep.release()

@@ -16,9 +16,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c2")
 ap.add_argument("--passes", type=int, default=6)
 ap.add_argument("--mode", default="ordered")
+ap.add_argument("--mesh-in-memory", action="store_true")
 args = ap.parse_args()
 cfg = bench.CONFIGS[args.config]
-arrays = bench.build_arrays(cfg)
+arrays = bench.build_arrays(cfg, via_file=not args.mesh_in_memory)
 dev = runtime.Device(0)
 sc = scene.scene_from_arrays(arrays, dev)
 r = Renderer(sc, seeds=bench.seeds_for(cfg["width"] * cfg["height"], 0),
