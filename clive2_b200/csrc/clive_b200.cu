@@ -60,6 +60,9 @@ struct clv_ctx {
     int counting;
     unsigned long long launches;
     int sm_count;
+    int walk_mode;       /* fused pass, stages 1-4: 0 = automatic, 1 = megakernel (k_fused_walks), 2 = wavefront (k_walk_*) */
+    int walk_refill_below, walk_schedule; /* k_walk_trace: refill threshold and vote weight, as for k_connect_rays */
+    int trace_blocks_per_sm[2];           /* resident blocks of k_walk_trace (cache-resident / large flavour) */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
@@ -116,6 +119,11 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
      * 1.093 ms for k_connect_rays; C3: 12 / 16 / 24 -> 6.70 / 6.44 / 6.44 ms */
     c->refill_below = getenv("CLV_REFILL_BELOW") ? atoi(getenv("CLV_REFILL_BELOW")) : 16;
     c->ray_schedule = getenv("CLV_RAY_SCHEDULE") ? atoi(getenv("CLV_RAY_SCHEDULE")) : 8; /* measured: C2 1.15 -> 1.10 ms, C3 8.07 -> 7.10 ms */
+    c->walk_mode = getenv("CLV_WALK_MODE") ? atoi(getenv("CLV_WALK_MODE")) : 0;
+    c->walk_refill_below = getenv("CLV_WALK_REFILL_BELOW") ? atoi(getenv("CLV_WALK_REFILL_BELOW")) : 24;
+    if (c->walk_refill_below < 1) c->walk_refill_below = 1;
+    c->walk_schedule = getenv("CLV_WALK_SCHEDULE") ? atoi(getenv("CLV_WALK_SCHEDULE")) : 8;
+    c->trace_blocks_per_sm[0] = c->trace_blocks_per_sm[1] = 0; /* asked from the occupancy calculator on first use */
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -251,6 +259,10 @@ extern "C" int clv_host_free(void *h_ptr) {
  * are issue-bound and lose with fewer registers.  Measured (walks at 64 / 48 / 40 / 32 registers per thread): C2 (2.8 MB)
  * 0.98 / 1.01 / - / - ms, C3 (60 MB) 6.81 / 6.32 / 6.13 / 6.17 ms, C4 (700 MB) 25.5 / 22.5 / 21.2 / 19.6 ms; occlusion
  * rays at 63 / 48 / 40 / 32 registers: C2 0.99 / 1.00 ms, C3 6.73 / 6.60 / - / 8.71 ms, C4 14.3 / 13.5 / 13.9 / 16.4 ms. */
+/* which scenes run stages 1-4 as wavefront rounds when the walk mode is automatic (measured: profiles/r02_notes.md) */
+#ifndef CLV_WAVEFRONT_BY_DEFAULT
+#define CLV_WAVEFRONT_BY_DEFAULT(large_scene) (large_scene)
+#endif
 #ifndef CLV_LARGE_SCENE_BYTES
 #define CLV_LARGE_SCENE_BYTES (32u << 20)
 #endif
@@ -534,7 +546,7 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
     Cnt<COUNT> cnt;
     Camera c = camera[0];
     OccRay ray;
-    int stack[CLV_STACK];
+    int stack[CLV_OCC_STACK];
     bool have = false;
     uint32_t task = 0;
     int next = 0; /* warp-uniform: first task of the chunk not handed out yet */
@@ -732,6 +744,126 @@ k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, cons
     flush_counters<COUNT>(cnt, counters);
 }
 
+/* ---- wavefront form of stages 1-4: k_walk_init, then per round k_walk_trace + k_walk_shade ----------- *
+ * The megakernel above runs a sample's <= 12 closest-hit searches inside one thread, bounce-synchronously: a warp waits for
+ * its slowest ray at every bounce and ncu counts 5-11 of 32 lanes per instruction.  Here a round traces ray number r of
+ * every sample that still has one:
+ *   k_walk_trace  persistent warps.  A lane that finishes its search takes the next ray of the round's queue (one
+ *                 atomicAdd per warp and refill: warp-level work fetch), and per iteration the warp runs ONE kind of
+ *                 step — an inner node or a whole leaf — for the lanes that wait for it, chosen by majority vote
+ *   k_walk_shade  one thread per traced ray: BSDF sampling, vertex store, next ray; survivors are appended to the next
+ *                 round's queue (one atomicAdd per warp)
+ * Same per-ray operations in the same order as the megakernel: bit-identical results. */
+struct WalkQueues {
+    uint32_t *q[2];   /* ping-pong lists of sample slots */
+    uint32_t *count;  /* [CLV_WALK_ROUNDS + 1]: entries of round r's list (round 0 = every sample of the slice, implicit) */
+    uint32_t *cursor; /* [CLV_WALK_ROUNDS]: next unfetched entry of round r's list */
+};
+#define CLV_WALK_COUNTER_WORDS 32 /* per slice: count[13] + cursor[12], padded */
+
+template <bool SOA>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, const float *surface_areas,
+            const int32_t *light_triangle_indices, int light_count, const Material *materials, uint32_t *seeds,
+            PathStore store, WalkState ws, WalkQueues wq) {
+    const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < CLV_WALK_COUNTER_WORDS) wq.count[threadIdx.x] = 0u; /* count[] and cursor[] are one block */
+    if (id >= n_end) return;
+    uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
+    uint32_t seed0 = sd.x, seed1 = sd.y;
+    wavefront_init_sample<SOA>(id, light_triangles, surface_areas, light_triangle_indices, light_count, materials, seed0, seed1,
+                               store, ws);
+    reinterpret_cast<uint2 *>(seeds)[id] = make_uint2(seed0, seed1);
+}
+
+#ifndef CLV_TRACE_MIN_BLOCKS
+#define CLV_TRACE_MIN_BLOCKS (1024 / CLV_BLOCK) /* <= 64 registers per thread */
+#endif
+#ifndef CLV_TRACE_MIN_BLOCKS_LARGE
+#define CLV_TRACE_MIN_BLOCKS_LARGE (1280 / CLV_BLOCK) /* <= 48 registers per thread */
+#endif
+template <bool COUNT, int LARGE>
+__global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_TRACE_MIN_BLOCKS_LARGE : CLV_TRACE_MIN_BLOCKS)
+k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *cursor,
+             WalkState ws, AccelView A, Counters *counters, int refill_below, int schedule) {
+    const uint32_t count = queue ? *count_ptr : n_identity;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Cnt<COUNT> cnt;
+    HitRay ray;
+    StackEntry st[CLV_STACK];
+    bool have = false, exhausted = false; /* exhausted is warp-uniform */
+    uint32_t slot = 0;
+    for (;;) {
+        const unsigned holding = __ballot_sync(0xffffffffu, have);
+        if (!exhausted && __popc(holding) < refill_below) {
+            /* warp-level work fetch: the idle lanes take the next entries of the round's queue */
+            const unsigned idle = ~holding;
+            const int n_idle = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t my = base + (uint32_t)__popc(idle & lt_mask);
+            if (!have && my < count) {
+                slot = queue ? queue[my] : first + my;
+                const V4 a0 = ws.s0[slot], a1 = ws.s1[slot];
+                ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
+                cnt.ray_ref();
+                if (hit_begin<COUNT>(A, ray, cnt) == HIT_RUNNING) have = true;
+                else ws.hit[slot] = v4(i2f(-1), CLV_INF, 0.0f, 0.0f);
+            }
+            if ((uint64_t)base + (uint64_t)n_idle >= (uint64_t)count) exhausted = true;
+        } else if (holding == 0u) {
+            break;
+        }
+        /* majority vote: one inner-node step for the lanes at inner nodes, or one whole leaf for the lanes at leaves */
+        const bool at_inner = have && ray.cur >= 0;
+        const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && !at_inner));
+        int status = HIT_RUNNING;
+        if (n_inner * schedule >= n_leaf * 4) { if (at_inner) status = hit_inner_step<COUNT>(A, ray, st, cnt); }
+        else if (have && !at_inner) status = hit_leaf_step<COUNT>(A, ray, st, cnt);
+        if (status == HIT_DONE) {
+            have = false;
+            ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
+        }
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+template <bool COUNT, bool SOA>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_walk_shade(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *queue_out,
+             uint32_t *count_out, const uint32_t *sample_ids, const Material *materials, const Camera *camera, AccelView A,
+             uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters) {
+    const uint32_t count = queue ? *count_ptr : n_identity;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    Cnt<COUNT> cnt;
+    const Camera c = camera[0];
+    for (uint64_t w0 = (uint64_t)warp * 32u; w0 < count; w0 += (uint64_t)n_warps * 32u) { /* warp-uniform trip count */
+        const uint32_t idx = (uint32_t)w0 + (uint32_t)lane;
+        bool more = false;
+        uint32_t slot = 0;
+        if (idx < count) {
+            slot = queue ? queue[idx] : first + idx;
+            const uint32_t gid = sample_ids ? sample_ids[slot] : slot;
+            uint2 sd = reinterpret_cast<uint2 *>(seeds)[slot];
+            uint32_t seed0 = sd.x, seed1 = sd.y;
+            more = wavefront_shade_sample<COUNT, SOA>(slot, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt);
+            if (seed0 != sd.x || seed1 != sd.y) reinterpret_cast<uint2 *>(seeds)[slot] = make_uint2(seed0, seed1);
+        }
+        const unsigned staying = __ballot_sync(0xffffffffu, more);
+        if (staying) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(count_out, (uint32_t)__popc(staying));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) queue_out[base + (uint32_t)__popc(staying & ((1u << lane) - 1u))] = slot;
+        }
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
 /* stages 6-8: finalize (identity sample bins) + light image + accumulation; clears the per-pass light image */
 __global__ void __launch_bounds__(CLV_BLOCK)
 k_fused_finalize(uint32_t n_pixels, const WeightAggregator *aggs, const Camera *camera, V4 *light_image, Accum *accum,
@@ -864,19 +996,21 @@ extern "C" int clv_set_stage_traverse_mode(int mode) {
     return CLV_OK;
 }
 
+struct clv_renderer;
+static int mark_connect(clv_renderer *r, cudaStream_t st, int which); /* timing mark after enumerate / rays / finish */
 /* enumerate -> rays -> finish for the samples [first, n) on `stream`; `cs` holds this slice's own task list */
 static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat, bool large, uint32_t first, uint32_t n,
                           const uint32_t *sample_ids, const PathStore &store,
                           bool soa, const AccelView &view, const Material *mats, const Camera *cam,
                           ConnectScratch cs, WeightAggregator *aggs, V4 *out, const LightSink &sink,
-                          cudaEvent_t *mid_events /* NULL or 2 events: after enumerate, after rays */) {
+                          struct clv_renderer *timed /* NULL, or the renderer whose timing marks follow each kernel */) {
     Counters *ctr = c->d_counters + COUNTERS_CONNECT;
     const uint32_t len = n - first;
 #define CALL(M, CT, SO) k_connect_enumerate<M, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, store, view, mats, cam, cs, ctr)
     DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     LAUNCHED(c);
-    if (mid_events) CK(cudaEventRecord(mid_events[0], stream));
+    if (timed && mark_connect(timed, stream, 0) != CLV_OK) return CLV_ERR_CUDA;
     const uint64_t warps = ((uint64_t)len * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
     const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
     if (large && mode == CLV_TRAVERSE_ORDERED && !c->counting && soa) {
@@ -888,7 +1022,7 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
 #undef CALL
     }
     LAUNCHED(c);
-    if (mid_events) CK(cudaEventRecord(mid_events[1], stream));
+    if (timed && mark_connect(timed, stream, 1) != CLV_OK) return CLV_ERR_CUDA;
 #define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
     if (soa) {
         if (splat) { if (c->counting) FIN(true, true, true); else FIN(true, false, true); }
@@ -899,6 +1033,7 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
     }
 #undef FIN
     LAUNCHED(c);
+    if (timed && mark_connect(timed, stream, 2) != CLV_OK) return CLV_ERR_CUDA;
     return CLV_OK;
 }
 
@@ -1028,8 +1163,9 @@ extern "C" int clv_light_image_splat(clv_ctx *c, uint32_t n_entries, uint32_t n_
 /* ---------------------------------------------------------------------------------------------------------------
  * section 5: fused renderer
  * ------------------------------------------------------------------------------------------------------------- */
-#define CLV_PASS_KERNELS 5 /* walks, connect-enumerate, connect-rays, connect-finish, finalize */
-#define CLV_PASS_EVENTS (CLV_PASS_KERNELS + 1)
+/* kernels of a fused pass as the timing interface names them (clv_renderer_kernel_times) */
+enum { TK_FUSED_WALKS = 0, TK_ENUMERATE, TK_RAYS, TK_FINISH, TK_FINALIZE, TK_WALK_TRACE, TK_WALK_SHADE, CLV_TIMED_KERNELS };
+#define CLV_PASS_KERNELS CLV_TIMED_KERNELS
 struct clv_renderer {
     clv_ctx *ctx;
     const clv_accel *accel;
@@ -1059,8 +1195,16 @@ struct clv_renderer {
     unsigned long long passes;
     /* optional per-kernel timing: events around each of the five kernels of every pass */
     int timing;
-    std::vector<cudaEvent_t> events; /* CLV_PASS_EVENTS per pass: before walks, after each of the five kernels */
+    /* timing marks: an event after every launch of a timed pass, tagged with the kernel it follows (-1 = start of a
+     * pass); the time between two consecutive marks is the later one's kernel (one slice, one stream: launches serialise) */
+    std::vector<cudaEvent_t> events;
+    std::vector<int> event_kernel;
     double kernel_ms[CLV_PASS_KERNELS];
+    /* wavefront walks (k_walk_*) */
+    V4 *d_walk_state;      /* 5 parts (s0..s3, hit) x n_local */
+    float *d_walk_jitter;  /* [n_local][2] */
+    uint32_t *d_walk_queue; /* 2 x n_local */
+    uint32_t *d_walk_counters; /* CLV_MAX_SLICES x CLV_WALK_COUNTER_WORDS */
     unsigned long long timed_passes;
 };
 
@@ -1075,6 +1219,8 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     dev_free(r->ctx, r->d_connect_scratch);
     dev_free(r->ctx, r->d_tone_sum);
     dev_free(r->ctx, r->d_tone_image);
+    dev_free(r->ctx, r->d_walk_state); dev_free(r->ctx, r->d_walk_jitter); dev_free(r->ctx, r->d_walk_queue);
+    dev_free(r->ctx, r->d_walk_counters);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     clv_accel_destroy(const_cast<clv_accel *>(r->accel)); /* drops the renderer's reference */
     delete r;
@@ -1156,6 +1302,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     TRY(zalloc((void **)&r->d_connect_scratch, connect_scratch_bytes(n_local)));
     TRY(zalloc((void **)&r->d_tone_sum, 16));
     TRY(zalloc((void **)&r->d_tone_image, (size_t)n_pixels * 3));
+    r->d_walk_state = nullptr; r->d_walk_jitter = nullptr; r->d_walk_queue = nullptr; r->d_walk_counters = nullptr;
     TRY(load_seeds(r, h_seeds));
 #undef TRY
     CK(cudaStreamSynchronize(c->stream));
@@ -1193,19 +1340,97 @@ extern "C" int clv_renderer_set_traverse_mode(clv_renderer *r, int mode) {
     return CLV_OK;
 }
 
+static int mark(clv_renderer *r, cudaStream_t st, int kernel);
+static int mark_connect(clv_renderer *r, cudaStream_t st, int which) { return mark(r, st, TK_ENUMERATE + which); }
+static int mark(clv_renderer *r, cudaStream_t st, int kernel) {
+    if (!r->timing) return CLV_OK;
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, st));
+    r->events.push_back(e);
+    r->event_kernel.push_back(kernel);
+    return CLV_OK;
+}
+
+/* buffers of the wavefront walks, allocated the first time a pass runs in that mode */
+static int ensure_walk_buffers(clv_renderer *r) {
+    if (r->d_walk_state) return CLV_OK;
+    clv_ctx *c = r->ctx;
+    const size_t n = r->n_local;
+    CK(dev_alloc(c, &r->d_walk_state, n * 5 * sizeof(V4)));
+    CK(dev_alloc(c, &r->d_walk_jitter, n * 2 * sizeof(float)));
+    CK(dev_alloc(c, &r->d_walk_queue, n * 2 * sizeof(uint32_t)));
+    CK(dev_alloc(c, &r->d_walk_counters, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(r->d_walk_counters, 0, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t), c->stream));
+    return CLV_OK;
+}
+
+/* persistent grid of k_walk_trace: every SM filled with the resident blocks of the flavour, never more warps than rays */
+template <typename K>
+static int trace_grid(clv_ctx *c, K kernel, int flavour, uint32_t n_rays, unsigned *grid_out) {
+    if (!c->trace_blocks_per_sm[flavour]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CLV_BLOCK, 0));
+        c->trace_blocks_per_sm[flavour] = per_sm > 0 ? per_sm : 1;
+    }
+    const uint64_t resident = (uint64_t)c->sm_count * (uint64_t)c->trace_blocks_per_sm[flavour];
+    const uint64_t needed = ((uint64_t)n_rays + CLV_BLOCK - 1) / CLV_BLOCK;
+    *grid_out = (unsigned)std::max<uint64_t>(1, std::min(resident, needed));
+    return CLV_OK;
+}
+
+/* stages 1-4 of the samples [first, end) as wavefront rounds on `st` */
+static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, uint32_t first, uint32_t end, const uint32_t *ids,
+                                  const PathStore &store, bool soa, bool large) {
+    clv_ctx *c = r->ctx;
+    const uint32_t len = end - first;
+    const size_t n = r->n_local;
+    WalkState ws;
+    ws.s0 = r->d_walk_state; ws.s1 = ws.s0 + n; ws.s2 = ws.s1 + n; ws.s3 = ws.s2 + n; ws.hit = ws.s3 + n;
+    ws.jitter = r->d_walk_jitter;
+    WalkQueues wq;
+    wq.q[0] = r->d_walk_queue + first;      /* a slice's lists never hold more than its own samples */
+    wq.q[1] = r->d_walk_queue + n + first;
+    wq.count = r->d_walk_counters + (size_t)slice * CLV_WALK_COUNTER_WORDS;
+    wq.cursor = wq.count + (CLV_WALK_ROUNDS + 1);
+    static_assert(2 * CLV_WALK_ROUNDS + 1 <= CLV_WALK_COUNTER_WORDS, "walk counters");
+    Counters *ctr = c->d_counters + COUNTERS_WALK;
+    if (soa) k_walk_init<true><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq);
+    else k_walk_init<false><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq);
+    LAUNCHED(c);
+    int rc = mark(r, st, TK_WALK_SHADE);
+    if (rc != CLV_OK) return rc;
+    unsigned tgrid = 1;
+    if (large) rc = trace_grid(c, k_walk_trace<false, 1>, 1, len, &tgrid);
+    else if (c->counting) rc = trace_grid(c, k_walk_trace<true, 0>, 0, len, &tgrid);
+    else rc = trace_grid(c, k_walk_trace<false, 0>, 0, len, &tgrid);
+    if (rc != CLV_OK) return rc;
+    const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 16u, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK));
+    for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
+        const uint32_t *qin = round == 0 ? nullptr : wq.q[round & 1];
+        uint32_t *qout = wq.q[(round + 1) & 1];
+        const uint32_t n_identity = round == 0 ? len : 0u;
+        if (large) k_walk_trace<false, 1><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
+        else if (c->counting) k_walk_trace<true, 0><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
+        else k_walk_trace<false, 0><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
+        LAUNCHED(c);
+        if ((rc = mark(r, st, TK_WALK_TRACE)) != CLV_OK) return rc;
+#define SHADE(CT, SO) k_walk_shade<CT, SO><<<sgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, qout, wq.count + round + 1, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr)
+        if (soa) { if (c->counting) SHADE(true, true); else SHADE(false, true); }
+        else { if (c->counting) SHADE(true, false); else SHADE(false, false); }
+#undef SHADE
+        LAUNCHED(c);
+        if ((rc = mark(r, st, TK_WALK_SHADE)) != CLV_OK) return rc;
+    }
+    return CLV_OK;
+}
+
 static int launch_pass(clv_renderer *r) {
     clv_ctx *c = r->ctx;
     const uint32_t *ids = r->sample_ids.empty() ? nullptr : r->d_sample_ids;
     uint32_t n = r->n_local;
-    size_t ev0 = r->events.size();
-    if (r->timing) {
-        for (int k = 0; k < CLV_PASS_EVENTS; k++) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            r->events.push_back(e);
-        }
-        CK(cudaEventRecord(r->events[ev0], c->stream));
-    }
+    int rc = mark(r, c->stream, -1);
+    if (rc != CLV_OK) return rc;
     PathStore store;
     memset(&store, 0, sizeof store);
     store.light_paths = r->d_light_paths;
@@ -1221,6 +1446,11 @@ static int launch_pass(clv_renderer *r) {
     const ConnectScratch cs_all = connect_scratch_at(r->d_connect_scratch, n);
     /* default configuration (ORDERED, SoA records, no counters) on a scene larger than the caches */
     const bool large = r->accel->large && r->mode == CLV_TRAVERSE_ORDERED && !c->counting && soa;
+    /* stages 1-4 as wavefront rounds or as the megakernel.  The wavefront kernels exist for the ORDERED traversal only (the
+     * reference-order mode is a parity instrument, not a product path).  Automatic: see clv_ctx_walk_mode */
+    const bool wavefront = r->mode == CLV_TRAVERSE_ORDERED &&
+                           (c->walk_mode == 2 || (c->walk_mode == 0 && CLV_WAVEFRONT_BY_DEFAULT(r->accel->large)));
+    if (wavefront && (rc = ensure_walk_buffers(r)) != CLV_OK) return rc;
     /* slices: whole blocks each; one slice (everything on the context's stream) when per-kernel events are wanted */
     int slices = c->pass_slices > 0 ? c->pass_slices : (n >= (uint32_t)c->sm_count * 1024u ? 3 : 1);
     if (r->timing) slices = 1;
@@ -1233,30 +1463,33 @@ static int launch_pass(clv_renderer *r) {
         if (first >= end) continue;
         cudaStream_t st = k == 0 ? c->stream : c->slice_stream[k];
         if (k > 0) CK(cudaStreamWaitEvent(st, c->slice_fork, 0));
-        if (large) {
-            k_fused_walks<TRAVERSE_ORDERED, false, true, 1><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters);
+        if (wavefront) {
+            if ((rc = launch_wavefront_walks(r, st, k, first, end, ids, store, soa, large)) != CLV_OK) return rc;
         } else {
+            if (large) {
+                k_fused_walks<TRAVERSE_ORDERED, false, true, 1><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters);
+            } else {
 #define CALL(M, CT, SO) k_fused_walks<M, CT, SO><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters)
-            DISPATCH_MCS(r->mode, c->counting, soa, CALL);
+                DISPATCH_MCS(r->mode, c->counting, soa, CALL);
 #undef CALL
+            }
+            LAUNCHED(c);
+            if ((rc = mark(r, st, TK_FUSED_WALKS)) != CLV_OK) return rc;
         }
-        LAUNCHED(c);
-        if (r->timing) CK(cudaEventRecord(r->events[ev0 + 1], st));
         ConnectScratch cs = cs_all;
         cs.task_count = cs_all.task_count + k;
         cs.tasks = cs_all.tasks + (size_t)first * 36;
-        int rc = launch_connect(c, st, r->mode, true, large, first, end, ids, store, soa, r->accel->view, r->d_materials,
-                                r->d_camera, cs, r->d_aggs, nullptr, sink, r->timing ? &r->events[ev0 + 2] : nullptr);
+        rc = launch_connect(c, st, r->mode, true, large, first, end, ids, store, soa, r->accel->view, r->d_materials,
+                            r->d_camera, cs, r->d_aggs, nullptr, sink, r);
         if (rc != CLV_OK) return rc;
         if (k > 0) {
             CK(cudaEventRecord(c->slice_join[k], st));
             CK(cudaStreamWaitEvent(c->stream, c->slice_join[k], 0));
         }
     }
-    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 4], c->stream));
     k_fused_finalize<<<GRID(r->n_pixels), CLV_BLOCK, 0, c->stream>>>(r->n_pixels, r->d_aggs, r->d_camera, r->d_light_image, r->d_accum, r->d_pass_weight);
     LAUNCHED(c);
-    if (r->timing) CK(cudaEventRecord(r->events[ev0 + 5], c->stream));
+    if ((rc = mark(r, c->stream, TK_FINALIZE)) != CLV_OK) return rc;
     r->passes++;
     return CLV_OK;
 }
@@ -1267,26 +1500,54 @@ extern "C" int clv_renderer_kernel_timing(clv_renderer *r, int enabled) {
     r->timing = enabled ? 1 : 0;
     return CLV_OK;
 }
-extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_t *passes_out, int reset) {
+extern "C" int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_KERNEL_SLOTS], uint64_t *passes_out, int reset) {
     REQUIRE(r && ms_out && passes_out, "null");
+    static_assert(CLV_TIMED_KERNELS <= CLV_TIMED_KERNEL_SLOTS, "timing slots");
     CK(cudaSetDevice(r->ctx->device));
     CK(cudaStreamSynchronize(r->ctx->stream));
-    for (size_t i = 0; i + CLV_PASS_KERNELS < r->events.size(); i += CLV_PASS_EVENTS) {
-        for (int k = 0; k < CLV_PASS_KERNELS; k++) {
-            float ms = 0.0f;
-            CK(cudaEventElapsedTime(&ms, r->events[i + k], r->events[i + k + 1]));
-            r->kernel_ms[k] += ms;
-        }
-        r->timed_passes++;
+    for (size_t i = 0; i < r->events.size(); i++) {
+        const int k = r->event_kernel[i];
+        if (k < 0) { r->timed_passes++; continue; }
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, r->events[i - 1], r->events[i]));
+        r->kernel_ms[k] += ms;
     }
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     r->events.clear();
-    for (int k = 0; k < CLV_PASS_KERNELS; k++) ms_out[k] = r->kernel_ms[k];
+    r->event_kernel.clear();
+    for (int k = 0; k < CLV_TIMED_KERNEL_SLOTS; k++) ms_out[k] = k < CLV_TIMED_KERNELS ? r->kernel_ms[k] : 0.0;
     *passes_out = r->timed_passes;
     if (reset) {
         for (int k = 0; k < CLV_PASS_KERNELS; k++) r->kernel_ms[k] = 0.0;
         r->timed_passes = 0;
     }
+    return CLV_OK;
+}
+
+/* scheduling knobs of the two ray kernels (none changes a result); returns the previous value through *previous */
+extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *previous) {
+    REQUIRE(c && name, "null");
+    int *slot = nullptr;
+    if (!strcmp(name, "walk_refill_below")) slot = &c->walk_refill_below;
+    else if (!strcmp(name, "walk_schedule")) slot = &c->walk_schedule;
+    else if (!strcmp(name, "connect_refill_below")) slot = &c->refill_below;
+    else if (!strcmp(name, "connect_schedule")) slot = &c->ray_schedule;
+    else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
+    if (previous) *previous = *slot;
+    if (value >= 0) {
+        if ((slot == &c->walk_refill_below || slot == &c->walk_schedule) && value < 1) value = 1;
+        *slot = value;
+    }
+    return CLV_OK;
+}
+
+/* stages 1-4 of the fused pass: 0 = automatic, 1 = megakernel (k_fused_walks), 2 = wavefront (k_walk_init / k_walk_trace /
+ * k_walk_shade).  < 0 only queries.  Results are bit-identical in both. */
+extern "C" int clv_ctx_walk_mode(clv_ctx *c, int mode, int *current_out) {
+    REQUIRE(c, "null ctx");
+    REQUIRE(mode <= 2, "walk mode is 0 (automatic), 1 (megakernel) or 2 (wavefront)");
+    if (mode >= 0) c->walk_mode = mode;
+    if (current_out) *current_out = c->walk_mode;
     return CLV_OK;
 }
 

@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "clv_device.cuh"
@@ -31,7 +32,27 @@ struct HostAccel {
     std::vector<V4> tris;             /* 3 per triangle, reference order */
     std::vector<int32_t> camera_tris; /* indices of is_camera triangles */
     int32_t root_ref;
+    int32_t binary_depth, wide_depth; /* inner nodes on the longest root-to-leaf path: what bounds the traversal stacks */
 };
+
+/* inner nodes on the longest root-to-leaf path (iterative: a degenerate tree can be 10^5 levels deep) */
+template <class CHILDREN>
+inline int32_t tree_depth(int32_t root_ref, CHILDREN children) {
+    if (root_ref < 0) return 0;
+    std::vector<std::pair<int32_t, int32_t>> stack;
+    stack.push_back({root_ref, 1});
+    int32_t deepest = 0;
+    while (!stack.empty()) {
+        auto [ref, depth] = stack.back();
+        stack.pop_back();
+        if (depth > deepest) deepest = depth;
+        int32_t kids[4];
+        int n = children(ref, kids);
+        for (int k = 0; k < n; k++)
+            if (kids[k] >= 0) stack.push_back({kids[k], depth + 1});
+    }
+    return deepest;
+}
 
 inline NodeRec pack_node(const Box &l, const Box &r, int32_t lref, int32_t rref) {
     NodeRec n;
@@ -162,6 +183,23 @@ inline const char *build_host_accel(const Box *boxes, int32_t n_boxes, const Tri
         }
     }
     build_wide(H);
+    H.binary_depth = tree_depth(H.root_ref, [&](int32_t ref, int32_t kids[4]) {
+        memcpy(&kids[0], &H.nodes[ref].d.x, 4);
+        memcpy(&kids[1], &H.nodes[ref].d.y, 4);
+        return 2;
+    });
+    H.wide_depth = tree_depth(H.wide_root_ref, [&](int32_t ref, int32_t kids[4]) {
+        memcpy(kids, &H.wide[ref].q[6], 16); /* leaves and empty slots are negative */
+        return 4;
+    });
+    /* the traversal stacks hold one deferred sibling per binary level / three per 4-wide level (clv_device.cuh): a deeper
+     * tree is refused here, loudly, instead of silently dropping pushes in the kernels.  (The reference's own 64-entry
+     * stack silently aborts the search in that case, trace.metal:149.) */
+    if (H.binary_depth > CLV_MAX_BINARY_DEPTH || H.wide_depth > CLV_MAX_WIDE_DEPTH) {
+        snprintf(why, sizeof why, "BVH too deep for the traversal stacks: %d binary levels (max %d), %d 4-wide levels (max %d)",
+                 H.binary_depth, CLV_MAX_BINARY_DEPTH, H.wide_depth, CLV_MAX_WIDE_DEPTH);
+        return why;
+    }
     H.tris.resize((size_t)n_tris * 3);
     H.camera_tris.clear();
     for (int32_t i = 0; i < n_tris; i++) {

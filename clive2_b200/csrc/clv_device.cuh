@@ -44,7 +44,12 @@
 #define CLV_DELTA 0.0001f     /* trace.metal:5 */
 #define CLV_INF (clv_bits_to_float(0x7f800000u))
 #define CLV_MAX_BOUNCES 6     /* trace.metal:407 */
-#define CLV_STACK 96          /* trace.metal:145 has 64; the 4-wide flavour keeps up to 3 siblings per level */
+/* Traversal stacks (thread-private local memory).  The reference's stack has 64 int entries (trace.metal:145) and its
+ * search silently stops when it fills; here a search defers at most ONE sibling per level of the binary tree (three per
+ * level of the 4-wide collapse), pruned children are never pushed, and clv_accel_create REFUSES a tree deeper than
+ * these bounds (CLV_ERR_INVALID) instead of dropping pushes: the `sp < CLV_*STACK` tests below are memory-safety guards
+ * that never fire on an accepted structure.  Closest-hit entries are (t_entry, ref) packed into one 64-bit word: half
+ * the local-memory instructions of two 32-bit arrays, 256 B per thread instead of 768 B. */
 /* which node layout the ORDERED flavour traverses: the 4-wide collapse of the BVH (1) or the binary nodes (0),
  * separately for closest-hit searches (random walks) and occlusion queries (connection rays) */
 #ifndef CLV_WIDE_CLOSEST
@@ -53,6 +58,10 @@
 #ifndef CLV_WIDE_OCCLUSION
 #define CLV_WIDE_OCCLUSION 1
 #endif
+#define CLV_STACK (CLV_WIDE_CLOSEST ? 96 : 32) /* closest-hit: 64-bit (t, ref) entries */
+#define CLV_OCC_STACK 64                       /* occlusion queries over the 4-wide nodes: 32-bit refs */
+#define CLV_MAX_BINARY_DEPTH (CLV_WIDE_CLOSEST ? CLV_OCC_STACK / 3 : CLV_STACK) /* deepest accepted tree (inner levels) */
+#define CLV_MAX_WIDE_DEPTH (CLV_OCC_STACK / 3)
 
 namespace clv {
 
@@ -132,6 +141,11 @@ CLV_HD int f2i(float f) {
 #endif
 }
 CLV_HD float i2f(int i) { return clv_bits_to_float((uint32_t)i); }
+/* one closest-hit stack entry: entry distance of a deferred child in the high word, its ref in the low word */
+typedef unsigned long long StackEntry;
+CLV_HD StackEntry stack_entry(float t, int ref) { return ((StackEntry)(uint32_t)f2i(t) << 32) | (StackEntry)(uint32_t)ref; }
+CLV_HD float entry_t(StackEntry e) { return i2f((int)(uint32_t)(e >> 32)); }
+CLV_HD int entry_ref(StackEntry e) { return (int)(uint32_t)e; }
 
 /* ---- work counters (instrumented kernel variants only; the timed variants compile all of this out) -------------- */
 struct Counters {
@@ -249,8 +263,7 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
      * inner nodes step together until every lane has reached a leaf (or finished), then all leaves are processed
      * together.  (A loop with several back edges lets the lanes drift apart for good: the first version of this
      * function ran its slab tests with 5 of 32 lanes active, profiles/r01_c2_ncu_v1.md.) */
-    int st_ref[CLV_STACK];
-    float st_t[CLV_STACK];
+    StackEntry st[CLV_STACK];
     int sp = 0;
     int best_rank = 0x7fffffff;
     cnt.ray_traced();
@@ -274,13 +287,13 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
             wide_sort(tk, rk);
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                if (tk[k] < CLV_INF && sp < CLV_STACK) { st_ref[sp] = rk[k]; st_t[sp] = tk[k]; sp++; }
+                if (tk[k] < CLV_INF && sp < CLV_STACK) { st[sp] = stack_entry(tk[k], rk[k]); sp++; }
             have = tk[3] < CLV_INF;
             cur = rk[3];
             while (!have && sp > 0) {
                 sp--;
-                float t = st_t[sp];
-                if (t <= best_t) { cur = st_ref[sp]; have = true; }
+                const StackEntry e = st[sp];
+                if (entry_t(e) <= best_t) { cur = entry_ref(e); have = true; }
             }
             return;
         }
@@ -315,11 +328,12 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
             cur = (go_l && (left_first || !go_r)) ? lref : rref;
             have = go_l || go_r;
         }
-        if (push && sp < CLV_STACK) { st_ref[sp] = push_ref; st_t[sp] = push_t; sp++; }
+        if (push && sp < CLV_STACK) { st[sp] = stack_entry(push_t, push_ref); sp++; }
         while (!have && sp > 0) {
             sp--;
-            float t = st_t[sp];
-            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+            const StackEntry e = st[sp];
+            const float t = entry_t(e);
+            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = entry_ref(e); have = true; }
         }
     };
     /* one leaf: test its triangles */
@@ -349,8 +363,9 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
         if (stop) sp = 0; /* early exit of a predicate ray: nothing left to look at */
         while (!have && sp > 0) {
             sp--;
-            float t = st_t[sp];
-            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = st_ref[sp]; have = true; }
+            const StackEntry e = st[sp];
+            const float t = entry_t(e);
+            if ((MODE == TRAVERSE_REFERENCE) ? (t < best_t) : (t <= best_t)) { cur = entry_ref(e); have = true; }
         }
     };
     /* while-while: lanes at inner nodes step together until every lane has reached a leaf (or finished), then all
@@ -360,6 +375,75 @@ CLV_HD void closest_hit(const AccelView &A, V3 o, V3 d, V3 inv, int &best_i, flo
         while (have && cur >= 0) inner_step();
         if (have) leaf_step();
     }
+}
+
+/* ---- resumable closest hit (wavefront walks) ------------------------------------------------------------------------ *
+ * The ORDERED search of closest_hit over the binary nodes, cut into single steps — one inner node or one whole leaf — so
+ * that a warp can hold 32 rays at different stages, run ONE kind of step per iteration for the lanes that wait for it
+ * (majority vote) and hand a finished lane the next ray of the queue (k_walk_trace).  Same operations per ray in the same
+ * order as closest_hit<TRAVERSE_ORDERED>, hence the same (best_i, best_t, u, v) bits; tests/hostemu checks both against
+ * the oracle.  Scalars only (registers); the stack of packed (t, ref) entries is a separate local array. */
+struct HitRay {
+    V3 o, d, inv;
+    float best_t, bu, bv;
+    int best_i, best_rank;
+    int cur, sp;
+};
+enum { HIT_RUNNING = 0, HIT_DONE = 1 };
+
+template <bool COUNT>
+CLV_HD int hit_begin(const AccelView &A, HitRay &r, Cnt<COUNT> &cnt) {
+    cnt.ray_traced();
+    r.best_i = -1; r.best_t = CLV_INF; r.bu = 0.0f; r.bv = 0.0f; r.best_rank = 0x7fffffff;
+    r.sp = 0;
+    bool hit;
+    float te;
+    slab_test(r.o, r.inv, xyz(A.root_min), xyz(A.root_max), hit, te);
+    if (!(hit && te < r.best_t)) return HIT_DONE;
+    r.cur = A.root_ref;
+    return HIT_RUNNING;
+}
+/* next deferred child that can still hold a closer (or tying) hit, or the end of the search */
+CLV_HD int hit_pop(HitRay &r, const StackEntry *st) {
+    while (r.sp > 0) {
+        r.sp--;
+        const StackEntry e = st[r.sp];
+        if (entry_t(e) <= r.best_t) { r.cur = entry_ref(e); return HIT_RUNNING; }
+    }
+    return HIT_DONE;
+}
+template <bool COUNT>
+CLV_HD int hit_inner_step(const AccelView &A, HitRay &r, StackEntry *st, Cnt<COUNT> &cnt) {
+    const V4 *n = A.nodes + 4 * (size_t)r.cur;
+    V4 n0 = ld4(n), n1 = ld4(n + 1), n2 = ld4(n + 2), n3 = ld4(n + 3);
+    cnt.node();
+    bool hl, hr;
+    float tl, tr;
+    slab_test(r.o, r.inv, v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), hl, tl);
+    slab_test(r.o, r.inv, v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), hr, tr);
+    const int lref = f2i(n3.x), rref = f2i(n3.y);
+    const bool go_l = hl && tl <= r.best_t, go_r = hr && tr <= r.best_t;
+    const bool left_first = tl < tr; /* tie: right first, the reference's order */
+    if (go_l && go_r && r.sp < CLV_STACK) { st[r.sp] = stack_entry(left_first ? tr : tl, left_first ? rref : lref); r.sp++; }
+    if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return HIT_RUNNING; }
+    return hit_pop(r, st);
+}
+template <bool COUNT>
+CLV_HD int hit_leaf_step(const AccelView &A, HitRay &r, const StackEntry *st, Cnt<COUNT> &cnt) {
+    const int code = ~r.cur;
+    const int first = code >> 4, count = code & 15;
+    for (int i = first; i < first + count; i++) {
+        const V4 *tp = A.tris + 3 * (size_t)i;
+        V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+        cnt.tri();
+        float t, u, v;
+        if (tri_test(r.o, r.d, xyz(a), xyz(b), xyz(c), t, u, v) &&
+            (t < r.best_t || (t == r.best_t && t < CLV_INF && f2i(a.w) < r.best_rank))) {
+            r.best_i = i; r.best_t = t; r.bu = u; r.bv = v;
+            r.best_rank = f2i(a.w);
+        }
+    }
+    return hit_pop(r, st);
 }
 
 /* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
@@ -411,7 +495,7 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
             const bool any = tk[near] < CLV_INF;
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (k != near && tk[k] < CLV_INF && sp < CLV_STACK) stack[sp++] = rk[k];
+                if (k != near && tk[k] < CLV_INF && sp < CLV_OCC_STACK) stack[sp++] = rk[k];
             if (any) cur = rk[near];
             else if (sp > 0) cur = stack[--sp];
             else status = OCC_CLEAR;
@@ -428,7 +512,7 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
         int lref = f2i(n3.x), rref = f2i(n3.y);
         bool go_l = hl && tl <= r.t_bound, go_r = hr && tr <= r.t_bound;
         bool left_first = tl < tr;
-        if (go_l && go_r && sp < CLV_STACK) stack[sp++] = left_first ? rref : lref;
+        if (go_l && go_r && sp < CLV_OCC_STACK) stack[sp++] = left_first ? rref : lref;
         if (go_l || go_r) cur = (go_l && (left_first || !go_r)) ? lref : rref;
         else if (sp > 0) cur = stack[--sp];
         else status = OCC_CLEAR;
@@ -470,7 +554,7 @@ CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> 
             if (tk[k] < tk[near]) near = k;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (k != near && tk[k] < CLV_INF && r.sp < CLV_STACK) stack[r.sp++] = rk[k];
+            if (k != near && tk[k] < CLV_INF && r.sp < CLV_OCC_STACK) stack[r.sp++] = rk[k];
         if (tk[near] < CLV_INF) { r.cur = rk[near]; return OCC_RUNNING; }
         if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
         return OCC_CLEAR;
@@ -486,7 +570,7 @@ CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> 
     int lref = f2i(n3.x), rref = f2i(n3.y);
     bool go_l = hl && tl <= r.t_bound, go_r = hr && tr <= r.t_bound;
     bool left_first = tl < tr;
-    if (go_l && go_r && r.sp < CLV_STACK) stack[r.sp++] = left_first ? rref : lref;
+    if (go_l && go_r && r.sp < CLV_OCC_STACK) stack[r.sp++] = left_first ? rref : lref;
     if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return OCC_RUNNING; }
     if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
     return OCC_CLEAR;
@@ -533,7 +617,7 @@ CLV_HD bool visibility_test(const AccelView &A, V3 a_origin, int a_triangle, V3 
         OccRay r;
         r.o = a_origin; r.d = direction; r.inv = inv; r.skip = b_triangle;
         if (!test_one(A, b_triangle, a_origin, direction, r.t_bound, r.rank_bound)) return false;
-        int stack[CLV_STACK];
+        int stack[CLV_OCC_STACK];
         int st = occ_begin<COUNT>(A, r, cnt);
         while (st == OCC_RUNNING) st = occ_round<COUNT>(A, r, stack, cnt);
         return st == OCC_CLEAR;
@@ -673,10 +757,10 @@ CLV_HD Ray zero_ray() {
 }
 
 /* generate_camera_rays, trace.metal:1020-1067 */
-CLV_HD Ray make_camera_ray(const Camera &c, int pixel_idx, uint32_t &seed0, uint32_t &seed1) {
+/* ... from the two jitter draws (the wavefront walks draw them up front, in the reference's order, and build the ray
+ * when the sample's light walk is over) */
+CLV_HD Ray camera_ray_from_jitter(const Camera &c, int pixel_idx, float x_offset, float y_offset) {
     Ray ray = zero_ray();
-    float x_offset = xorshift_random(seed0);
-    float y_offset = xorshift_random(seed1);
     int pixel_x = pixel_idx % c.pixel_width;
     int pixel_y = pixel_idx / c.pixel_width;
     float x_n = ((float)pixel_x + x_offset - 0.5f * (float)c.pixel_width) / (float)c.pixel_width;
@@ -700,6 +784,11 @@ CLV_HD Ray make_camera_ray(const Camera &c, int pixel_idx, uint32_t &seed0, uint
     ray.tot_importance = ray.c_importance;
     ray.pixel_idx = pixel_idx;
     return ray;
+}
+CLV_HD Ray make_camera_ray(const Camera &c, int pixel_idx, uint32_t &seed0, uint32_t &seed1) {
+    float x_offset = xorshift_random(seed0);
+    float y_offset = xorshift_random(seed1);
+    return camera_ray_from_jitter(c, pixel_idx, x_offset, y_offset);
 }
 
 /* generate_light_rays, trace.metal:1070-1124 (light_index clamped to count-1: the reference reads out of bounds
@@ -824,117 +913,158 @@ struct SoaSink {
 };
 
 /* ---- random walk: generate_paths, trace.metal:381-532 ----------------------------------------------------------- *
- * Vertices are written to out_path->rays[i] as they are produced (the reference builds the Path in thread memory and
- * copies 1040 bytes at the end).  Slots >= length keep whatever they held; nothing downstream reads them.  A path of
- * length 0 gets a zeroed rays[0], which is what connect_paths' splat-weight code then reads (the reference reads
- * uninitialised memory there; the oracle reads zeros).
+ * Vertices are written to their slot as they are produced (the reference builds the Path in thread memory and copies
+ * 1040 bytes at the end).  Slots >= length keep whatever they held; nothing downstream reads them.  A path of length 0
+ * gets a zeroed rays[0], which is what connect_paths' splat-weight code then reads (the reference reads uninitialised
+ * memory there; the oracle reads zeros).
+ *
+ * The walk is written as begin / bounce / finish around the closest-hit search so that two drivers share every
+ * operation: `random_walk` (one thread runs the whole walk: the stage-level ABI and the megakernel k_fused_walks) and the
+ * wavefront kernels (k_walk_trace traces the ray of every live walk, k_walk_shade runs `walk_bounce` on the hits).
  */
+struct WalkRegs { /* what a walk carries from one bounce to the next */
+    V3 o, d;        /* the ray about to be traced (inv_direction = rcp(d), the same bits the reference stores) */
+    V3 rc;          /* its colour = throughput up to this vertex */
+    float ray_tot;  /* tot_importance of the vertex the ray leaves */
+    float carry_imp;
+    int ray_hit_light;
+    V3 last_stored_color;
+    V4 uni;         /* unidirectional estimate, trace.metal:523-528 */
+    bool uni_found;
+    int length;
+};
+
+/* vertex 0 = the generated ray: stored (speculatively, like every vertex: slot i only counts once length > i) */
+template <typename SINK>
+CLV_HD void walk_begin(const Ray &ray, const SINK &sink, WalkRegs &W) {
+    const bool from_camera = ray.from_camera != 0;
+    sink.store(0, ray);
+    W.o = xyz(ray.origin); W.d = xyz(ray.direction); W.rc = xyz(ray.color);
+    W.ray_tot = ray.tot_importance;
+    W.carry_imp = from_camera ? ray.c_importance : 1.0f / (2.0f * CLV_PI);
+    W.ray_hit_light = ray.hit_light;
+    W.last_stored_color = v3(0, 0, 0);
+    W.uni = v4(0, 0, 0, 0);
+    W.uni_found = false;
+    W.length = 0;
+}
+
+/* Bounce i of a walk given the closest hit of its ray (trace.metal:414-516).  Returns false when the walk ends here
+ * (miss, side test, microfacet rejection, f == 0); otherwise vertex i is confirmed (its reverse pdf patched in), vertex
+ * i + 1 is stored when the loop will trace another ray (i + 1 < 6), and W holds that ray. */
+template <bool COUNT, typename SINK>
+CLV_HD bool walk_bounce(WalkRegs &W, int i, bool from_camera, int best_i, float best_t, float u, float v, const AccelView &A,
+                        const Material *materials, uint32_t &seed0, uint32_t &seed1, const SINK &sink, Cnt<COUNT> &cnt) {
+    if (best_i == -1) return false;
+    const V3 o = W.o, d = W.d, rc = W.rc;
+    const float ray_tot = W.ray_tot;
+
+    const Triangle *tri = A.ref_triangles + best_i;
+    V3 tn = xyz(ld4(&tri->normal));
+    V3 n0 = xyz(ld4(&tri->n0)), n1 = xyz(ld4(&tri->n1)), n2 = xyz(ld4(&tri->n2));
+    int tri_material = tri->material, tri_is_light = tri->is_light, tri_is_camera = tri->is_camera;
+    const Material *mat = materials + tri_material;
+    V3 mat_color = xyz(ld4(&mat->color));
+    int mat_type = mat->type;
+    float alpha = mat->alpha, ior = mat->ior;
+
+    V3 n;
+    float ni, no;
+    V3 sampled_normal = normalize((n0 * (1 - u - v) + n1 * u) + n2 * v);
+    float side = dot(-d, tn);
+    if (side > 0) { n = sampled_normal; ni = 1.0f; no = ior; }
+    else if (side < 0) { n = -sampled_normal; ni = ior; no = 1.0f; }
+    else return false;
+
+    Ray nr = zero_ray();
+    if (from_camera) nr.c_importance = W.carry_imp; else nr.l_importance = W.carry_imp;
+    nr.origin = pad0(o + d * best_t);
+    nr.material = tri_material;
+    nr.triangle = best_i;
+    nr.hit_light = (tri_is_light && dot(d, tn) < 0.0f) ? best_i : -1;
+    nr.hit_camera = tri_is_camera ? best_i : -1;
+
+    V3 wi = -d;
+    float rand_x_a = xorshift_random(seed0);
+    float rand_y_a = xorshift_random(seed1);
+    float rand_x_b = xorshift_random(seed0);
+    float rand_y_b = xorshift_random(seed1);
+
+    V3 wo = v3(0, 0, 0);
+    float f = 1.0f, c_p = 1.0f, l_p = 1.0f;
+    V3 m = GGX_sample(n, rand_x_a, rand_y_a, alpha);
+    if (dot(wi, m) < 0.0f) return false;
+    if (dot(m, n) < 0.0f) return false;
+    nr.normal = pad0(n);
+
+    float fresnel = degreve_fresnel(wi, m, ni, no);
+    /* material dispatch of :474-487 resolved to one of three bounce kinds first, so that each bounce function is
+     * instantiated once (the walk kernel is larger than the instruction cache) */
+    int kind; /* 0 diffuse, 1 reflect, 2 transmit */
+    if (mat_type == 0) kind = 0;
+    else if (mat_type == 1) kind = (rand_x_b <= fresnel) ? 1 : 2;
+    else if (mat_type == 2) kind = (rand_x_b <= fresnel) ? 1 : 0;
+    else kind = 1;
+    if (kind == 0) diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
+    else if (kind == 1) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+    else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
+
+    float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
+    if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);
+    else nr.color = pad0(rc * f);
+    nr.direction = pad0(wo);
+    nr.inv_direction = pad0(rcp(wo));
+
+    float next_carry;
+    if (from_camera) {
+        next_carry = c_p;
+        nr.tot_importance = ray_tot * nr.c_importance;
+    } else {
+        next_carry = l_p;
+        nr.tot_importance = ray_tot * nr.l_importance;
+    }
+    if (f == 0.0f) return false;
+
+    /* path.rays[i] = ray with the reverse-direction pdf the bounce produced (:499-507, :512) */
+    sink.patch(i, from_camera, from_camera ? l_p : c_p);
+    cnt.vertex(1);
+    W.length = i + 1;
+    if (!W.uni_found && W.ray_hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
+        V3 c = W.last_stored_color / ray_tot;
+        W.uni = v4(c.x, c.y, c.z, 1.0f);
+        W.uni_found = true;
+    }
+    W.last_stored_color = rc;
+
+    /* the next vertex goes to its slot BEFORE its bounce is known to succeed (slot i + 1 only counts once length > i + 1;
+     * the one field that bounce still changes is patched then).  That ends the live range of the 32-word record here
+     * instead of across the traversal, which is what bounds the walk kernels' registers and therefore their occupancy. */
+    if (i + 1 < CLV_MAX_BOUNCES) sink.store(i + 1, nr);
+    W.o = xyz(nr.origin); W.d = wo; W.rc = xyz(nr.color);
+    W.ray_tot = nr.tot_importance;
+    W.ray_hit_light = nr.hit_light;
+    W.carry_imp = next_carry;
+    return true;
+}
+
 template <int MODE, bool COUNT, typename SINK>
 CLV_HD void random_walk(Ray ray, const AccelView &A, const Material *materials, uint32_t &seed0, uint32_t &seed1,
                         const SINK &sink, V4 *out_uni, Cnt<COUNT> &cnt) {
     const bool from_camera = ray.from_camera != 0;
-    float carry_imp = from_camera ? ray.c_importance : 1.0f / (2.0f * CLV_PI);
-    int length = 0;
-    V4 uni = v4(0, 0, 0, 0);
-    bool uni_found = false;
-    V3 last_stored_color = v3(0, 0, 0);
-
+    WalkRegs W;
+    walk_begin(ray, sink, W);
+    /* the first ray is traced with the inv_direction its record carries (a caller of the stage-level ABI may pass any),
+     * later ones with rcp(direction), which is what the bounce stores into the record (trace.metal:497) */
+    const V3 inv0 = xyz(ray.inv_direction);
     for (int i = 0; i < CLV_MAX_BOUNCES; i++) {
-        /* The vertex goes to its slot BEFORE the bounce is known to succeed (slot i only counts once length > i; the
-         * one field the bounce still changes is patched below).  That ends the live range of the 32-word record here
-         * instead of across the traversal, which is what bounds this kernel's registers and therefore its occupancy. */
-        sink.store(i, ray);
-        const V3 o = xyz(ray.origin), d = xyz(ray.direction), inv = xyz(ray.inv_direction), rc = xyz(ray.color);
-        const float ray_tot = ray.tot_importance;
-        const int ray_hit_light = ray.hit_light;
         int best_i = -1;
         float best_t = CLV_INF, u = 0.0f, v = 0.0f;
         cnt.ray_ref();
-        closest_hit<MODE, COUNT>(A, o, d, inv, best_i, best_t, u, v, cnt, -CLV_INF, -1);
-        if (best_i == -1) break;
-
-        const Triangle *tri = A.ref_triangles + best_i;
-        V3 tn = xyz(ld4(&tri->normal));
-        V3 n0 = xyz(ld4(&tri->n0)), n1 = xyz(ld4(&tri->n1)), n2 = xyz(ld4(&tri->n2));
-        int tri_material = tri->material, tri_is_light = tri->is_light, tri_is_camera = tri->is_camera;
-        const Material *mat = materials + tri_material;
-        V3 mat_color = xyz(ld4(&mat->color));
-        int mat_type = mat->type;
-        float alpha = mat->alpha, ior = mat->ior;
-
-        V3 n;
-        float ni, no;
-        V3 sampled_normal = normalize((n0 * (1 - u - v) + n1 * u) + n2 * v);
-        float side = dot(-d, tn);
-        if (side > 0) { n = sampled_normal; ni = 1.0f; no = ior; }
-        else if (side < 0) { n = -sampled_normal; ni = ior; no = 1.0f; }
-        else break;
-
-        Ray nr = zero_ray();
-        if (from_camera) nr.c_importance = carry_imp; else nr.l_importance = carry_imp;
-        nr.origin = pad0(o + d * best_t);
-        nr.material = tri_material;
-        nr.triangle = best_i;
-        nr.hit_light = (tri_is_light && dot(d, tn) < 0.0f) ? best_i : -1;
-        nr.hit_camera = tri_is_camera ? best_i : -1;
-
-        V3 wi = -d;
-        float rand_x_a = xorshift_random(seed0);
-        float rand_y_a = xorshift_random(seed1);
-        float rand_x_b = xorshift_random(seed0);
-        float rand_y_b = xorshift_random(seed1);
-
-        V3 wo = v3(0, 0, 0);
-        float f = 1.0f, c_p = 1.0f, l_p = 1.0f;
-        V3 m = GGX_sample(n, rand_x_a, rand_y_a, alpha);
-        if (dot(wi, m) < 0.0f) break;
-        if (dot(m, n) < 0.0f) break;
-        nr.normal = pad0(n);
-
-        float fresnel = degreve_fresnel(wi, m, ni, no);
-        /* material dispatch of :474-487 resolved to one of three bounce kinds first, so that each bounce function is
-         * instantiated once (the walk kernel is larger than the instruction cache) */
-        int kind; /* 0 diffuse, 1 reflect, 2 transmit */
-        if (mat_type == 0) kind = 0;
-        else if (mat_type == 1) kind = (rand_x_b <= fresnel) ? 1 : 2;
-        else if (mat_type == 2) kind = (rand_x_b <= fresnel) ? 1 : 0;
-        else kind = 1;
-        if (kind == 0) diffuse_bounce(wi, n, from_camera, rand_x_b, rand_y_b, wo, f, c_p, l_p);
-        else if (kind == 1) reflect_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-        else transmit_bounce(wi, n, m, ni, no, alpha, from_camera, wo, f, c_p, l_p);
-
-        float wi_n = dot(wi, tn), wo_n = dot(wo, tn);
-        if ((wi_n > 0.0f && wo_n > 0.0f) || (wi_n < 0.0f && wo_n > 0.0f)) nr.color = pad0((rc * f) * mat_color);
-        else nr.color = pad0(rc * f);
-        nr.direction = pad0(wo);
-        nr.inv_direction = pad0(rcp(wo));
-
-        float next_carry;
-        if (from_camera) {
-            next_carry = c_p;
-            nr.tot_importance = ray_tot * nr.c_importance;
-        } else {
-            next_carry = l_p;
-            nr.tot_importance = ray_tot * nr.l_importance;
-        }
-        if (f == 0.0f) break;
-
-        /* path.rays[i] = ray with the reverse-direction pdf the bounce produced (:499-507, :512) */
-        sink.patch(i, from_camera, from_camera ? l_p : c_p);
-        cnt.vertex(1);
-        length = i + 1;
-        if (!uni_found && ray_hit_light >= 0) { /* trace.metal:523-528 (i >= 1 here: generated rays have -1) */
-            V3 c = last_stored_color / ray_tot;
-            uni = v4(c.x, c.y, c.z, 1.0f);
-            uni_found = true;
-        }
-        last_stored_color = rc;
-
-        ray = nr;
-        carry_imp = next_carry;
+        closest_hit<MODE, COUNT>(A, W.o, W.d, i == 0 ? inv0 : rcp(W.d), best_i, best_t, u, v, cnt, -CLV_INF, -1);
+        if (!walk_bounce<COUNT>(W, i, from_camera, best_i, best_t, u, v, A, materials, seed0, seed1, sink, cnt)) break;
     }
-    sink.finish(length, from_camera);
-    *out_uni = uni;
+    sink.finish(W.length, from_camera);
+    *out_uni = W.uni;
 }
 CLV_HDM void AosSink::finish(int length, bool from_camera) const {
     if (length == 0) path->rays[0] = zero_ray();
@@ -1385,7 +1515,7 @@ CLV_HD void connect_sample(const PV &P, uint32_t entry_id, uint32_t agg_slot, co
 #endif
         m &= m - 1;
         OccRay ray;
-        int stack[CLV_STACK];
+        int stack[CLV_OCC_STACK];
         int st = connect_ray_begin<MODE, COUNT>(q, P, Sens, A, c, ray, cnt);
         while (st == OCC_RUNNING) st = occ_round<COUNT>(A, ray, stack, cnt);
         if (st == OCC_CLEAR) visible |= 1ull << q;
@@ -1467,6 +1597,113 @@ CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light
     a->uni[1] += nan_to_num0(uni.y);
     a->uni[2] += nan_to_num0(uni.z);
     a->count += 1.0f;
+}
+
+/* ---- wavefront form of stages 1-4 (k_walk_init / k_walk_trace / k_walk_shade) ------------------------------------------ *
+ * A sample runs its light walk, then its camera walk (the camera walk's RNG state is where the light walk left it, so the
+ * two cannot overlap).  Its walk state lives in global memory between kernels, 16-byte parts, part-major over the samples:
+ *   s0: origin.xyz, tot_importance of the vertex the ray leaves     s1: direction.xyz, carried importance
+ *   s2: colour.xyz, flags (bit 0 camera walk, bits 1-3 bounce index, bit 4 unidirectional estimate found)
+ *   s3: last stored colour.xyz, hit_light of the current vertex (camera walk only: feeds the unidirectional estimate)
+ *   hit: closest hit of the current ray (triangle, t, u, v)         jitter: the two sensor-jitter draws of the camera ray
+ * k_walk_trace reads s0/s1 (32 B per ray) and writes hit (16 B); k_walk_shade reads and writes everything else.
+ * Round r of a pass traces ray number r of every sample that still has one (at most 12: 6 bounces per walk). */
+struct WalkState {
+    V4 *s0, *s1, *s2, *s3, *hit;
+    float *jitter; /* [n][2] */
+};
+enum { WS_CAMERA = 1, WS_BOUNCE_SHIFT = 1, WS_UNI_FOUND = 16 };
+#define CLV_WALK_ROUNDS (2 * CLV_MAX_BOUNCES)
+
+template <bool SOA> struct SinkOf;
+template <> struct SinkOf<true> {
+    typedef SoaSink type;
+    static CLV_HDM SoaSink make(const PathStore &st, uint32_t slot, int which) {
+        SoaSink k;
+        k.v = st.soa; k.len = st.soa_len; k.n = st.n; k.slot = slot; k.sub = which;
+        return k;
+    }
+};
+template <> struct SinkOf<false> {
+    typedef AosSink type;
+    static CLV_HDM AosSink make(const PathStore &st, uint32_t slot, int which) {
+        AosSink k;
+        k.path = (which ? st.camera_paths : st.light_paths) + slot;
+        return k;
+    }
+};
+
+CLV_HD void walk_state_save(const WalkState &ws, uint32_t slot, const WalkRegs &W, int which, int bounce) {
+    ws.s0[slot] = v4(W.o.x, W.o.y, W.o.z, W.ray_tot);
+    ws.s1[slot] = v4(W.d.x, W.d.y, W.d.z, W.carry_imp);
+    ws.s2[slot] = v4(W.rc.x, W.rc.y, W.rc.z, i2f(which | (bounce << WS_BOUNCE_SHIFT) | (W.uni_found ? WS_UNI_FOUND : 0)));
+    if (which) ws.s3[slot] = v4(W.last_stored_color.x, W.last_stored_color.y, W.last_stored_color.z, i2f(W.ray_hit_light));
+}
+
+/* start of a sample's pass: both generators in the reference's order (light rays, then camera rays: renderer.py:281-282),
+ * light walk ready for its first ray */
+template <bool SOA>
+CLV_HD void wavefront_init_sample(uint32_t slot, const Triangle *light_triangles, const float *surface_areas,
+                                  const int32_t *light_triangle_indices, int light_count, const Material *materials,
+                                  uint32_t &seed0, uint32_t &seed1, const PathStore &store, const WalkState &ws) {
+    Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
+    ws.jitter[2 * (size_t)slot] = xorshift_random(seed0); /* make_camera_ray's two draws */
+    ws.jitter[2 * (size_t)slot + 1] = xorshift_random(seed1);
+    WalkRegs W;
+    walk_begin(lray, SinkOf<SOA>::make(store, slot, SUB_LIGHT), W);
+    walk_state_save(ws, slot, W, SUB_LIGHT, 0);
+}
+
+/* one bounce of a sample given the hit of its current ray; returns true while the sample has another ray to trace */
+template <bool COUNT, bool SOA>
+CLV_HD bool wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *materials, const Camera &c, const AccelView &A,
+                                   uint32_t &seed0, uint32_t &seed1, const PathStore &store, const WalkState &ws, Accum *accum,
+                                   Cnt<COUNT> &cnt) {
+    const V4 a0 = ws.s0[slot], a1 = ws.s1[slot], a2 = ws.s2[slot], h = ws.hit[slot];
+    const int flags = f2i(a2.w);
+    const int which = flags & WS_CAMERA, bounce = (flags >> WS_BOUNCE_SHIFT) & 7;
+    WalkRegs W;
+    W.o = xyz(a0); W.ray_tot = a0.w;
+    W.d = xyz(a1); W.carry_imp = a1.w;
+    W.rc = xyz(a2);
+    W.uni_found = (flags & WS_UNI_FOUND) != 0;
+    W.uni = v4(0, 0, 0, 0);
+    W.length = bounce; /* every earlier bounce of this walk succeeded */
+    W.last_stored_color = v3(0, 0, 0);
+    W.ray_hit_light = -1;
+    if (which) {
+        const V4 a3 = ws.s3[slot];
+        W.last_stored_color = xyz(a3);
+        W.ray_hit_light = f2i(a3.w);
+    }
+    const bool had_uni = W.uni_found;
+    bool more;
+    {
+        typename SinkOf<SOA>::type sink = SinkOf<SOA>::make(store, slot, which);
+        more = walk_bounce<COUNT>(W, bounce, which != 0, f2i(h.x), h.y, h.z, h.w, A, materials, seed0, seed1, sink, cnt);
+        more = more && bounce + 1 < CLV_MAX_BOUNCES;
+        if (!more) sink.finish(W.length, which != 0);
+    }
+    if (which && W.uni_found && !had_uni) {
+        /* renderer.py:273-278: the estimate is added to this pixel's accumulator the moment it is known; a pass that
+         * finds none adds 0, which leaves the sum's bits unchanged */
+        Accum *a = accum + gid;
+        a->uni[0] += nan_to_num0(W.uni.x);
+        a->uni[1] += nan_to_num0(W.uni.y);
+        a->uni[2] += nan_to_num0(W.uni.z);
+    }
+    if (more) {
+        walk_state_save(ws, slot, W, which, bounce + 1);
+        return true;
+    }
+    if (!which) { /* light walk over: the camera walk starts with the RNG state the light walk leaves */
+        Ray cray = camera_ray_from_jitter(c, (int)gid, ws.jitter[2 * (size_t)slot], ws.jitter[2 * (size_t)slot + 1]);
+        walk_begin(cray, SinkOf<SOA>::make(store, slot, SUB_CAMERA), W);
+        walk_state_save(ws, slot, W, SUB_CAMERA, 0);
+        return true;
+    }
+    accum[gid].count += 1.0f;
+    return false;
 }
 
 /* stages 6-8 for one pixel: adaptive_finalize_samples with identity bins, the light image the connect kernel

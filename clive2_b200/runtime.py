@@ -23,6 +23,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "li
 _lib = None
 
 TRAVERSE_REFERENCE_ORDER, TRAVERSE_ORDERED = 0, 1
+WALK_AUTO, WALK_MEGAKERNEL, WALK_WAVEFRONT = 0, 1, 2  # clv_ctx_walk_mode
 BUF_SUMMED_IMAGE, BUF_SUMMED_SAMPLE_COUNTS, BUF_SUMMED_SAMPLE_WEIGHTS, BUF_UNIDIRECTIONAL = 0, 1, 2, 3
 BUF_SEEDS, BUF_ACCUM_PACKED, BUF_LIGHT_PATHS, BUF_CAMERA_PATHS, BUF_AGGREGATORS, BUF_PASS_WEIGHT = 4, 5, 6, 7, 8, 9
 
@@ -81,6 +82,8 @@ SIGNATURES = {
     "clv_counters_read": [_vp, C.POINTER(C.c_uint64), _int],
     "clv_launch_count": [_vp, C.POINTER(C.c_uint64)],
     "clv_ctx_pass_slices": [_vp, _int, C.POINTER(C.c_int)],
+    "clv_ctx_walk_mode": [_vp, _int, C.POINTER(C.c_int)],
+    "clv_ctx_set_knob": [_vp, C.c_char_p, _int, C.POINTER(C.c_int)],
     "clv_measure_read_bandwidth": [_vp, _sz, _int, C.POINTER(C.c_double)],
     "clv_renderer_kernel_timing": [_vp, _int],
     "clv_renderer_kernel_times": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), _int],
@@ -459,6 +462,23 @@ class Device:
         return int(n.value)
 
     @property
+    def walk_mode(self):
+        """Stages 1-4 of the fused pass: 0 automatic, 1 megakernel, 2 wavefront rounds (clv_ctx_walk_mode)."""
+        out = C.c_int()
+        _check(self.lib.clv_ctx_walk_mode(self.ctx, -1, C.byref(out)))
+        return int(out.value)
+
+    @walk_mode.setter
+    def walk_mode(self, mode):
+        _check(self.lib.clv_ctx_walk_mode(self.ctx, int(mode), None))
+
+    def knob(self, name, value=-1):
+        """Set (value >= 0) or query a scheduling knob of the ray kernels (clv_ctx_set_knob); returns the previous value."""
+        prev = C.c_int()
+        _check(self.lib.clv_ctx_set_knob(self.ctx, name.encode(), int(value), C.byref(prev)))
+        return int(prev.value)
+
+    @property
     def pass_slices(self):
         """Number of independent sample slices (streams) a fused pass is launched as (4 * slices + 1 kernels per
         pass); 0 = automatic (3 from one full wave of samples up, else 1)."""
@@ -642,6 +662,8 @@ class FusedRenderer:
     """Thin owner of a `clv_renderer`: one call per sample pass, accumulators resident on the device."""
     #: kernels of one pass, in launch order
     KERNELS = ("k_fused_walks", "k_connect_enumerate", "k_connect_rays", "k_connect_finish", "k_fused_finalize")
+    #: slots of clv_renderer_kernel_times (the walks are either the megakernel or the two wavefront kernels)
+    TIMED = KERNELS + ("k_walk_trace", "k_walk_shade")
 
     def __init__(self, device, accel, arrays, seeds, sample_ids=None):
         self.device, self.accel = device, accel
@@ -697,9 +719,9 @@ class FusedRenderer:
 
     def kernel_times(self, reset=True):
         """(ms per kernel summed over the timed passes, number of passes)."""
-        ms, n = (C.c_double * 5)(), C.c_uint64()
+        ms, n = (C.c_double * 8)(), C.c_uint64()
         _check(self.device.lib.clv_renderer_kernel_times(self.handle, ms, C.byref(n), int(bool(reset))))
-        return dict(zip(self.KERNELS, ms)), int(n.value)
+        return {k: v for k, v in zip(self.TIMED, ms) if v > 0.0 or k in self.KERNELS[1:]}, int(n.value)
 
     def reset(self, seeds=None):
         s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32).reshape(self.n_pixels, 2)

@@ -257,11 +257,25 @@ CLV_API int clv_renderer_set_path_records(clv_renderer *r, int enabled);
  * 64-byte node records fetched, 48-byte triangle records fetched, 128-byte path vertices written / staged */
 CLV_API int clv_counters_enable(clv_ctx *ctx, int enabled);
 CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
-/* per-kernel device time of the fused pass: CUDA events recorded on the launch stream around each of its five
- * kernels (walks, connect-enumerate, connect-rays, connect-finish, finalize) while enabled; `kernel_times` waits,
- * returns the accumulated milliseconds and the number of passes they cover */
+/* per-kernel device time of the fused pass: CUDA events recorded on the launch stream after every launch while
+ * enabled (the pass then runs as one slice on one stream); `kernel_times` waits and returns the milliseconds accumulated
+ * per kernel — slots: 0 k_fused_walks (megakernel walks), 1 k_connect_enumerate, 2 k_connect_rays, 3 k_connect_finish,
+ * 4 k_fused_finalize, 5 k_walk_trace (all rounds), 6 k_walk_init + k_walk_shade (all rounds), 7 unused — and the number of
+ * passes they cover */
+#define CLV_TIMED_KERNEL_SLOTS 8
 CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
-CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[5], uint64_t *passes_out, int reset);
+CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_KERNEL_SLOTS], uint64_t *passes_out, int reset);
+/* Stages 1-4 of the fused pass (ray generation + both random walks; renderer.py:281-285) run either as ONE megakernel,
+ * a thread per sample (k_fused_walks), or as wavefront rounds: k_walk_init, then 12 x (k_walk_trace: persistent warps
+ * that fetch rays from the round's queue as their lanes finish; k_walk_shade: the bounce of every traced ray).  Same
+ * results, bit for bit.  mode 0 = automatic (wavefront for scenes whose traversal records exceed the caches; env
+ * CLV_WALK_MODE), 1 = megakernel, 2 = wavefront; < 0 only queries. */
+CLV_API int clv_ctx_walk_mode(clv_ctx *ctx, int mode, int *current_out);
+/* Scheduling knobs of the two ray kernels, for measurement sweeps (none changes a result): "walk_refill_below" /
+ * "connect_refill_below" = lanes still holding a ray below which a warp of k_walk_trace / k_connect_rays fetches new
+ * rays (1..32); "walk_schedule" / "connect_schedule" = vote weight w, an inner-node step wins when
+ * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form).  value < 0 only queries. */
+CLV_API int clv_ctx_set_knob(clv_ctx *ctx, const char *name, int value, int *previous);
 /* streaming-read bandwidth (GB/s) of a scratch buffer of nbytes read iters times: the L2 read peak for nbytes well
  * below the 126 MB L2 (the bound of the cache-resident configurations), the HBM read peak for nbytes >> L2 */
 CLV_API int clv_measure_read_bandwidth(clv_ctx *ctx, size_t nbytes, int iters, double *gbs_out);

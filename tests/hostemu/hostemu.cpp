@@ -5,6 +5,7 @@
  * libclive_b200.so.  The `-m gpu` tests repeat the same comparisons on the real kernels.
  * Build: tests/hostemu/__init__.py (g++ -O2 -fopenmp -ffp-contract=off: same arithmetic contract as -fmad=false).
  */
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -204,16 +205,66 @@ EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAc
 /* one fused pass exactly as clv_renderer_run_sample launches it: walks -> connect (splat) -> finalize+accumulate.
  * soa != NULL selects the renderer's compact SoA vertex records (soa: V4[2*6*4*n_local], soa_len: int32[2*n_local]),
  * otherwise the reference's Path records are used. */
+/* stages 1-4 the way k_walk_init / k_walk_trace / k_walk_shade run them: rounds over a queue of live samples, each ray
+ * traced with the resumable single-step search (hit_begin / hit_inner_step / hit_leaf_step), each hit shaded by
+ * wavefront_shade_sample, survivors appended to the next round's queue */
+template <bool SOA>
+static void wavefront_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
+                            const int32_t *lti, int light_count, const Material *mats, const Camera *cam, const EmuAccel *a,
+                            uint32_t *seeds, PathStore store, Accum *accum, Cnt<true> &cnt) {
+    std::vector<V4> state((size_t)n_local * 5);
+    std::vector<float> jitter((size_t)n_local * 2);
+    WalkState ws;
+    ws.s0 = state.data(); ws.s1 = ws.s0 + n_local; ws.s2 = ws.s1 + n_local; ws.s3 = ws.s2 + n_local; ws.hit = ws.s3 + n_local;
+    ws.jitter = jitter.data();
+    std::vector<uint32_t> queue(n_local), next;
+    for (uint32_t id = 0; id < n_local; id++) {
+        uint32_t s0 = seeds[2 * (size_t)id], s1 = seeds[2 * (size_t)id + 1];
+        wavefront_init_sample<SOA>(id, lt, areas, lti, light_count, mats, s0, s1, store, ws);
+        seeds[2 * (size_t)id] = s0; seeds[2 * (size_t)id + 1] = s1;
+        queue[id] = id;
+    }
+    for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
+        /* a later round's queue is in whatever order the warps of the previous one appended to it: reverse it here so that
+         * a dependence on the order would show */
+        if (round & 1) std::reverse(queue.begin(), queue.end());
+        for (uint32_t slot : queue) { /* k_walk_trace */
+            HitRay ray;
+            StackEntry st[CLV_STACK];
+            ray.o = xyz(ws.s0[slot]); ray.d = xyz(ws.s1[slot]); ray.inv = rcp(ray.d);
+            cnt.ray_ref();
+            int status = hit_begin<true>(a->view, ray, cnt);
+            while (status == HIT_RUNNING)
+                status = ray.cur >= 0 ? hit_inner_step<true>(a->view, ray, st, cnt) : hit_leaf_step<true>(a->view, ray, st, cnt);
+            ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
+        }
+        next.clear();
+        for (uint32_t slot : queue) { /* k_walk_shade */
+            uint32_t gid = sample_ids ? sample_ids[slot] : slot;
+            uint32_t s0 = seeds[2 * (size_t)slot], s1 = seeds[2 * (size_t)slot + 1];
+            if (wavefront_shade_sample<true, SOA>(slot, gid, mats, cam[0], a->view, s0, s1, store, ws, accum, cnt)) next.push_back(slot);
+            seeds[2 * (size_t)slot] = s0; seeds[2 * (size_t)slot + 1] = s1;
+        }
+        queue.swap(next);
+    }
+}
+
 template <int MODE, bool SOA>
 static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
                        const int32_t *lti, int light_count, const Material *mats, const Camera *cam, const EmuAccel *a,
-                       uint32_t *seeds, PathStore store, WeightAggregator *aggs, V4 *light_image, Accum *accum) {
+                       uint32_t *seeds, PathStore store, WeightAggregator *aggs, V4 *light_image, Accum *accum, int wavefront) {
     uint32_t n_pixels = (uint32_t)(cam[0].pixel_width * cam[0].pixel_height);
+    if (wavefront) {
+        Cnt<true> cnt;
+        wavefront_walks<SOA>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, accum, cnt);
+        merge(cnt);
+    }
 #pragma omp parallel
     {
         Cnt<true> cnt;
 #pragma omp for schedule(dynamic, 64)
         for (int64_t id = 0; id < (int64_t)n_local; id++) {
+            if (wavefront) continue;
             uint32_t gid = sample_ids ? sample_ids[id] : (uint32_t)id;
             uint32_t s0 = seeds[2 * id], s1 = seeds[2 * id + 1];
             fused_walk_sample<MODE, true, SOA>((uint32_t)id, gid, lt, areas, lti, light_count, mats, cam[0], a->view, s0, s1,
@@ -247,12 +298,13 @@ static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Trian
 EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
                            const int32_t *lti, int light_count, const Material *mats, const Camera *cam,
                            const EmuAccel *a, uint32_t *seeds, Path *light_paths, Path *camera_paths,
-                           WeightAggregator *aggs, V4 *light_image, Accum *accum, int mode, V4 *soa, int32_t *soa_len) {
+                           WeightAggregator *aggs, V4 *light_image, Accum *accum, int mode, V4 *soa, int32_t *soa_len,
+                           int wavefront) {
     PathStore store;
     memset(&store, 0, sizeof store);
     store.light_paths = light_paths; store.camera_paths = camera_paths; store.soa = soa; store.soa_len = soa_len;
     store.n = n_local;
-#define GO(M, SO) fused_pass<M, SO>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, aggs, light_image, accum)
+#define GO(M, SO) fused_pass<M, SO>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, aggs, light_image, accum, wavefront && M == TRAVERSE_ORDERED)
     if (soa) { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, true); else GO(TRAVERSE_ORDERED, true); }
     else { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, false); else GO(TRAVERSE_ORDERED, false); }
 #undef GO

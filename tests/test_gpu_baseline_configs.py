@@ -92,6 +92,40 @@ def test_c4_terrain_10m_160x90_vs_checker(dev):
     compare_with_checker(dev, a, passes=2, seed=11)
 
 
+@pytest.mark.parametrize("preset,w,h,passes", [("empty", 256, 256, 4), ("bench-spheres", 512, 512, 3)])
+def test_wavefront_walks_at_bench_size_vs_checker_and_megakernel(dev, preset, w, h, passes):
+    """Stages 1-4 as wavefront rounds (k_walk_init / k_walk_trace / k_walk_shade), forced on the cache-resident
+    configurations where the automatic mode keeps the megakernel: same bits as the checker and as the megakernel."""
+    a = arrays(preset, w, h)
+    b = w * h
+    before = dev.walk_mode
+    try:
+        dev.walk_mode = runtime.WALK_WAVEFRONT
+        n0 = dev.launch_count
+        compare_with_checker(dev, a, passes=passes, seed=77)
+        assert dev.launch_count - n0 > passes * 25  # init + 12 x (trace, shade) + connection + finalize per slice
+        outs = []
+        for mode in (runtime.WALK_MEGAKERNEL, runtime.WALK_WAVEFRONT):
+            dev.walk_mode = mode
+            sc = scene.scene_from_arrays(a, dev)
+            r = Renderer(sc, seeds=seeds_for(b, seed=78), path_records=True)
+            for _ in range(2):
+                r.run_sample()
+            outs.append(dict(seeds=r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * b), cam=r._fr.read(runtime.BUF_CAMERA_PATHS, T.Path, b),
+                             lig=r._fr.read(runtime.BUF_LIGHT_PATHS, T.Path, b),
+                             aggs=r._fr.read(runtime.BUF_AGGREGATORS, T.WeightAggregator, b), acc=r._accum().copy()))
+            r.release()
+            sc.release()
+    finally:
+        dev.walk_mode = before
+    mega, wave = outs
+    assert np.array_equal(mega["seeds"], wave["seeds"])
+    assert_paths_equal(mega["cam"], wave["cam"], "camera Path records, megakernel vs wavefront")
+    assert_paths_equal(mega["lig"], wave["lig"], "light Path records, megakernel vs wavefront")
+    assert_bits_equal(mega["aggs"], wave["aggs"], "aggregators", nan_equal=True)
+    assert np.array_equal(mega["acc"][..., 4:8].view(np.uint32), wave["acc"][..., 4:8].view(np.uint32))
+
+
 def both_orders(dev, a, passes, seed):
     w, h = a.pixel_width, a.pixel_height
     b = w * h

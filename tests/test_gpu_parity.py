@@ -315,6 +315,7 @@ def test_full_size_properties(dev):
     dev.synchronize()
     # walks + three connection kernels per slice of the samples, one finalize kernel per pass
     per_pass, rem = divmod(dev.launch_count - n0, 4)
+    assert dev.walk_mode == runtime.WALK_AUTO  # cache-resident scene: the megakernel walks
     assert rem == 0 and (per_pass - 1) % (len(runtime.FusedRenderer.KERNELS) - 1) == 0 and 5 <= per_pass <= 33
     assert (r.summed_sample_counts == 4).all()
     img = r.summed_image

@@ -445,7 +445,7 @@ def test_light_counts_bit_exact(O, E, n_extra):
     assert len(np.unique(R.light_rays["triangle"])) == int(a.light_counts)  # every light gets picked
 
 
-def _fused_vs_oracle_renderer(E, a, seeds, passes=3):
+def _fused_vs_oracle_renderer(E, a, seeds, passes=3, wavefront=False):
     b = a.pixel_width * a.pixel_height
     ref = OracleRenderer(a, seeds, shared_math=True)
     s = seeds.copy()
@@ -458,7 +458,7 @@ def _fused_vs_oracle_renderer(E, a, seeds, passes=3):
     try:
         for _ in range(passes):
             ref.run_sample()
-            E.fused_pass(a, acc, s, None, None, aggs, light_image, accum, soa=soa, soa_len=soa_len)
+            E.fused_pass(a, acc, s, None, None, aggs, light_image, accum, soa=soa, soa_len=soa_len, wavefront=wavefront)
     finally:
         E.accel_destroy(acc)
     assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), s, "RNG state")
@@ -471,18 +471,69 @@ def _fused_vs_oracle_renderer(E, a, seeds, passes=3):
         np.testing.assert_allclose(accum[:, 0:3], ref.summed_image.reshape(b, 3), rtol=5e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("wavefront", [False, True], ids=["megakernel", "wavefront"])
 @pytest.mark.parametrize("which", range(len(AWKWARD_CAMERAS)))
-def test_fused_pass_awkward_cameras(E, which):
+def test_fused_pass_awkward_cameras(E, which, wavefront):
     """The fused pass (atomic splats instead of sort + bins + gather) where light-image entries fall beyond the last
     pixel or do not exist at all: dropped / absent exactly as in the reference's gather."""
     w, h = 32, 24
-    _fused_vs_oracle_renderer(E, awkward_camera_arrays(which, w, h), seeds_for(w * h, seed=5))
+    _fused_vs_oracle_renderer(E, awkward_camera_arrays(which, w, h), seeds_for(w * h, seed=5), wavefront=wavefront)
 
 
+@pytest.mark.parametrize("wavefront", [False, True], ids=["megakernel", "wavefront"])
 @pytest.mark.parametrize("n_extra", [0, 9])
-def test_fused_pass_light_counts(E, n_extra):
+def test_fused_pass_light_counts(E, n_extra, wavefront):
     w, h = 32, 24
-    _fused_vs_oracle_renderer(E, many_lights_arrays(n_extra, w, h), seeds_for(w * h, seed=6))
+    _fused_vs_oracle_renderer(E, many_lights_arrays(n_extra, w, h), seeds_for(w * h, seed=6), wavefront=wavefront)
+
+
+@pytest.mark.parametrize("preset,w,h", [("empty", 40, 40), ("bench-spheres", 48, 36)])
+def test_wavefront_walks_vs_oracle_renderer(E, preset, w, h):
+    """Stages 1-4 as wavefront rounds (the logic of k_walk_init / k_walk_trace / k_walk_shade: resumable single-step
+    closest-hit search, per-bounce walk state in memory, live-sample queues) against the oracle renderer."""
+    _fused_vs_oracle_renderer(E, arrays(preset, w, h), seeds_for(w * h, seed=12), passes=3, wavefront=True)
+
+
+@pytest.mark.parametrize("use_soa", [False, True], ids=["path_records", "soa_records"])
+def test_wavefront_walks_write_the_same_records_as_the_megakernel(E, use_soa):
+    """Same Path records / SoA vertex records, lengths, RNG state, aggregators and accumulators from both drivers of the
+    walk (GGX + transmission scene, 3 passes), byte for byte where a record is defined."""
+    w, h = 40, 30
+    a = arrays("bench-spheres", w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=21)
+    acc = E.accel(a.boxes, a.triangles)
+    outs = []
+    try:
+        for wavefront in (False, True):
+            s = seeds.copy()
+            lp, cp = np.zeros(b, T.Path), np.zeros(b, T.Path)
+            aggs = np.zeros(b, T.WeightAggregator)
+            li = np.zeros((b, 4), np.float32)
+            accum = np.zeros((b, 8), np.float32)
+            soa = np.zeros((2 * 6 * 4 * b, 4), np.float32) if use_soa else None
+            soa_len = np.zeros(2 * b, np.int32) if use_soa else None
+            for _ in range(3):
+                E.fused_pass(a, acc, s, lp, cp, aggs, li, accum, soa=soa, soa_len=soa_len, wavefront=wavefront)
+            outs.append((s, aggs, accum, lp, cp, soa, soa_len))
+    finally:
+        E.accel_destroy(acc)
+    m, wv = outs
+    assert_bits_equal(m[0], wv[0], "RNG state")
+    assert_bits_equal(m[1], wv[1], "aggregators")
+    assert_bits_equal(m[2][:, 4:8].copy(), wv[2][:, 4:8].copy(), "unidirectional + counts")
+    np.testing.assert_allclose(wv[2][:, 0:4], m[2][:, 0:4], rtol=2e-4, atol=1e-6)
+    if use_soa:
+        assert np.array_equal(m[6], wv[6])
+        # a vertex slot is defined while its index < length (+ slot 0 of an empty path); compare those
+        parts = m[5].reshape(2, 6, 4, b, 4), wv[5].reshape(2, 6, 4, b, 4)
+        for sub in range(2):
+            for k in range(6):
+                live = (m[6][sub * b:(sub + 1) * b] > k) | ((k == 0) & (m[6][sub * b:(sub + 1) * b] == 0))
+                assert np.array_equal(parts[0][sub, k][:, live].view(np.uint32), parts[1][sub, k][:, live].view(np.uint32)), (sub, k)
+    else:
+        assert_paths_equal(m[3], wv[3], "light paths")
+        assert_paths_equal(m[4], wv[4], "camera paths")
 
 
 def test_random_number_exactly_one(O, E):
