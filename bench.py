@@ -132,6 +132,23 @@ class ClockSampler:
 # scenes
 # ---------------------------------------------------------------------------------------------------------------------
 def build_arrays(cfg, width=None, height=None, via_file=True, bvh_builder="auto"):
+    """`_build_arrays`, optionally memoised on /dev/shm across processes (CLV_SCENE_CACHE=1: measurement sweeps that start
+    one process per build variant; never set by the driver's runs)."""
+    if os.environ.get("CLV_SCENE_CACHE") != "1" or not os.path.isdir("/dev/shm"):
+        return _build_arrays(cfg, width, height, via_file, bvh_builder)
+    from clive2_b200.scene import SceneArrays
+    w, h = width or cfg["width"], height or cfg["height"]
+    base = f"/dev/shm/clv_scene_cache_{cfg['preset']}_{w}x{h}_{int(bool(via_file))}_"
+    if all(os.path.exists(base + f + ".npy") for f in ARRAY_FIELDS):
+        return SceneArrays(pixel_width=w, pixel_height=h, **{f: np.load(base + f + ".npy") for f in ARRAY_FIELDS})
+    a = _build_arrays(cfg, width, height, via_file, bvh_builder)
+    for f in ARRAY_FIELDS:
+        np.save(base + f + ".tmp.npy", getattr(a, f))
+        os.replace(base + f + ".tmp.npy", base + f + ".npy")
+    return a
+
+
+def _build_arrays(cfg, width=None, height=None, via_file=True, bvh_builder="auto"):
     """Scene arrays of a configuration.  C3 / C4 go through the file path BASELINE names (load.py:76-95 of the reference):
     the procedural mesh is written as OBJ / PLY and read back by the package's own readers (`via_file=False`: the
     in-memory mesh of the scene preset)."""

@@ -782,6 +782,13 @@ k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, con
 #ifndef CLV_TRACE_MIN_BLOCKS_LARGE
 #define CLV_TRACE_MIN_BLOCKS_LARGE (1280 / CLV_BLOCK) /* <= 48 registers per thread */
 #endif
+/* node layout the trace kernel walks: the binary nodes (0) or their 4-wide collapse (1), per flavour */
+#ifndef CLV_TRACE_WIDE
+#define CLV_TRACE_WIDE 0
+#endif
+#ifndef CLV_TRACE_WIDE_LARGE
+#define CLV_TRACE_WIDE_LARGE 0
+#endif
 template <bool COUNT, int LARGE>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_TRACE_MIN_BLOCKS_LARGE : CLV_TRACE_MIN_BLOCKS)
 k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *cursor,
@@ -789,9 +796,10 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
     const uint32_t count = queue ? *count_ptr : n_identity;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr bool WIDE = LARGE ? (CLV_TRACE_WIDE_LARGE != 0) : (CLV_TRACE_WIDE != 0);
     Cnt<COUNT> cnt;
     HitRay ray;
-    StackEntry st[CLV_STACK];
+    StackEntry st[CLV_HIT_STACK(WIDE)];
     bool have = false, exhausted = false; /* exhausted is warp-uniform */
     uint32_t slot = 0;
     for (;;) {
@@ -809,7 +817,7 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
                 const V4 a0 = ws.s0[slot], a1 = ws.s1[slot];
                 ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
                 cnt.ray_ref();
-                if (hit_begin<COUNT>(A, ray, cnt) == HIT_RUNNING) have = true;
+                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) have = true;
                 else ws.hit[slot] = v4(i2f(-1), CLV_INF, 0.0f, 0.0f);
             }
             if ((uint64_t)base + (uint64_t)n_idle >= (uint64_t)count) exhausted = true;
@@ -821,8 +829,9 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
         const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && !at_inner));
         int status = HIT_RUNNING;
-        if (n_inner * schedule >= n_leaf * 4) { if (at_inner) status = hit_inner_step<COUNT>(A, ray, st, cnt); }
-        else if (have && !at_inner) status = hit_leaf_step<COUNT>(A, ray, st, cnt);
+        if (n_inner * schedule >= n_leaf * 4) {
+            if (at_inner) status = WIDE ? hit_inner_step_wide<COUNT>(A, ray, st, cnt) : hit_inner_step<COUNT>(A, ray, st, cnt);
+        } else if (have && !at_inner) status = hit_leaf_step<COUNT>(A, ray, st, cnt);
         if (status == HIT_DONE) {
             have = false;
             ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
@@ -831,8 +840,11 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
     flush_counters<COUNT>(cnt, counters);
 }
 
+#ifndef CLV_SHADE_MIN_BLOCKS
+#define CLV_SHADE_MIN_BLOCKS 1 /* no register cap */
+#endif
 template <bool COUNT, bool SOA>
-__global__ void __launch_bounds__(CLV_BLOCK)
+__global__ void __launch_bounds__(CLV_BLOCK, CLV_SHADE_MIN_BLOCKS)
 k_walk_shade(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *queue_out,
              uint32_t *count_out, const uint32_t *sample_ids, const Material *materials, const Camera *camera, AccelView A,
              uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters) {

@@ -126,6 +126,48 @@ inline int32_t wide_of(HostAccel &H, int32_t bin_ref) {
     H.wide[me] = w;
     return (int32_t)me;
 }
+/* Order of the binary node records in memory.  0: the reference's breadth-first box order (bvh.py:329-389), synthetic
+ * leaf-chain nodes last — the two children of a node are neighbours, a node and its grandchildren are not.  1: depth-first
+ * pre-order, the subtree the reference visits LAST (left) directly behind its parent: a subtree is one contiguous range,
+ * so a search that descends stays inside ever smaller address ranges (sector / page / TLB locality).  Refs are renumbered;
+ * boxes, leaves and therefore every search result are unchanged. */
+#ifndef CLV_BINARY_NODE_ORDER
+#define CLV_BINARY_NODE_ORDER 0
+#endif
+inline void renumber_depth_first(HostAccel &H) {
+    if (H.root_ref < 0) return;
+    const size_t n = H.nodes.size();
+    std::vector<int32_t> new_index(n, -1);
+    std::vector<int32_t> stack;
+    stack.push_back(H.root_ref);
+    int32_t next = 0;
+    while (!stack.empty()) {
+        const int32_t ref = stack.back();
+        stack.pop_back();
+        new_index[ref] = next++;
+        int32_t l, r;
+        memcpy(&l, &H.nodes[ref].d.x, 4);
+        memcpy(&r, &H.nodes[ref].d.y, 4);
+        if (r >= 0) stack.push_back(r);
+        if (l >= 0) stack.push_back(l); /* popped first: the left subtree follows its parent */
+    }
+    std::vector<NodeRec> out((size_t)next);
+    for (size_t i = 0; i < n; i++) {
+        if (new_index[i] < 0) continue; /* unreachable (never the case for a well-formed tree) */
+        NodeRec rec = H.nodes[i];
+        int32_t kids[2];
+        memcpy(&kids[0], &rec.d.x, 4);
+        memcpy(&kids[1], &rec.d.y, 4);
+        for (int k = 0; k < 2; k++)
+            if (kids[k] >= 0) kids[k] = new_index[kids[k]];
+        memcpy(&rec.d.x, &kids[0], 4);
+        memcpy(&rec.d.y, &kids[1], 4);
+        out[new_index[i]] = rec;
+    }
+    H.root_ref = new_index[H.root_ref];
+    H.nodes.swap(out);
+}
+
 inline void build_wide(HostAccel &H) {
     H.wide.clear();
     H.wide_root_ref = wide_of(H, H.root_ref);
@@ -182,6 +224,9 @@ inline const char *build_host_accel(const Box *boxes, int32_t n_boxes, const Tri
             else for (int32_t i = bx.left; i < bx.right; i++) rank[i] = next++;
         }
     }
+#if CLV_BINARY_NODE_ORDER == 1
+    renumber_depth_first(H);
+#endif
     build_wide(H);
     H.binary_depth = tree_depth(H.root_ref, [&](int32_t ref, int32_t kids[4]) {
         memcpy(&kids[0], &H.nodes[ref].d.x, 4);

@@ -391,7 +391,9 @@ struct HitRay {
 };
 enum { HIT_RUNNING = 0, HIT_DONE = 1 };
 
-template <bool COUNT>
+/* stack entries a resumable search needs: one deferred sibling per binary level, three per 4-wide level */
+#define CLV_HIT_STACK(WIDE) ((WIDE) ? CLV_OCC_STACK : 32)
+template <bool COUNT, bool WIDE = false>
 CLV_HD int hit_begin(const AccelView &A, HitRay &r, Cnt<COUNT> &cnt) {
     cnt.ray_traced();
     r.best_i = -1; r.best_t = CLV_INF; r.bu = 0.0f; r.bv = 0.0f; r.best_rank = 0x7fffffff;
@@ -400,7 +402,7 @@ CLV_HD int hit_begin(const AccelView &A, HitRay &r, Cnt<COUNT> &cnt) {
     float te;
     slab_test(r.o, r.inv, xyz(A.root_min), xyz(A.root_max), hit, te);
     if (!(hit && te < r.best_t)) return HIT_DONE;
-    r.cur = A.root_ref;
+    r.cur = WIDE ? A.wroot_ref : A.root_ref;
     return HIT_RUNNING;
 }
 /* next deferred child that can still hold a closer (or tying) hit, or the end of the search */
@@ -426,6 +428,21 @@ CLV_HD int hit_inner_step(const AccelView &A, HitRay &r, StackEntry *st, Cnt<COU
     const bool left_first = tl < tr; /* tie: right first, the reference's order */
     if (go_l && go_r && r.sp < CLV_STACK) { st[r.sp] = stack_entry(left_first ? tr : tl, left_first ? rref : lref); r.sp++; }
     if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return HIT_RUNNING; }
+    return hit_pop(r, st);
+}
+/* the same step over the 4-wide collapse of the tree (clv_accel_build.h): up to four child boxes per record, continue with
+ * the nearest survivor, keep the others farthest first.  Half the dependent record fetches per ray of the binary form. */
+template <bool COUNT>
+CLV_HD int hit_inner_step_wide(const AccelView &A, HitRay &r, StackEntry *st, Cnt<COUNT> &cnt) {
+    float tk[4];
+    int rk[4];
+    wide_test(A.wnodes + 8 * (size_t)r.cur, r.o, r.inv, r.best_t, tk, rk);
+    cnt.node();
+    wide_sort(tk, rk);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (tk[k] < CLV_INF && r.sp < CLV_HIT_STACK(true)) { st[r.sp] = stack_entry(tk[k], rk[k]); r.sp++; }
+    if (tk[3] < CLV_INF) { r.cur = rk[3]; return HIT_RUNNING; }
     return hit_pop(r, st);
 }
 template <bool COUNT>

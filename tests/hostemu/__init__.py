@@ -22,8 +22,9 @@ def build(force=False):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    extra = os.environ.get("CLV_HOSTEMU_EXTRA", "").split()  # e.g. -DCLV_BINARY_NODE_ORDER=1: check a build option on the host
     subprocess.run([gxx, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
-                    "-fvisibility=hidden", "-shared", "-Wno-unknown-pragmas", "-o", LIB, SOURCES[0]], check=True)
+                    "-fvisibility=hidden", "-shared", "-Wno-unknown-pragmas"] + extra + ["-o", LIB, SOURCES[0]], check=True)
     return LIB
 
 
@@ -97,10 +98,10 @@ class HostEmu:
                    mode=MODE_ORDERED, soa=None, soa_len=None, wavefront=False):
         """One fused pass.  With `soa` (float32 (2*6*4*n_local, 4)) and `soa_len` (int32 (2*n_local,)) the renderer's compact
         SoA vertex records are used instead of the Path arrays.  `wavefront`: stages 1-4 as the rounds of k_walk_init /
-        k_walk_trace / k_walk_shade instead of the per-sample megakernel."""
+        k_walk_trace / k_walk_shade instead of the per-sample megakernel (2: the trace steps over the 4-wide nodes)."""
         n_local = len(seeds)
         self.lib.emu_fused_pass(C.c_uint32(n_local), _p(sample_ids), _p(arrays.light_triangles),
                                 _p(arrays.light_surface_areas), _p(arrays.light_triangle_indices),
                                 C.c_int(int(arrays.light_counts)), _p(arrays.materials), _p(arrays.camera), accel,
                                 _p(seeds), _p(light_paths), _p(camera_paths), _p(aggs), _p(light_image), _p(accum),
-                                C.c_int(mode), _p(soa), _p(soa_len), C.c_int(int(bool(wavefront))))
+                                C.c_int(mode), _p(soa), _p(soa_len), C.c_int(int(wavefront)))

@@ -211,7 +211,7 @@ EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAc
 template <bool SOA>
 static void wavefront_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
                             const int32_t *lti, int light_count, const Material *mats, const Camera *cam, const EmuAccel *a,
-                            uint32_t *seeds, PathStore store, Accum *accum, Cnt<true> &cnt) {
+                            uint32_t *seeds, PathStore store, Accum *accum, Cnt<true> &cnt, bool wide) {
     std::vector<V4> state((size_t)n_local * 5);
     std::vector<float> jitter((size_t)n_local * 2);
     WalkState ws;
@@ -230,12 +230,14 @@ static void wavefront_walks(uint32_t n_local, const uint32_t *sample_ids, const 
         if (round & 1) std::reverse(queue.begin(), queue.end());
         for (uint32_t slot : queue) { /* k_walk_trace */
             HitRay ray;
-            StackEntry st[CLV_STACK];
+            StackEntry st[CLV_HIT_STACK(true)];
             ray.o = xyz(ws.s0[slot]); ray.d = xyz(ws.s1[slot]); ray.inv = rcp(ray.d);
             cnt.ray_ref();
-            int status = hit_begin<true>(a->view, ray, cnt);
-            while (status == HIT_RUNNING)
-                status = ray.cur >= 0 ? hit_inner_step<true>(a->view, ray, st, cnt) : hit_leaf_step<true>(a->view, ray, st, cnt);
+            int status = wide ? hit_begin<true, true>(a->view, ray, cnt) : hit_begin<true, false>(a->view, ray, cnt);
+            while (status == HIT_RUNNING) {
+                if (ray.cur < 0) status = hit_leaf_step<true>(a->view, ray, st, cnt);
+                else status = wide ? hit_inner_step_wide<true>(a->view, ray, st, cnt) : hit_inner_step<true>(a->view, ray, st, cnt);
+            }
             ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
         }
         next.clear();
@@ -256,7 +258,7 @@ static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Trian
     uint32_t n_pixels = (uint32_t)(cam[0].pixel_width * cam[0].pixel_height);
     if (wavefront) {
         Cnt<true> cnt;
-        wavefront_walks<SOA>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, accum, cnt);
+        wavefront_walks<SOA>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, accum, cnt, wavefront == 2);
         merge(cnt);
     }
 #pragma omp parallel
@@ -304,7 +306,7 @@ EXPORT void emu_fused_pass(uint32_t n_local, const uint32_t *sample_ids, const T
     memset(&store, 0, sizeof store);
     store.light_paths = light_paths; store.camera_paths = camera_paths; store.soa = soa; store.soa_len = soa_len;
     store.n = n_local;
-#define GO(M, SO) fused_pass<M, SO>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, aggs, light_image, accum, wavefront && M == TRAVERSE_ORDERED)
+#define GO(M, SO) fused_pass<M, SO>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, aggs, light_image, accum, M == TRAVERSE_ORDERED ? wavefront : 0)
     if (soa) { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, true); else GO(TRAVERSE_ORDERED, true); }
     else { if (mode == TRAVERSE_REFERENCE) GO(TRAVERSE_REFERENCE, false); else GO(TRAVERSE_ORDERED, false); }
 #undef GO

@@ -487,11 +487,12 @@ def test_fused_pass_light_counts(E, n_extra, wavefront):
     _fused_vs_oracle_renderer(E, many_lights_arrays(n_extra, w, h), seeds_for(w * h, seed=6), wavefront=wavefront)
 
 
+@pytest.mark.parametrize("wavefront", [1, 2], ids=["binary_nodes", "wide_nodes"])
 @pytest.mark.parametrize("preset,w,h", [("empty", 40, 40), ("bench-spheres", 48, 36)])
-def test_wavefront_walks_vs_oracle_renderer(E, preset, w, h):
+def test_wavefront_walks_vs_oracle_renderer(E, preset, w, h, wavefront):
     """Stages 1-4 as wavefront rounds (the logic of k_walk_init / k_walk_trace / k_walk_shade: resumable single-step
     closest-hit search, per-bounce walk state in memory, live-sample queues) against the oracle renderer."""
-    _fused_vs_oracle_renderer(E, arrays(preset, w, h), seeds_for(w * h, seed=12), passes=3, wavefront=True)
+    _fused_vs_oracle_renderer(E, arrays(preset, w, h), seeds_for(w * h, seed=12), passes=3, wavefront=wavefront)
 
 
 @pytest.mark.parametrize("use_soa", [False, True], ids=["path_records", "soa_records"])

@@ -87,6 +87,9 @@ def main():
         for b in (1, 2, 4):
             for wgt in (1.0, 2.0):
                 rows.append((f"refill<{r}, vote inner vs <= {b} tris, weight {wgt}", dict(schedule=4, refill=r, batch=b, weight=wgt)))
+    for coop in (25, 40):
+        for wgt in (1.0, 2.0):
+            rows.append((f"refill<32, vote inner vs COOPERATIVE leaf (+{coop}), w {wgt}", dict(schedule=5, refill=32, batch=coop, weight=wgt)))
     for name, kw in rows:
         u, slots = run(**kw)
         print(f"{name:58s} {u:.3f}  {slots / base_slots:.3f}")

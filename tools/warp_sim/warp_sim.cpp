@@ -129,6 +129,9 @@ enum { S_SYNC_WHILE = 0,   /* no refill: 32 rays start together, while-while, wa
        S_STEP_BOTH = 3,    /* refill below R, per iteration: inner block (lanes at inner nodes) then triangle block of at
                               most B triangles (lanes in leaves) — both run when anyone needs them */
        S_STEP_VOTE = 4,    /* like 3 but only the block more lanes wait for (weighted) runs */
+       S_COOP_LEAF = 5,    /* vote; a leaf step spreads ALL pending triangles of the lanes at leaves over the 32 lanes
+                              (ray data by shuffle, results by warp reduction): ceil(total / 32) rounds of
+                              (c_tri + c_coop) slots; tri_batch = c_coop (extra instructions per cooperative test) */
 };
 
 struct Lane { const uint8_t *p, *end; int tri_left; bool have; };
@@ -198,6 +201,17 @@ EXPORT void sim_run(const Traces *T, const uint32_t *order, uint32_t n, int sche
                 int ni = 0, nl = 0;
                 for (int k = 0; k < 32; k++) { ni += at_inner(k); nl += at_leaf(k); }
                 if (ni * vote_weight >= nl) inner_block(); else leaf_block(0);
+            } else if (schedule == S_COOP_LEAF) {
+                int ni = 0, nl = 0, total = 0;
+                for (int k = 0; k < 32; k++) { ni += at_inner(k); if (at_leaf(k)) { nl++; total += *L[k].p; } }
+                /* compare lanes kept busy: an inner step occupies ni lanes, a cooperative leaf step min(32, total) */
+                if (ni * vote_weight >= std::min(32, total) && ni > 0) inner_block();
+                else if (total > 0) {
+                    const int rounds = (total + 31) / 32;
+                    slots += rounds * (C->c_tri + (double)tri_batch) + C->c_leaf_setup + 12.0 /* scan */;
+                    useful += total * C->c_tri;
+                    for (int k = 0; k < 32; k++) if (at_leaf(k)) advance(k);
+                }
             } else if (schedule == S_STEP_BOTH) {
                 inner_block();
                 leaf_block(tri_batch);
