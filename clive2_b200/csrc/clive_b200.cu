@@ -62,7 +62,9 @@ struct clv_ctx {
     int sm_count;
     int walk_mode;       /* fused pass, stages 1-4: 0 = automatic, 1 = megakernel (k_fused_walks), 2 = wavefront (k_walk_*) */
     int walk_refill_below, walk_schedule; /* k_walk_trace: refill threshold and vote weight, as for k_connect_rays */
+    int walk_grid_divisor;                /* k_walk_trace: persistent grid = resident blocks / divisor (slices co-reside) */
     int trace_blocks_per_sm[2];           /* resident blocks of k_walk_trace (cache-resident / large flavour) */
+    int connect_dynamic_fetch, rays_blocks_per_sm[2]; /* k_connect_rays: dynamic work fetch on a persistent grid */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
@@ -123,7 +125,15 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     c->walk_refill_below = getenv("CLV_WALK_REFILL_BELOW") ? atoi(getenv("CLV_WALK_REFILL_BELOW")) : 24;
     if (c->walk_refill_below < 1) c->walk_refill_below = 1;
     c->walk_schedule = getenv("CLV_WALK_SCHEDULE") ? atoi(getenv("CLV_WALK_SCHEDULE")) : 8;
+    /* with the pass cut into slices, a trace grid of HALF the resident blocks lets the kernels of two slices share the SMs,
+     * so one slice's tail (a few long rays, latency bound) overlaps another's work: C4, 3 slices, divisor 1 / 2 / 3 ->
+     * 29.7 / 28.8 / 30.2 ms per pass; 2 slices divisor 1: 28.9; 4 slices divisor 1 / 2: 30.6 / 29.5 */
+    c->walk_grid_divisor = getenv("CLV_WALK_GRID_DIVISOR") ? std::max(1, atoi(getenv("CLV_WALK_GRID_DIVISOR"))) : 2;
     c->trace_blocks_per_sm[0] = c->trace_blocks_per_sm[1] = 0; /* asked from the occupancy calculator on first use */
+    c->rays_blocks_per_sm[0] = c->rays_blocks_per_sm[1] = 0;
+    /* measured (k_connect_rays, ms per pass, static 512-task chunks -> dynamic fetch): C4 12.99 -> 11.07, C3 6.47 -> 5.87,
+     * C2 0.95 -> 0.85; C1 126 -> 136 Msamples/s */
+    c->connect_dynamic_fetch = getenv("CLV_CONNECT_DYNAMIC") ? atoi(getenv("CLV_CONNECT_DYNAMIC")) : 1;
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -465,6 +475,7 @@ __global__ void k_reset_light_indices(uint32_t n, int32_t *pix, int32_t *path, i
 struct ConnectScratch { /* device buffers shared by the three kernels */
     uint32_t *tasks;      /* [n * 36] */
     uint32_t *task_count; /* [1] */
+    uint32_t *cursor;     /* [1]: next task not handed out yet (dynamic work fetch of k_connect_rays) */
     unsigned int *vis;    /* [n][2]: visibility bits of strategies 0..41 */
     float *sensor;        /* [n][CLV_SENSOR_WORDS] */
 };
@@ -535,13 +546,16 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
 template <int MODE, bool COUNT, bool SOA, int LARGE = 0>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_RAYS_MIN_BLOCKS_LARGE : CLV_RAYS_MIN_BLOCKS)
 k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratch cs,
-               Counters *counters, int refill_below, int schedule) {
+               Counters *counters, int refill_below, int schedule, int dynamic_fetch) {
     const uint32_t count = *cs.task_count;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const uint64_t first = (uint64_t)warp * CLV_RAY_CHUNK;
+    /* two ways to deal the task list to the warps: static = warp w owns the CLV_RAY_CHUNK tasks starting at w * chunk
+     * (grid sized for the worst case, surplus warps leave at once); dynamic = persistent warps take the next tasks of
+     * the list whenever they refill (one atomicAdd per warp and refill), so no warp is left with a long chunk at the end */
+    const uint64_t first = dynamic_fetch ? 0ull : (uint64_t)warp * CLV_RAY_CHUNK;
     if (first >= count) return; /* whole warp */
-    const int total = (int)min((uint64_t)CLV_RAY_CHUNK, (uint64_t)count - first);
+    int total = dynamic_fetch ? 0x7fffffff : (int)min((uint64_t)CLV_RAY_CHUNK, (uint64_t)count - first);
     const uint32_t *tasks = cs.tasks + first;
     Cnt<COUNT> cnt;
     Camera c = camera[0];
@@ -554,8 +568,16 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
         const unsigned holding = __ballot_sync(0xffffffffu, have);
         if (next < total && __popc(holding) < refill_below) {
             const unsigned idle = ~holding;
+            if (dynamic_fetch) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cs.cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                next = (int)min(base, count);            /* this refill hands out [base, base + idle lanes) */
+                if ((uint64_t)base + (uint64_t)__popc(idle) >= (uint64_t)count) total = (int)count; /* list exhausted */
+                else total = 0x7fffffff;
+            }
             const int my = next + __popc(idle & ((1u << lane) - 1u));
-            if (!have && my < total) {
+            if (!have && my < (dynamic_fetch ? (int)count : total)) {
                 task = tasks[my];
                 const uint32_t slot = task >> 6;
                 const int q = (int)(task & 63u);
@@ -567,6 +589,7 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
                 if (st == OCC_CLEAR) atomicOr(&cs.vis[2 * (size_t)slot + (q >> 5)], 1u << (q & 31));
             }
             next += __popc(idle);
+            if (dynamic_fetch && total != 0x7fffffff) next = total; /* nothing left to fetch: stop refilling */
         } else if (holding == 0u) {
             break;
         }
@@ -607,7 +630,7 @@ k_connect_finish(uint32_t first, uint32_t n, const uint32_t *sample_ids, PathSto
     __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
     const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     Cnt<COUNT> cnt;
-    if (id == first) *cs.task_count = 0u; /* every ray of this pass is done (stream order): reset the list for the next */
+    if (id == first) { *cs.task_count = 0u; *cs.cursor = 0u; } /* every ray of this pass is done (stream order): reset the list for the next */
     const unsigned warp_lanes = __ballot_sync(0xffffffffu, id < n);
     if (id < n) {
         Camera c = camera[0];
@@ -780,14 +803,17 @@ k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, con
 #define CLV_TRACE_MIN_BLOCKS (1024 / CLV_BLOCK) /* <= 64 registers per thread */
 #endif
 #ifndef CLV_TRACE_MIN_BLOCKS_LARGE
-#define CLV_TRACE_MIN_BLOCKS_LARGE (1280 / CLV_BLOCK) /* <= 48 registers per thread */
+/* measured at C4 / C3 (ms per pass of all trace rounds; binary nodes): 64 / 48 / 40 / 32 registers -> 13.9 / 13.2 / 13.6 /
+ * 14.9 and 4.64 / 4.51 / 4.81 / 5.62; over the 4-wide nodes: 64 / 48 / 40 -> 12.2 / 12.4 / 13.5 and 4.33 / 4.52 / 5.07:
+ * the kernel does not respond to occupancy (profiles/r02_notes.md) */
+#define CLV_TRACE_MIN_BLOCKS_LARGE (1024 / CLV_BLOCK) /* <= 64 registers per thread */
 #endif
 /* node layout the trace kernel walks: the binary nodes (0) or their 4-wide collapse (1), per flavour */
 #ifndef CLV_TRACE_WIDE
 #define CLV_TRACE_WIDE 0
 #endif
 #ifndef CLV_TRACE_WIDE_LARGE
-#define CLV_TRACE_WIDE_LARGE 0
+#define CLV_TRACE_WIDE_LARGE 1 /* half the dependent record fetches per ray: C4 13.2 -> 12.2 ms, C3 4.51 -> 4.33 ms */
 #endif
 template <bool COUNT, int LARGE>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_TRACE_MIN_BLOCKS_LARGE : CLV_TRACE_MIN_BLOCKS)
@@ -817,7 +843,10 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
                 const V4 a0 = ws.s0[slot], a1 = ws.s1[slot];
                 ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
                 cnt.ray_ref();
-                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) have = true;
+                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) {
+                    have = true;
+                    if (CLV_PREFETCH_NEXT) prefetch_ref<WIDE>(WIDE ? A.wnodes : A.nodes, A.tris, ray.cur);
+                }
                 else ws.hit[slot] = v4(i2f(-1), CLV_INF, 0.0f, 0.0f);
             }
             if ((uint64_t)base + (uint64_t)n_idle >= (uint64_t)count) exhausted = true;
@@ -831,7 +860,7 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
         int status = HIT_RUNNING;
         if (n_inner * schedule >= n_leaf * 4) {
             if (at_inner) status = WIDE ? hit_inner_step_wide<COUNT>(A, ray, st, cnt) : hit_inner_step<COUNT>(A, ray, st, cnt);
-        } else if (have && !at_inner) status = hit_leaf_step<COUNT>(A, ray, st, cnt);
+        } else if (have && !at_inner) status = hit_leaf_step<COUNT, WIDE>(A, ray, st, cnt);
         if (status == HIT_DONE) {
             have = false;
             ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
@@ -841,7 +870,9 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
 }
 
 #ifndef CLV_SHADE_MIN_BLOCKS
-#define CLV_SHADE_MIN_BLOCKS 1 /* no register cap */
+/* measured at C4 / C3 (ms per pass of all shade rounds): uncapped (117 registers) / 96 / 80 / 64 / 48 / 40 / 32 ->
+ * 4.17 / 3.46 / 3.42 / 2.70 / 3.57 / 3.90 / 4.18 and 2.05 / 1.66 / 1.65 / 1.24 / 1.70 / 1.81 / 1.98 */
+#define CLV_SHADE_MIN_BLOCKS (1024 / CLV_BLOCK) /* <= 64 registers per thread */
 #endif
 template <bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK, CLV_SHADE_MIN_BLOCKS)
@@ -959,7 +990,8 @@ static size_t connect_scratch_bytes(uint32_t n) {
 static ConnectScratch connect_scratch_at(void *mem, uint32_t n) {
     ConnectScratch cs;
     char *p = (char *)mem;
-    cs.task_count = (uint32_t *)p;
+    cs.task_count = (uint32_t *)p;   /* header: task_count[CLV_MAX_SLICES] then cursor[CLV_MAX_SLICES] */
+    cs.cursor = cs.task_count + CLV_MAX_SLICES;
     p += 64;
     cs.tasks = (uint32_t *)p;
     p += (size_t)n * 36 * 4;
@@ -1024,12 +1056,26 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
     LAUNCHED(c);
     if (timed && mark_connect(timed, stream, 0) != CLV_OK) return CLV_ERR_CUDA;
     const uint64_t warps = ((uint64_t)len * 36 + CLV_RAY_CHUNK - 1) / CLV_RAY_CHUNK;
-    const unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
-    if (large && mode == CLV_TRAVERSE_ORDERED && !c->counting && soa) {
+    unsigned ray_blocks = (unsigned)((warps + CLV_WARPS_PER_BLOCK - 1) / CLV_WARPS_PER_BLOCK);
+    const bool large_flavour = large && mode == CLV_TRAVERSE_ORDERED && !c->counting && soa;
+    const int dyn = c->connect_dynamic_fetch && (uint64_t)len * 36 < 0x7fffffffull; /* task positions are ints in the kernel */
+    if (dyn) {
+        /* persistent grid: the SMs filled once (resident blocks of the flavour in use), never more warps than the worst-case
+         * number of 32-task groups */
+        int &per_sm = c->rays_blocks_per_sm[large_flavour ? 1 : 0];
+        if (!per_sm) {
+            if (large_flavour) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_connect_rays<TRAVERSE_ORDERED, false, true, 1>, CLV_BLOCK, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_connect_rays<TRAVERSE_ORDERED, false, true, 0>, CLV_BLOCK, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const uint64_t need = ((uint64_t)len * 36 + CLV_BLOCK - 1) / CLV_BLOCK;
+        ray_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * (uint64_t)per_sm, need));
+    }
+    if (large_flavour) {
         /* the renderer's default configuration on a scene larger than the caches: high-occupancy flavour */
-        k_connect_rays<TRAVERSE_ORDERED, false, true, 1><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule);
+        k_connect_rays<TRAVERSE_ORDERED, false, true, 1><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule, dyn);
     } else {
-#define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule)
+#define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule, dyn)
         DISPATCH_MCS(mode, c->counting, soa, CALL);
 #undef CALL
     }
@@ -1379,13 +1425,15 @@ static int ensure_walk_buffers(clv_renderer *r) {
 
 /* persistent grid of k_walk_trace: every SM filled with the resident blocks of the flavour, never more warps than rays */
 template <typename K>
-static int trace_grid(clv_ctx *c, K kernel, int flavour, uint32_t n_rays, unsigned *grid_out) {
+static int trace_grid(clv_ctx *c, K kernel, int flavour, uint32_t n_rays, bool sliced, unsigned *grid_out) {
     if (!c->trace_blocks_per_sm[flavour]) {
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CLV_BLOCK, 0));
         c->trace_blocks_per_sm[flavour] = per_sm > 0 ? per_sm : 1;
     }
-    const uint64_t resident = (uint64_t)c->sm_count * (uint64_t)c->trace_blocks_per_sm[flavour];
+    /* a pass that runs as one slice (per-kernel timing) has nobody to share the SMs with: full grid */
+    const uint64_t divisor = sliced ? (uint64_t)std::max(1, c->walk_grid_divisor) : 1u;
+    const uint64_t resident = std::max<uint64_t>(1, (uint64_t)c->sm_count * (uint64_t)c->trace_blocks_per_sm[flavour] / divisor);
     const uint64_t needed = ((uint64_t)n_rays + CLV_BLOCK - 1) / CLV_BLOCK;
     *grid_out = (unsigned)std::max<uint64_t>(1, std::min(resident, needed));
     return CLV_OK;
@@ -1393,7 +1441,7 @@ static int trace_grid(clv_ctx *c, K kernel, int flavour, uint32_t n_rays, unsign
 
 /* stages 1-4 of the samples [first, end) as wavefront rounds on `st` */
 static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, uint32_t first, uint32_t end, const uint32_t *ids,
-                                  const PathStore &store, bool soa, bool large) {
+                                  const PathStore &store, bool soa, bool large, bool sliced) {
     clv_ctx *c = r->ctx;
     const uint32_t len = end - first;
     const size_t n = r->n_local;
@@ -1413,9 +1461,9 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
     int rc = mark(r, st, TK_WALK_SHADE);
     if (rc != CLV_OK) return rc;
     unsigned tgrid = 1;
-    if (large) rc = trace_grid(c, k_walk_trace<false, 1>, 1, len, &tgrid);
-    else if (c->counting) rc = trace_grid(c, k_walk_trace<true, 0>, 0, len, &tgrid);
-    else rc = trace_grid(c, k_walk_trace<false, 0>, 0, len, &tgrid);
+    if (large) rc = trace_grid(c, k_walk_trace<false, 1>, 1, len, sliced, &tgrid);
+    else if (c->counting) rc = trace_grid(c, k_walk_trace<true, 0>, 0, len, sliced, &tgrid);
+    else rc = trace_grid(c, k_walk_trace<false, 0>, 0, len, sliced, &tgrid);
     if (rc != CLV_OK) return rc;
     const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 16u, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK));
     for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
@@ -1476,7 +1524,7 @@ static int launch_pass(clv_renderer *r) {
         cudaStream_t st = k == 0 ? c->stream : c->slice_stream[k];
         if (k > 0) CK(cudaStreamWaitEvent(st, c->slice_fork, 0));
         if (wavefront) {
-            if ((rc = launch_wavefront_walks(r, st, k, first, end, ids, store, soa, large)) != CLV_OK) return rc;
+            if ((rc = launch_wavefront_walks(r, st, k, first, end, ids, store, soa, large, slices > 1)) != CLV_OK) return rc;
         } else {
             if (large) {
                 k_fused_walks<TRAVERSE_ORDERED, false, true, 1><<<GRID(end - first), CLV_BLOCK, 0, st>>>(first, end, ids, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, r->d_accum, c->d_counters);
@@ -1490,6 +1538,7 @@ static int launch_pass(clv_renderer *r) {
         }
         ConnectScratch cs = cs_all;
         cs.task_count = cs_all.task_count + k;
+        cs.cursor = cs_all.cursor + k;
         cs.tasks = cs_all.tasks + (size_t)first * 36;
         rc = launch_connect(c, st, r->mode, true, large, first, end, ids, store, soa, r->accel->view, r->d_materials,
                             r->d_camera, cs, r->d_aggs, nullptr, sink, r);
@@ -1544,6 +1593,8 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
     else if (!strcmp(name, "walk_schedule")) slot = &c->walk_schedule;
     else if (!strcmp(name, "connect_refill_below")) slot = &c->refill_below;
     else if (!strcmp(name, "connect_schedule")) slot = &c->ray_schedule;
+    else if (!strcmp(name, "connect_dynamic_fetch")) slot = &c->connect_dynamic_fetch;
+    else if (!strcmp(name, "walk_grid_divisor")) slot = &c->walk_grid_divisor;
     else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
     if (previous) *previous = *slot;
     if (value >= 0) {

@@ -133,6 +133,45 @@ CLV_HD V4 ld4(const V4 *p) {
     return *p;
 #endif
 }
+/* Software prefetch of traversal records into L1 (device only; measured options, profiles/r02_notes.md).
+ * CLV_PREFETCH_LEAF: a leaf step first requests every 128-byte line of its triangle range, so that the per-triangle loads
+ * of its loop overlap instead of exposing one memory round trip each.  CLV_PREFETCH_NEXT: the record a search will read
+ * next (inner node or first lines of a leaf) is requested the moment it is chosen — the lane may wait several warp
+ * iterations for its kind of step to win the vote. */
+#ifndef CLV_PREFETCH_LEAF
+#define CLV_PREFETCH_LEAF 0
+#endif
+#ifndef CLV_PREFETCH_NEXT
+#define CLV_PREFETCH_NEXT 0
+#endif
+CLV_HD void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+/* every 128-byte line of the triangle records [first, first + count) */
+CLV_HD void prefetch_leaf(const V4 *tris, int first, int count) {
+#if defined(__CUDA_ARCH__)
+    const char *p = (const char *)(tris + 3 * (size_t)first);
+    const char *end = p + 48 * count;
+    p = (const char *)((size_t)p & ~(size_t)127);
+    for (; p < end; p += 128) prefetch_l1(p);
+#else
+    (void)tris; (void)first; (void)count;
+#endif
+}
+/* the record behind a child ref: one binary node (64 B) / 4-wide node (128 B), or a leaf's triangle range */
+template <bool WIDE>
+CLV_HD void prefetch_ref(const V4 *nodes, const V4 *tris, int ref) {
+#if defined(__CUDA_ARCH__)
+    if (ref >= 0) prefetch_l1(nodes + (WIDE ? 8 : 4) * (size_t)ref);
+    else prefetch_leaf(tris, (~ref) >> 4, (~ref) & 15);
+#else
+    (void)nodes; (void)tris; (void)ref;
+#endif
+}
 CLV_HD int f2i(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_int(f);
@@ -427,8 +466,11 @@ CLV_HD int hit_inner_step(const AccelView &A, HitRay &r, StackEntry *st, Cnt<COU
     const bool go_l = hl && tl <= r.best_t, go_r = hr && tr <= r.best_t;
     const bool left_first = tl < tr; /* tie: right first, the reference's order */
     if (go_l && go_r && r.sp < CLV_STACK) { st[r.sp] = stack_entry(left_first ? tr : tl, left_first ? rref : lref); r.sp++; }
-    if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return HIT_RUNNING; }
-    return hit_pop(r, st);
+    int status = HIT_RUNNING;
+    if (go_l || go_r) r.cur = (go_l && (left_first || !go_r)) ? lref : rref;
+    else status = hit_pop(r, st);
+    if (CLV_PREFETCH_NEXT && status == HIT_RUNNING) prefetch_ref<false>(A.nodes, A.tris, r.cur);
+    return status;
 }
 /* the same step over the 4-wide collapse of the tree (clv_accel_build.h): up to four child boxes per record, continue with
  * the nearest survivor, keep the others farthest first.  Half the dependent record fetches per ray of the binary form. */
@@ -442,13 +484,17 @@ CLV_HD int hit_inner_step_wide(const AccelView &A, HitRay &r, StackEntry *st, Cn
 #pragma unroll
     for (int k = 0; k < 3; k++)
         if (tk[k] < CLV_INF && r.sp < CLV_HIT_STACK(true)) { st[r.sp] = stack_entry(tk[k], rk[k]); r.sp++; }
-    if (tk[3] < CLV_INF) { r.cur = rk[3]; return HIT_RUNNING; }
-    return hit_pop(r, st);
+    int status = HIT_RUNNING;
+    if (tk[3] < CLV_INF) r.cur = rk[3];
+    else status = hit_pop(r, st);
+    if (CLV_PREFETCH_NEXT && status == HIT_RUNNING) prefetch_ref<true>(A.wnodes, A.tris, r.cur);
+    return status;
 }
-template <bool COUNT>
+template <bool COUNT, bool WIDE = false>
 CLV_HD int hit_leaf_step(const AccelView &A, HitRay &r, const StackEntry *st, Cnt<COUNT> &cnt) {
     const int code = ~r.cur;
     const int first = code >> 4, count = code & 15;
+    if (CLV_PREFETCH_LEAF && !CLV_PREFETCH_NEXT) prefetch_leaf(A.tris, first, count);
     for (int i = first; i < first + count; i++) {
         const V4 *tp = A.tris + 3 * (size_t)i;
         V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
@@ -460,7 +506,9 @@ CLV_HD int hit_leaf_step(const AccelView &A, HitRay &r, const StackEntry *st, Cn
             r.best_rank = f2i(a.w);
         }
     }
-    return hit_pop(r, st);
+    const int status = hit_pop(r, st);
+    if (CLV_PREFETCH_NEXT && status == HIT_RUNNING) prefetch_ref<WIDE>(WIDE ? A.wnodes : A.nodes, A.tris, r.cur);
+    return status;
 }
 
 /* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
@@ -572,9 +620,11 @@ CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> 
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (k != near && tk[k] < CLV_INF && r.sp < CLV_OCC_STACK) stack[r.sp++] = rk[k];
-        if (tk[near] < CLV_INF) { r.cur = rk[near]; return OCC_RUNNING; }
-        if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
-        return OCC_CLEAR;
+        if (tk[near] < CLV_INF) r.cur = rk[near];
+        else if (r.sp > 0) r.cur = stack[--r.sp];
+        else return OCC_CLEAR;
+        if (CLV_PREFETCH_NEXT) prefetch_ref<true>(A.wnodes, A.tris, r.cur);
+        return OCC_RUNNING;
     }
 #endif
     const V4 *n = A.nodes + 4 * (size_t)r.cur;
@@ -588,15 +638,18 @@ CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> 
     bool go_l = hl && tl <= r.t_bound, go_r = hr && tr <= r.t_bound;
     bool left_first = tl < tr;
     if (go_l && go_r && r.sp < CLV_OCC_STACK) stack[r.sp++] = left_first ? rref : lref;
-    if (go_l || go_r) { r.cur = (go_l && (left_first || !go_r)) ? lref : rref; return OCC_RUNNING; }
-    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
-    return OCC_CLEAR;
+    if (go_l || go_r) r.cur = (go_l && (left_first || !go_r)) ? lref : rref;
+    else if (r.sp > 0) r.cur = stack[--r.sp];
+    else return OCC_CLEAR;
+    if (CLV_PREFETCH_NEXT) prefetch_ref<false>(A.nodes, A.tris, r.cur);
+    return OCC_RUNNING;
 }
 /* ... or one whole leaf */
 template <bool COUNT>
 CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<COUNT> &cnt) {
     int code = ~r.cur;
     int first = code >> 4, count = code & 15;
+    if (CLV_PREFETCH_LEAF && !CLV_PREFETCH_NEXT) prefetch_leaf(A.tris, first, count);
     bool blocked = false;
     for (int i = first; i < first + count; i++) {
         const V4 *tp = A.tris + 3 * (size_t)i;
@@ -608,7 +661,11 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
             blocked = true;
     }
     if (blocked) return OCC_BLOCKED;
-    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
+    if (r.sp > 0) {
+        r.cur = stack[--r.sp];
+        if (CLV_PREFETCH_NEXT) prefetch_ref<CLV_WIDE_OCCLUSION != 0>(CLV_WIDE_OCCLUSION ? A.wnodes : A.nodes, A.tris, r.cur);
+        return OCC_RUNNING;
+    }
     return OCC_CLEAR;
 }
 

@@ -274,7 +274,9 @@ CLV_API int clv_ctx_walk_mode(clv_ctx *ctx, int mode, int *current_out);
 /* Scheduling knobs of the two ray kernels, for measurement sweeps (none changes a result): "walk_refill_below" /
  * "connect_refill_below" = lanes still holding a ray below which a warp of k_walk_trace / k_connect_rays fetches new
  * rays (1..32); "walk_schedule" / "connect_schedule" = vote weight w, an inner-node step wins when
- * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form).  value < 0 only queries. */
+ * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form); "connect_dynamic_fetch" = 1: k_connect_rays as
+ * persistent warps that fetch tasks with one atomicAdd per refill, 0: static 512-task chunks per warp; "walk_grid_divisor" =
+ * k_walk_trace's persistent grid is the resident blocks / divisor.  value < 0 only queries. */
 CLV_API int clv_ctx_set_knob(clv_ctx *ctx, const char *name, int value, int *previous);
 /* streaming-read bandwidth (GB/s) of a scratch buffer of nbytes read iters times: the L2 read peak for nbytes well
  * below the 126 MB L2 (the bound of the cache-resident configurations), the HBM read peak for nbytes >> L2 */

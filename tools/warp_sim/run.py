@@ -105,6 +105,17 @@ def main():
                      ("SORTED queue: sync while-while", dict(schedule=0))):
         u, slots = run(**kw)
         print(f"{name:58s} {u:.3f}  {slots / base_slots:.3f}")
+    # leaves capped by chaining (synthetic same-box nodes): does a more uniform leaf length pay for the extra inner steps?
+    lib.sim_traces_split_leaves.restype = C.c_void_p
+    order = np.arange(n, dtype=np.uint32)
+    keep = traces
+    for cap in (15, 8, 6, 4, 3, 2):
+        traces = C.c_void_p(lib.sim_traces_split_leaves(keep, cap))
+        u, slots = run(schedule=2, refill=24, weight=2.0)
+        u1, slots1 = run(schedule=2, refill=24, weight=1.0)
+        print(f"leaves <= {cap:2d}: refill<24 vote, weight 2: issue slots vs sync {slots / base_slots:.3f}   weight 1: {slots1 / base_slots:.3f}")
+        lib.sim_traces_destroy(traces)
+    traces = keep
     lib.sim_traces_destroy(traces)
     lib.sim_accel_destroy(acc)
 

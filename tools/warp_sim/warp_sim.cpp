@@ -114,6 +114,26 @@ EXPORT Traces *sim_trace_rays(const SimAccel *a, const Ray *rays, uint32_t n, in
     return T;
 }
 EXPORT void sim_traces_destroy(Traces *T) { delete T; }
+/* leaves longer than `max_leaf` become a synthetic inner node (same box: both halves are always visited) over two halves,
+ * recursively — what clv_accel_build.h leaf_ref() does for leaves longer than 15 */
+static void split_leaf(std::vector<uint8_t> &out, int k, int max_leaf) {
+    if (k <= max_leaf) { out.push_back((uint8_t)k); return; }
+    out.push_back(0);
+    split_leaf(out, k / 2, max_leaf);
+    split_leaf(out, k - k / 2, max_leaf);
+}
+EXPORT Traces *sim_traces_split_leaves(const Traces *T, int max_leaf) {
+    Traces *R = new Traces();
+    R->first.push_back(0);
+    for (size_t r = 0; r + 1 < T->first.size(); r++) {
+        for (uint64_t i = T->first[r]; i < T->first[r + 1]; i++) {
+            if (T->steps[i] == 0) R->steps.push_back(0);
+            else split_leaf(R->steps, T->steps[i], max_leaf);
+        }
+        R->first.push_back(R->steps.size());
+    }
+    return R;
+}
 EXPORT void sim_trace_stats(const Traces *T, double out[4]) {
     uint64_t n = T->first.size() - 1, inner = 0, leaves = 0, tris = 0;
     for (uint8_t s : T->steps) { if (s == 0) inner++; else { leaves++; tris += s; } }
