@@ -541,6 +541,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         cw, cc = ({k: v / max(my_passes, 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
+        NBT = 128 if accel_stats.get("trace_uses_wide") else 64  # ... and the wavefront trace kernel
         VB = 64  # bytes of one stored path vertex in the renderer's SoA records (four 16-byte parts)
         alg = {
             # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record
@@ -557,7 +558,7 @@ def run_ours(args, cfg, rank, local_rank, world):
             "k_fused_finalize": batch * (9 * 80 + 32 + 64),
             # wavefront walks, all 12 rounds of a pass.  trace: node + triangle records fetched + per ray origin/direction
             # parts read (32 B), hit written (16 B), queue entry (4 B)
-            "k_walk_trace": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * (32 + 16 + 4),
+            "k_walk_trace": cw["node_fetches"] * NBT + cw["tri_fetches"] * 48 + cw["rays_ref"] * (32 + 16 + 4),
             # shade (+ init): per ray hit (16 B) + walk state read and written (3-4 parts each way, 112 B) + seeds RMW
             # (16 B) + queue entry read + written (8 B) + the hit triangle's shading record (80 B); path vertices written
             # (64 B + 4 B patch); per sample: generators (seeds 16 B, jitter 8 B, state 48 B) + accumulator RMW (64 B)

@@ -269,6 +269,15 @@ extern "C" int clv_host_free(void *h_ptr) {
  * are issue-bound and lose with fewer registers.  Measured (walks at 64 / 48 / 40 / 32 registers per thread): C2 (2.8 MB)
  * 0.98 / 1.01 / - / - ms, C3 (60 MB) 6.81 / 6.32 / 6.13 / 6.17 ms, C4 (700 MB) 25.5 / 22.5 / 21.2 / 19.6 ms; occlusion
  * rays at 63 / 48 / 40 / 32 registers: C2 0.99 / 1.00 ms, C3 6.73 / 6.60 / - / 8.71 ms, C4 14.3 / 13.5 / 13.9 / 16.4 ms. */
+/* node layout k_walk_trace walks: the binary nodes (0) or their 4-wide collapse (1), per kernel flavour */
+#ifndef CLV_TRACE_WIDE
+#define CLV_TRACE_WIDE 0
+#endif
+#ifndef CLV_TRACE_WIDE_LARGE
+#define CLV_TRACE_WIDE_LARGE 1 /* half the dependent record fetches per ray: C4 13.2 -> 12.2 ms, C3 4.51 -> 4.33 ms */
+#endif
+#define CLV_TRACE_WIDE_VALUE (CLV_TRACE_WIDE != 0)
+#define CLV_TRACE_WIDE_LARGE_VALUE (CLV_TRACE_WIDE_LARGE != 0)
 /* which scenes run stages 1-4 as wavefront rounds when the walk mode is automatic (measured: profiles/r02_notes.md) */
 #ifndef CLV_WAVEFRONT_BY_DEFAULT
 #define CLV_WAVEFRONT_BY_DEFAULT(large_scene) (large_scene)
@@ -286,6 +295,7 @@ struct clv_accel {
     AccelView view;
     uint64_t n_nodes, n_wide, n_tris;
     int large; /* traversal records exceed CLV_LARGE_SCENE_BYTES: the fused pass uses its high-occupancy kernel flavours */
+    int binary_depth, wide_depth; /* inner levels of the two node layouts (bounded by the traversal stacks) */
 };
 
 extern "C" int clv_accel_destroy(clv_accel *a);
@@ -340,6 +350,8 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     a->view.wroot_ref = H.wide_root_ref;
     a->n_wide = H.wide.size();
     a->large = (nb_nodes + nb_wide + nb_tris) > (size_t)CLV_LARGE_SCENE_BYTES;
+    a->binary_depth = H.binary_depth;
+    a->wide_depth = H.wide_depth;
     a->view.tris = a->d_tris;
     a->view.ref_triangles = a->d_ref_triangles;
     a->view.root_min = boxes[0].min;
@@ -365,7 +377,7 @@ extern "C" int clv_accel_destroy(clv_accel *a) {
     return CLV_OK;
 }
 
-extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[9]) {
+extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[12]) {
     REQUIRE(a && out, "null");
     out[0] = a->n_nodes * sizeof(NodeRec); /* binary nodes */
     out[1] = a->n_tris * 3 * sizeof(V4);
@@ -376,6 +388,9 @@ extern "C" int clv_accel_stats(clv_accel *a, uint64_t out[9]) {
     out[6] = CLV_WIDE_CLOSEST;             /* which of the two each search kind traverses in the ORDERED flavour */
     out[7] = CLV_WIDE_OCCLUSION;
     out[8] = (uint64_t)a->large;
+    out[9] = (uint64_t)(a->large ? CLV_TRACE_WIDE_LARGE_VALUE : CLV_TRACE_WIDE_VALUE); /* k_walk_trace steps over 4-wide nodes */
+    out[10] = (uint64_t)a->binary_depth;
+    out[11] = (uint64_t)a->wide_depth;
     return CLV_OK;
 }
 
@@ -807,13 +822,6 @@ k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, con
  * 14.9 and 4.64 / 4.51 / 4.81 / 5.62; over the 4-wide nodes: 64 / 48 / 40 -> 12.2 / 12.4 / 13.5 and 4.33 / 4.52 / 5.07:
  * the kernel does not respond to occupancy (profiles/r02_notes.md) */
 #define CLV_TRACE_MIN_BLOCKS_LARGE (1024 / CLV_BLOCK) /* <= 64 registers per thread */
-#endif
-/* node layout the trace kernel walks: the binary nodes (0) or their 4-wide collapse (1), per flavour */
-#ifndef CLV_TRACE_WIDE
-#define CLV_TRACE_WIDE 0
-#endif
-#ifndef CLV_TRACE_WIDE_LARGE
-#define CLV_TRACE_WIDE_LARGE 1 /* half the dependent record fetches per ray: C4 13.2 -> 12.2 ms, C3 4.51 -> 4.33 ms */
 #endif
 template <bool COUNT, int LARGE>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_TRACE_MIN_BLOCKS_LARGE : CLV_TRACE_MIN_BLOCKS)
@@ -1460,19 +1468,22 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
     LAUNCHED(c);
     int rc = mark(r, st, TK_WALK_SHADE);
     if (rc != CLV_OK) return rc;
+    /* the trace kernel's flavour follows the scene (not the path layout or the counters): an instrumented run counts
+     * the records of the very search the timed run performs */
+    const bool tl = r->accel->large != 0;
     unsigned tgrid = 1;
-    if (large) rc = trace_grid(c, k_walk_trace<false, 1>, 1, len, sliced, &tgrid);
-    else if (c->counting) rc = trace_grid(c, k_walk_trace<true, 0>, 0, len, sliced, &tgrid);
-    else rc = trace_grid(c, k_walk_trace<false, 0>, 0, len, sliced, &tgrid);
+    if (c->counting) rc = tl ? trace_grid(c, k_walk_trace<true, 1>, 1, len, sliced, &tgrid) : trace_grid(c, k_walk_trace<true, 0>, 0, len, sliced, &tgrid);
+    else rc = tl ? trace_grid(c, k_walk_trace<false, 1>, 1, len, sliced, &tgrid) : trace_grid(c, k_walk_trace<false, 0>, 0, len, sliced, &tgrid);
     if (rc != CLV_OK) return rc;
     const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 16u, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK));
     for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
         const uint32_t *qin = round == 0 ? nullptr : wq.q[round & 1];
         uint32_t *qout = wq.q[(round + 1) & 1];
         const uint32_t n_identity = round == 0 ? len : 0u;
-        if (large) k_walk_trace<false, 1><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
-        else if (c->counting) k_walk_trace<true, 0><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
-        else k_walk_trace<false, 0><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule);
+#define TRACE(CT, LG) k_walk_trace<CT, LG><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule)
+        if (c->counting) { if (tl) TRACE(true, 1); else TRACE(true, 0); }
+        else { if (tl) TRACE(false, 1); else TRACE(false, 0); }
+#undef TRACE
         LAUNCHED(c);
         if ((rc = mark(r, st, TK_WALK_TRACE)) != CLV_OK) return rc;
 #define SHADE(CT, SO) k_walk_shade<CT, SO><<<sgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, qout, wq.count + round + 1, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr)

@@ -298,11 +298,12 @@ class Accel:
         self.n_boxes, self.n_triangles = len(b), len(t)
 
     def stats(self):
-        out = (C.c_uint64 * 9)()
+        out = (C.c_uint64 * 12)()
         _check(self.device.lib.clv_accel_stats(self.handle, out))
         return {"node_bytes": int(out[0]), "triangle_bytes": int(out[1]), "nodes": int(out[2]), "triangles": int(out[3]),
                 "wide_node_bytes": int(out[4]), "wide_nodes": int(out[5]), "closest_uses_wide": bool(out[6]),
-                "occlusion_uses_wide": bool(out[7]), "large_scene_tuning": bool(out[8])}
+                "occlusion_uses_wide": bool(out[7]), "large_scene_tuning": bool(out[8]), "trace_uses_wide": bool(out[9]),
+                "binary_depth": int(out[10]), "wide_depth": int(out[11])}
 
     def release(self):
         if getattr(self, "handle", None):
