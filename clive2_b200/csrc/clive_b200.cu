@@ -65,6 +65,7 @@ struct clv_ctx {
     int walk_grid_divisor;                /* k_walk_trace: persistent grid = resident blocks / divisor (slices co-reside) */
     int trace_blocks_per_sm[2];           /* resident blocks of k_walk_trace (cache-resident / large flavour) */
     int connect_dynamic_fetch, rays_blocks_per_sm[2]; /* k_connect_rays: dynamic work fetch on a persistent grid */
+    int finish_cooperative;                           /* k_connect_finish: warp-cooperative form */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
@@ -134,6 +135,7 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     /* measured (k_connect_rays, ms per pass, static 512-task chunks -> dynamic fetch): C4 12.99 -> 11.07, C3 6.47 -> 5.87,
      * C2 0.95 -> 0.85; C1 126 -> 136 Msamples/s */
     c->connect_dynamic_fetch = getenv("CLV_CONNECT_DYNAMIC") ? atoi(getenv("CLV_CONNECT_DYNAMIC")) : 1;
+    c->finish_cooperative = getenv("CLV_FINISH_COOPERATIVE") ? atoi(getenv("CLV_FINISH_COOPERATIVE")) : 0;
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -666,6 +668,116 @@ k_connect_finish(uint32_t first, uint32_t n, const uint32_t *sample_ids, PathSto
     flush_counters<COUNT>(cnt, counters);
 }
 
+/* k_connect_finish, warp-cooperative form.  The per-sample form above leaves lanes idle twice over: samples have different
+ * numbers of surviving strategies (0..36) and strategies have different loop lengths (s, t), ncu: 13.8 of 32 lanes.  Here a
+ * warp owns 32 samples and, for t = 1..6 in turn, deals the surviving (sample, s) strategies of that t — listed s-major, so
+ * neighbouring lanes run the same (s, t) — to its 32 lanes, one strategy per lane (connect_strategy: same operations as the
+ * sequential form); the terms land in shared memory and every sample then adds ITS OWN terms in ascending s.  Sums are
+ * therefore formed in the reference's order (t outer, s inner): same bits. */
+template <bool SPLAT, bool COUNT, bool SOA>
+__global__ void __launch_bounds__(CLV_BLOCK)
+k_connect_finish_coop(uint32_t first, uint32_t n, const uint32_t *sample_ids, PathStore store, const Material *materials,
+                      const Camera *camera, ConnectScratch cs, WeightAggregator *aggs, V4 *out, LightSink sink,
+                      Counters *counters) {
+    __shared__ float scratch[CLV_CONNECT_SCRATCH * CLV_BLOCK];
+    __shared__ float pback[6 * CLV_BLOCK];
+    __shared__ float4 results[CLV_WARPS_PER_BLOCK][7 * 32];
+    __shared__ int ctx_words[4 * CLV_BLOCK]; /* len_c, len_l, spec_l, spec_c of every sample of the block */
+    const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Cnt<COUNT> cnt;
+    if (id == first) { *cs.task_count = 0u; *cs.cursor = 0u; }
+    const bool active = id < n;
+    const Camera c = camera[0];
+    typedef typename PathViewOf<SOA>::type PV;
+    ConnectCtx<PV> X;
+    unsigned long long survivors = 0ull;
+    uint32_t agg_slot = 0;
+    if (active) {
+        TArr S, Sens;
+        S.base = scratch + threadIdx.x;
+        S.stride = CLV_BLOCK;
+        Sens.base = cs.sensor + (size_t)id * CLV_SENSOR_WORDS;
+        Sens.stride = 1;
+        agg_slot = sample_ids ? sample_ids[id] : id;
+        unsigned long long valid0;
+        connect_stage<COUNT>(PathViewOf<SOA>::make(store, id, agg_slot), materials, S, Sens, X, valid0, cnt);
+        survivors = valid0 | (unsigned long long)cs.vis[2 * (size_t)id] | ((unsigned long long)cs.vis[2 * (size_t)id + 1] << 32);
+        ctx_words[4 * threadIdx.x + 0] = X.len_c;
+        ctx_words[4 * threadIdx.x + 1] = X.len_l;
+        ctx_words[4 * threadIdx.x + 2] = (int)X.spec_l;
+        ctx_words[4 * threadIdx.x + 3] = (int)X.spec_c;
+    }
+    __syncwarp();
+    const bool spec_sensor = materials[7].type > 0;
+    V3 total = v3(0, 0, 0);
+    float weight_sum = 0.0f;
+    TArr PB;
+    PB.base = pback + threadIdx.x;
+    PB.stride = CLV_BLOCK;
+    const uint32_t warp_first_id = id - (uint32_t)lane;
+    const int warp_first_tid = (int)threadIdx.x - lane;
+    for (int t = 1; t <= CLV_MAX_BOUNCES; t++) {
+        const unsigned bits = (unsigned)(survivors >> ((t - 1) * 7)) & 0x7fu;
+        unsigned m[7];
+        int off[8];
+        off[0] = 0;
+#pragma unroll
+        for (int s = 0; s < 7; s++) {
+            m[s] = __ballot_sync(0xffffffffu, (bits >> s) & 1u);
+            off[s + 1] = off[s] + __popc(m[s]);
+        }
+        const int n_tasks = off[7]; /* warp-uniform */
+        if (n_tasks == 0) continue;
+        for (int j = lane; j < n_tasks; j += 32) {
+            int s = 0;
+#pragma unroll
+            for (int k = 1; k < 7; k++) s += (j >= off[k]) ? 1 : 0;
+            /* off[] and m[] are indexed with a lane-dependent s: select without local-memory arrays */
+            unsigned ms = m[0];
+            int os = off[0];
+#pragma unroll
+            for (int k = 1; k < 7; k++) { if (s == k) { ms = m[k]; os = off[k]; } }
+            const int src = (int)__fns(ms, 0u, j - os + 1);
+            const uint32_t src_id = warp_first_id + (uint32_t)src;
+            const int src_tid = warp_first_tid + src;
+            ConnectCtx<PV> Y;
+            Y.P = PathViewOf<SOA>::make(store, src_id, 0u);
+            Y.len_c = ctx_words[4 * src_tid + 0];
+            Y.len_l = ctx_words[4 * src_tid + 1];
+            Y.spec_l = (unsigned)ctx_words[4 * src_tid + 2];
+            Y.spec_c = (unsigned)ctx_words[4 * src_tid + 3];
+            Y.spec_sensor = spec_sensor;
+            Y.S.base = scratch + src_tid;
+            Y.S.stride = CLV_BLOCK;
+            Y.Sens.base = cs.sensor + (size_t)src_id * CLV_SENSOR_WORDS;
+            Y.Sens.stride = 1;
+            V3 term;
+            float w;
+            bool add;
+            connect_strategy<SPLAT>(Y, (t - 1) * 7 + s, PB, src_id, materials, c, sink, term, w, add);
+            results[warp_in_block][j] = make_float4(term.x, term.y, term.z, add ? w : -1.0f); /* an accepted w is > 0 (or NaN) */
+        }
+        __syncwarp();
+        if (bits) {
+#pragma unroll
+            for (int s = 0; s < 7; s++) {
+                if ((bits >> s) & 1u) {
+                    const float4 r = results[warp_in_block][off[s] + __popc(m[s] & lt_mask)];
+                    if (!(r.w < 0.0f)) {
+                        total = total + v3(r.x, r.y, r.z);
+                        weight_sum += r.w;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (active) connect_write_aggregator(X.P, total, weight_sum, agg_slot, c, aggs, out);
+    flush_counters<COUNT>(cnt, counters);
+}
+
 __global__ void __launch_bounds__(CLV_BLOCK)
 k_adaptive_finalize_samples(uint32_t n, const WeightAggregator *aggs, const Camera *camera, V4 *out,
                             uint32_t *sample_counts, const uint32_t *bin_offsets, float *sample_weights) {
@@ -1089,7 +1201,8 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
     }
     LAUNCHED(c);
     if (timed && mark_connect(timed, stream, 1) != CLV_OK) return CLV_ERR_CUDA;
-#define FIN(SP, CT, SO) k_connect_finish<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr)
+#define FIN(SP, CT, SO) do { if (c->finish_cooperative) k_connect_finish_coop<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr); \
+                            else k_connect_finish<SP, CT, SO><<<GRID(len), CLV_BLOCK, 0, stream>>>(first, n, sample_ids, store, mats, cam, cs, aggs, out, sink, ctr); } while (0)
     if (soa) {
         if (splat) { if (c->counting) FIN(true, true, true); else FIN(true, false, true); }
         else { if (c->counting) FIN(false, true, true); else FIN(false, false, true); }
@@ -1606,6 +1719,7 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
     else if (!strcmp(name, "connect_schedule")) slot = &c->ray_schedule;
     else if (!strcmp(name, "connect_dynamic_fetch")) slot = &c->connect_dynamic_fetch;
     else if (!strcmp(name, "walk_grid_divisor")) slot = &c->walk_grid_divisor;
+    else if (!strcmp(name, "finish_cooperative")) slot = &c->finish_cooperative;
     else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
     if (previous) *previous = *slot;
     if (value >= 0) {

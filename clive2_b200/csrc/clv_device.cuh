@@ -1196,6 +1196,23 @@ struct LightSink {
     int n_pixels;
 };
 
+/* one 16-byte reduction per light-image splat (sm_90+: atomicAdd on float4, one RED.128 instead of four RED.32); the four
+ * components are added independently, exactly as four scalar atomics would */
+CLV_HD void atomic_add4(V4 *p, V4 v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+    float *f = &p->x;
+#pragma omp atomic
+    f[0] += v.x;
+#pragma omp atomic
+    f[1] += v.y;
+#pragma omp atomic
+    f[2] += v.z;
+#pragma omp atomic
+    f[3] += v.w;
+#endif
+}
 CLV_HD void atomic_add(float *p, float v) {
 #if defined(__CUDA_ARCH__)
     atomicAdd(p, v);
@@ -1369,26 +1386,21 @@ CLV_HD int connect_ray_begin(int q, const PV &P, TArr Sens, const AccelView &A, 
     return best_i == b_triangle ? OCC_CLEAR : OCC_BLOCKED;
 }
 
-/* finish: MIS + contributions of the surviving strategies, splat weights, aggregator */
+/* one surviving strategy q = (t-1)*7 + s of the sample behind X: its MIS weight (:693-776) and contribution (:778-823).
+ * t != 1: returns add = true with `term` = w*g*color/p_s and `w_out` = w, to be added to the sample's totals IN THE
+ * REFERENCE'S ORDER (t outer, s inner) by the caller; t == 1: the light-image entry is emitted here (splat or staged
+ * arrays) and add stays false.  PB: 6 floats of scratch private to the evaluating thread (p_values[0..s-1]). */
 template <bool SPLAT, typename PV>
-CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
-                           const Material *materials, const Camera &c, WeightAggregator *weight_aggregators, V4 *out,
-                           const LightSink &sink, unsigned warp_lanes /* device: lanes of the warp that make this call */) {
+CLV_HD void connect_strategy(const ConnectCtx<PV> &X, int q, TArr PB, uint32_t entry_id, const Material *materials,
+                             const Camera &c, const LightSink &sink, V3 &term, float &w_out, bool &add) {
     const PV &P = X.P;
     TArr S = X.S;
     const unsigned spec_l = X.spec_l, spec_c = X.spec_c;
     const int total_pixels = c.pixel_width * c.pixel_height;
-    V3 total_contribution = v3(0, 0, 0);
-    float contrib_weight_sum = 0.0f;
-
-    while (survivors) {
-        int q;
-#if defined(__CUDA_ARCH__)
-        q = __ffsll((long long)survivors) - 1;
-#else
-        q = __builtin_ctzll(survivors);
-#endif
-        survivors &= survivors - 1;
+    term = v3(0, 0, 0);
+    w_out = 0.0f;
+    add = false;
+    {
         const int t = q / 7 + 1, s = q % 7;
 
         V3 cam_n = v3(0, 0, 0), lig_o = v3(0, 0, 0), lig_n = v3(0, 0, 0), dir_l_to_c = v3(0, 0, 0);
@@ -1449,10 +1461,10 @@ CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors
             float num = (i == 0) ? S[L_LIMP] : S[L_LIMP + i] * S[G_LL + i - 1];
             float denom = S[L_CIMP + i] * ((i == s - 1) ? g_conn : S[G_LL + i]);
             p_i = p_i / (num / denom);
-            S[P_BACK + i] = p_i;
+            PB[i] = p_i;
         }
         float sum = 0.0f;
-        for (int i = 0; i < s; i++) sum += ((zmask >> i) & 1u) ? 0.0f : S[P_BACK + i];
+        for (int i = 0; i < s; i++) sum += ((zmask >> i) & 1u) ? 0.0f : PB[i];
         const float p_at_s = ((zmask >> s) & 1u) ? 0.0f : p_s;
         sum += p_at_s;
         p_i = p_s;
@@ -1496,8 +1508,9 @@ CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors
             g = g_conn; /* cosine_geometry_term(camera_ray, light_ray): symmetric, same bits */
         }
         if (t != 1) {
-            total_contribution = total_contribution + (color * (w * g)) / p_s;
-            contrib_weight_sum += w;
+            term = (color * (w * g)) / p_s;
+            w_out = w;
+            add = true;
         } else {
             float shade = new_light_f * g / p_s;
             if (SPLAT) {
@@ -1506,11 +1519,7 @@ CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors
                     int prior_light_ind = (s - 2 > 0) ? s - 2 : 0;
                     V3 contrib = (P.color(SUB_LIGHT, prior_light_ind) * (w * shade)) *
                                  xyz(ld4(&materials[P.material(SUB_LIGHT, s - 1)].color));
-                    float *px = &sink.splat_image[light_pixel_idx].x;
-                    atomic_add(px + 0, contrib.x);
-                    atomic_add(px + 1, contrib.y);
-                    atomic_add(px + 2, contrib.z);
-                    atomic_add(px + 3, w);
+                    atomic_add4(&sink.splat_image[light_pixel_idx], v4(contrib.x, contrib.y, contrib.z, w));
                 }
             } else {
                 size_t e = (size_t)entry_id + (size_t)s * (size_t)total_pixels;
@@ -1523,13 +1532,13 @@ CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors
         }
         }
     }
+}
 
-#if defined(__CUDA_ARCH__)
-    /* lanes leave the strategy loop at different times; without this the splat-weight code below ran with 2.3 of 32
-     * lanes active (ncu, profiles/r01_notes.md) */
-    __syncwarp(warp_lanes);
-#endif
-    /* 3x3 splat weights (:827-864) */
+/* finish: MIS + contributions of the surviving strategies, splat weights, aggregator */
+/* 3x3 splat weights (:827-864) and the aggregator record of one sample */
+template <typename PV>
+CLV_HD void connect_write_aggregator(const PV &P, V3 total_contribution, float contrib_weight_sum, uint32_t agg_slot,
+                                     const Camera &c, WeightAggregator *weight_aggregators, V4 *out) {
     WeightAggregator agg;
     for (int i = 0; i < 3; i++) { agg.pad0[i] = 0.0f; agg.pad1[i] = 0.0f; }
     const int pixel_idx = P.pixel_idx0();
@@ -1560,6 +1569,43 @@ CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors
     agg.contrib_weight_sum = contrib_weight_sum;
     if (out) out[agg_slot] = v4(total_contribution.x, total_contribution.y, total_contribution.z, 1.0f);
     weight_aggregators[agg_slot] = agg;
+}
+
+/* the sequential form: one thread evaluates its sample's survivors one after the other (host build, the stage-level ABI's
+ * Path records; k_connect_finish distributes the same evaluations over the lanes of a warp) */
+template <bool SPLAT, typename PV>
+CLV_HD void connect_finish(const ConnectCtx<PV> &X, unsigned long long survivors, uint32_t entry_id, uint32_t agg_slot,
+                           const Material *materials, const Camera &c, WeightAggregator *weight_aggregators, V4 *out,
+                           const LightSink &sink, unsigned warp_lanes /* device: lanes of the warp that make this call */) {
+    V3 total_contribution = v3(0, 0, 0);
+    float contrib_weight_sum = 0.0f;
+    TArr PB;
+    PB.base = &X.S[P_BACK];
+    PB.stride = X.S.stride;
+    while (survivors) {
+        int q;
+#if defined(__CUDA_ARCH__)
+        q = __ffsll((long long)survivors) - 1;
+#else
+        q = __builtin_ctzll(survivors);
+#endif
+        survivors &= survivors - 1;
+        V3 term;
+        float w;
+        bool add;
+        connect_strategy<SPLAT>(X, q, PB, entry_id, materials, c, sink, term, w, add);
+        /* one back edge only: a `continue` here would let the lanes that skip drift apart from the rest for good */
+        if (add) {
+            total_contribution = total_contribution + term;
+            contrib_weight_sum += w;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    /* lanes leave the strategy loop at different times; without this the splat-weight code below ran with 2.3 of 32
+     * lanes active (ncu, profiles/r01_notes.md) */
+    __syncwarp(warp_lanes);
+#endif
+    connect_write_aggregator(X.P, total_contribution, contrib_weight_sum, agg_slot, c, weight_aggregators, out);
 }
 
 /* the three phases for one sample, rays traced one after the other by the calling thread (host build; also the shape
