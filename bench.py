@@ -610,6 +610,7 @@ def run_ours(args, cfg, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(cfg, arrays, world, plan),
             "run": {"triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)), "accel_bytes": accel_bytes,
+                    "bvh_levels": {"binary": accel_stats.get("binary_depth"), "four_wide": accel_stats.get("wide_depth")},
                     "samples_per_pass_per_gpu": n_local, "passes_per_gpu": my_passes,
                     "launches_per_pass": launches // max(my_passes, 1),
                     "kernel_flavour": ("high-occupancy (traversal records exceed the caches)"

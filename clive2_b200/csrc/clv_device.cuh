@@ -49,7 +49,8 @@
  * level of the 4-wide collapse), pruned children are never pushed, and clv_accel_create REFUSES a tree deeper than
  * these bounds (CLV_ERR_INVALID) instead of dropping pushes: the `sp < CLV_*STACK` tests below are memory-safety guards
  * that never fire on an accepted structure.  Closest-hit entries are (t_entry, ref) packed into one 64-bit word: half
- * the local-memory instructions of two 32-bit arrays, 256 B per thread instead of 768 B. */
+ * the local-memory instructions of two 32-bit arrays, 320 B per thread instead of 768 B.  (The 10 M-triangle tree of
+ * BASELINE config 4 is 29 binary levels deep.) */
 /* which node layout the ORDERED flavour traverses: the 4-wide collapse of the BVH (1) or the binary nodes (0),
  * separately for closest-hit searches (random walks) and occlusion queries (connection rays) */
 #ifndef CLV_WIDE_CLOSEST
@@ -58,7 +59,7 @@
 #ifndef CLV_WIDE_OCCLUSION
 #define CLV_WIDE_OCCLUSION 1
 #endif
-#define CLV_STACK (CLV_WIDE_CLOSEST ? 96 : 32) /* closest-hit: 64-bit (t, ref) entries */
+#define CLV_STACK (CLV_WIDE_CLOSEST ? 96 : 40) /* closest-hit: 64-bit (t, ref) entries */
 #define CLV_OCC_STACK 64                       /* occlusion queries over the 4-wide nodes: 32-bit refs */
 #define CLV_MAX_BINARY_DEPTH (CLV_WIDE_CLOSEST ? CLV_OCC_STACK / 3 : CLV_STACK) /* deepest accepted tree (inner levels) */
 #define CLV_MAX_WIDE_DEPTH (CLV_OCC_STACK / 3)
@@ -431,7 +432,7 @@ struct HitRay {
 enum { HIT_RUNNING = 0, HIT_DONE = 1 };
 
 /* stack entries a resumable search needs: one deferred sibling per binary level, three per 4-wide level */
-#define CLV_HIT_STACK(WIDE) ((WIDE) ? CLV_OCC_STACK : 32)
+#define CLV_HIT_STACK(WIDE) ((WIDE) ? CLV_OCC_STACK : CLV_STACK)
 template <bool COUNT, bool WIDE = false>
 CLV_HD int hit_begin(const AccelView &A, HitRay &r, Cnt<COUNT> &cnt) {
     cnt.ray_traced();

@@ -128,7 +128,7 @@ CLV_API int clv_accel_destroy(clv_accel *accel);
  * searches of the ORDERED flavour traverse the 4-wide nodes, [8] 1 if the records exceed the cache-resident size and the
  * fused pass therefore runs its high-occupancy kernel flavours (same results, different register budget), [9] 1 if the
  * wavefront trace kernel steps over the 4-wide nodes for this structure, [10]/[11] inner levels of the binary / 4-wide
- * tree.  A tree deeper than the traversal stacks allow (32 binary / 21 4-wide levels) is refused by clv_accel_create with
+ * tree.  A tree deeper than the traversal stacks allow (40 binary / 21 4-wide levels) is refused by clv_accel_create with
  * CLV_ERR_INVALID — the kernels never drop a push (the reference's own 64-entry stack silently aborts the search,
  * trace.metal:149) */
 CLV_API int clv_accel_stats(clv_accel *accel, uint64_t out[12]);

@@ -155,6 +155,44 @@ def test_bad_bvh_arrays_are_rejected(E):
         E.accel(boxes, np.zeros(1, T.Triangle))
 
 
+def _chain_bvh(levels):
+    """A degenerate tree: every inner node has a one-triangle leaf on the left and the rest of the chain on the right."""
+    n_boxes, n_tris = 2 * levels + 1, levels + 1
+    boxes, tris = np.zeros(n_boxes, T.Box), np.zeros(n_tris, T.Triangle)
+    for k in range(n_tris):
+        tris["v0"][k, :3] = (k, 0, 0)
+        tris["v1"][k, :3] = (k + 1, 0, 0)
+        tris["v2"][k, :3] = (k, 1, 0)
+    for k in range(levels):  # inner node 2k: children 2k+1 (leaf, triangle k) and 2k+2 (rest)
+        boxes["left"][2 * k], boxes["right"][2 * k] = 2 * k + 1, 0
+        boxes["min"][2 * k, :3], boxes["max"][2 * k, :3] = (k, 0, 0), (n_tris + 1, 1, 0)
+        boxes["left"][2 * k + 1], boxes["right"][2 * k + 1] = k, k + 1
+        boxes["min"][2 * k + 1, :3], boxes["max"][2 * k + 1, :3] = (k, 0, 0), (k + 1, 1, 0)
+    boxes["left"][2 * levels], boxes["right"][2 * levels] = levels, levels + 1
+    boxes["min"][2 * levels, :3], boxes["max"][2 * levels, :3] = (levels, 0, 0), (levels + 1, 1, 0)
+    return boxes, tris
+
+
+def test_trees_deeper_than_the_traversal_stacks_are_refused_not_truncated(O, E):
+    """The reference's 64-entry stack silently aborts a search that overflows it (trace.metal:149).  Here a structure whose
+    tree could overflow the kernels' stacks (one deferred sibling per level) is refused when it is built; a tree at the
+    limit traverses exactly."""
+    boxes, tris = _chain_bvh(20)  # 20 binary levels: the 4-wide collapse has up to 3 deferred siblings per level
+    acc = E.accel(boxes, tris)
+    try:
+        rays = random_rays(2000, [0, 0, -3], [21, 1, 3], seed=4)
+        tri, t, _, _ = O.traverse(rays, boxes, tris)
+        for mode in (MODE_REFERENCE, MODE_ORDERED):
+            tri2, t2, _, _ = E.traverse(rays, acc, mode)
+            assert np.array_equal(tri, tri2)
+            assert np.array_equal(t[tri >= 0].view(np.uint32), t2[tri >= 0].view(np.uint32))
+        assert (tri >= 0).sum() > 100
+    finally:
+        E.accel_destroy(acc)
+    with pytest.raises(ValueError):
+        E.accel(*_chain_bvh(64))
+
+
 def test_fused_pass_matches_oracle_renderer(E):
     """clv_renderer_run_sample's kernel sequence vs the reference's eight stages (oracle): everything that does not go
     through the atomically splatted light image is bit exact; the image agrees to float-summation-order tolerance."""
