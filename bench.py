@@ -537,7 +537,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         np_ = max(timed, 1)
         # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
-        launches_of = {"k_walk_trace": 12, "k_walk_shade": 13}  # per pass; every other kernel is launched once
+        launches_of = {"k_walk_trace": 12, "k_walk_shade": 13 if "k_walk_trace" in kernel_ms else 1}  # per pass; every other kernel once
         cw, cc = ({k: v / max(my_passes, 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
@@ -564,6 +564,8 @@ def run_ours(args, cfg, rank, local_rank, world):
             # (64 B + 4 B patch); per sample: generators (seeds 16 B, jitter 8 B, state 48 B) + accumulator RMW (64 B)
             "k_walk_shade": cw["rays_ref"] * (16 + 112 + 16 + 8 + 80) + cw["vertices"] * 68 + n_local * (16 + 8 + 48 + 64),
         }
+        # the pipelined form runs trace and shade in ONE kernel (plus the separately timed k_walk_init, counted under shade)
+        alg["k_walk_pipeline"] = alg["k_walk_trace"] + alg["k_walk_shade"]
         for k in list(kernel_ms):
             alg.setdefault(k, 0.0)
         accel_bytes = accel_stats["node_bytes"] + accel_stats["wide_node_bytes"] + accel_stats["triangle_bytes"]
@@ -616,6 +618,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                     "kernel_flavour": ("high-occupancy (traversal records exceed the caches)"
                                        if accel_stats["large_scene_tuning"] else "cache-resident"),
                     "walks": "wavefront (k_walk_init + 12 x (k_walk_trace, k_walk_shade))" if "k_walk_trace" in kernel_ms
+                             else "wavefront, pipelined (k_walk_init + k_walk_pipeline)" if "k_walk_pipeline" in kernel_ms
                              else "megakernel (k_fused_walks)",
                     "mesh_source": "in-memory" if (args.mesh_in_memory or not cfg.get("mesh")) else
                                    f"{cfg['mesh'][0].upper()} file written and read back (load.write_{cfg['mesh'][0]} / read_{cfg['mesh'][0]})",

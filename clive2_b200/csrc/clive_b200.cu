@@ -284,6 +284,10 @@ extern "C" int clv_host_free(void *h_ptr) {
 #ifndef CLV_WAVEFRONT_BY_DEFAULT
 #define CLV_WAVEFRONT_BY_DEFAULT(large_scene) (large_scene)
 #endif
+/* ... and whether the wavefront walks then run as one pipelined kernel (1) or as 12 rounds of trace + shade (0) */
+#ifndef CLV_PIPELINE_BY_DEFAULT
+#define CLV_PIPELINE_BY_DEFAULT 0
+#endif
 #ifndef CLV_LARGE_SCENE_BYTES
 #define CLV_LARGE_SCENE_BYTES (32u << 20)
 #endif
@@ -915,9 +919,11 @@ template <bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK)
 k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, const float *surface_areas,
             const int32_t *light_triangle_indices, int light_count, const Material *materials, uint32_t *seeds,
-            PathStore store, WalkState ws, WalkQueues wq) {
+            PathStore store, WalkState ws, WalkQueues wq, uint32_t *pipe_ctrl) {
     const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x < CLV_WALK_COUNTER_WORDS) wq.count[threadIdx.x] = 0u; /* count[] and cursor[] are one block */
+    if (pipe_ctrl && blockIdx.x == 0 && threadIdx.x < 8) /* pipelined form: every sample's first ray is an implicit entry */
+        pipe_ctrl[threadIdx.x] = (threadIdx.x == 0 /* trace tail */ || threadIdx.x == 4 /* live */) ? n_end - first : 0u;
     if (id >= n_end) return;
     uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
     uint32_t seed0 = sd.x, seed1 = sd.y;
@@ -960,14 +966,14 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
             const uint32_t my = base + (uint32_t)__popc(idle & lt_mask);
             if (!have && my < count) {
                 slot = queue ? queue[my] : first + my;
-                const V4 a0 = ws.s0[slot], a1 = ws.s1[slot];
+                const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
                 ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
                 cnt.ray_ref();
                 if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) {
                     have = true;
                     if (CLV_PREFETCH_NEXT) prefetch_ref<WIDE>(WIDE ? A.wnodes : A.nodes, A.tris, ray.cur);
                 }
-                else ws.hit[slot] = v4(i2f(-1), CLV_INF, 0.0f, 0.0f);
+                else stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f));
             }
             if ((uint64_t)base + (uint64_t)n_idle >= (uint64_t)count) exhausted = true;
         } else if (holding == 0u) {
@@ -983,7 +989,7 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
         } else if (have && !at_inner) status = hit_leaf_step<COUNT, WIDE>(A, ray, st, cnt);
         if (status == HIT_DONE) {
             have = false;
-            ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
+            stcg4(ws.hit + slot, v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv));
         }
     }
     flush_counters<COUNT>(cnt, counters);
@@ -1023,6 +1029,161 @@ k_walk_shade(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) queue_out[base + (uint32_t)__popc(staying & ((1u << lane) - 1u))] = slot;
         }
+    }
+    flush_counters<COUNT>(cnt, counters);
+}
+
+/* ---- pipelined form of the wavefront walks: ONE persistent kernel per slice instead of 12 x (trace, shade) ------------- *
+ * The round form above ends every round with a tail: the last rays of a round are long (hundreds of steps, each a
+ * dependent memory round trip) and run alone while every other warp has left — ncu: the SMs are active 75 % of a trace
+ * launch — and a shard of the frame (multi-GPU) pays the same absolute tail on fewer rays.  Here nothing waits for a
+ * round: a warp that still holds rays keeps stepping them; a warp that holds none takes work from one of two queues —
+ *   trace queue  sample slots whose next ray is ready (entries 0..n0-1 are implicit: every sample's first ray)
+ *   done queue   sample slots whose ray has been traced and whose hit record waits for its bounce
+ * — shading a batch (which appends the survivors to the trace queue) or refilling its lanes with rays.  Both queues are
+ * linear (a sample contributes at most 12 entries per pass to each), reserved with one atomic per warp; an entry is valid
+ * once its slot word is written (the buffer starts as EMPTY).  Records that cross SMs inside the kernel (walk state, hit
+ * records, seeds) are read with L1-bypassing loads after a __threadfence handshake through the queue entry.  The kernel
+ * ends when the count of live samples reaches zero.  Same per-ray / per-bounce operations as the other two forms:
+ * bit-identical results. */
+struct WalkPipe {
+    uint32_t *ctrl;    /* [8]: 0 trace tail (reserved), 1 trace head (claimed), 2 done tail, 3 done head, 4 live samples, 5 error */
+    uint32_t *trace_q; /* explicit entries: index i >= n0 lives at trace_q[i - n0]; capacity 11 * n0 */
+    uint32_t *done_q;  /* capacity 12 * n0 */
+    uint32_t n0, first;
+};
+#define CLV_PIPE_EMPTY 0xffffffffu
+enum { PIPE_TRACE_TAIL = 0, PIPE_TRACE_HEAD, PIPE_DONE_TAIL, PIPE_DONE_HEAD, PIPE_LIVE, PIPE_ERROR };
+
+/* claim up to `want` entries of a queue: returns the first claimed index and the number claimed (0 when nothing is
+ * available or another warp won the race; the caller simply tries again later).  Never claims beyond the tail. */
+__device__ __forceinline__ uint32_t pipe_claim(volatile uint32_t *ctrl, int head_word, int tail_word, int want, int lane, int *got) {
+    uint32_t base = 0;
+    int k = 0;
+    if (lane == 0) {
+        const uint32_t head = ctrl[head_word], tail = ctrl[tail_word];
+        const int avail = (int)(tail - head);
+        if (avail > 0) {
+            k = min(want, avail);
+            if (atomicCAS((uint32_t *)&ctrl[head_word], head, head + (uint32_t)k) == head) base = head;
+            else k = 0;
+        }
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    *got = __shfl_sync(0xffffffffu, k, 0);
+    return base;
+}
+/* the slot word of a claimed entry (the producer reserved it before us and writes it a few instructions later) */
+__device__ __forceinline__ uint32_t pipe_wait(const volatile uint32_t *q, uint32_t index) {
+    uint32_t v = q[index];
+    while (v == CLV_PIPE_EMPTY) { __nanosleep(64); v = q[index]; }
+    __threadfence();
+    return v;
+}
+
+template <bool COUNT, bool SOA, int LARGE>
+__global__ void __launch_bounds__(CLV_BLOCK, 1024 / CLV_BLOCK)
+k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materials, const Camera *camera, AccelView A,
+                uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters, int refill_below, int schedule) {
+    constexpr bool WIDE = LARGE ? (CLV_TRACE_WIDE_LARGE != 0) : (CLV_TRACE_WIDE != 0);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    volatile uint32_t *ctrl = wp.ctrl;
+    const volatile uint32_t *trace_q = wp.trace_q, *done_q = wp.done_q;
+    const Camera c = camera[0];
+    Cnt<COUNT> cnt;
+    HitRay ray;
+    StackEntry st[CLV_HIT_STACK(WIDE)];
+    bool have = false;
+    uint32_t slot = 0;
+    unsigned idle_polls = 0;
+    int skip_polls = 0; /* warp-uniform: iterations to go before the trace queue is looked at again after it was found dry */
+    for (;;) {
+        const unsigned holding = __ballot_sync(0xffffffffu, have);
+        bool finished = false; /* this lane's ray ended in this iteration: its hit record is written, publish the slot */
+        /* ---- refill: idle lanes take rays from the trace queue ---- */
+        if (skip_polls > 0) skip_polls--;
+        else if (__popc(holding) < refill_below) {
+            const unsigned idle = ~holding;
+            int got;
+            const uint32_t base = pipe_claim(ctrl, PIPE_TRACE_HEAD, PIPE_TRACE_TAIL, __popc(idle), lane, &got);
+            const int rank = __popc(idle & lt_mask);
+            if (!have && rank < got) {
+                const uint32_t index = base + (uint32_t)rank;
+                slot = index < wp.n0 ? wp.first + index : pipe_wait(trace_q, index - wp.n0);
+                const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
+                ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
+                cnt.ray_ref();
+                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) have = true;
+                else { stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f)); finished = true; }
+            }
+            if (got) idle_polls = 0;
+            else if (holding) skip_polls = 3; /* a look at the queue is an L2 round trip on the critical path of every lane */
+        }
+        const unsigned tracing = __ballot_sync(0xffffffffu, have);
+        if (tracing) {
+            /* ---- one traversal step, kind chosen by majority vote ---- */
+            const bool at_inner = have && ray.cur >= 0;
+            const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
+            const int n_leaf = __popc(tracing) - n_inner;
+            int status = HIT_RUNNING;
+            if (n_inner * schedule >= n_leaf * 4) {
+                if (at_inner) status = WIDE ? hit_inner_step_wide<COUNT>(A, ray, st, cnt) : hit_inner_step<COUNT>(A, ray, st, cnt);
+            } else if (have && !at_inner) status = hit_leaf_step<COUNT, WIDE>(A, ray, st, cnt);
+            if (status == HIT_DONE) {
+                have = false;
+                stcg4(ws.hit + slot, v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv));
+                finished = true;
+            }
+        }
+        /* ---- publish the rays that ended: their samples wait for their bounce in the done queue ---- */
+        const unsigned fin = __ballot_sync(0xffffffffu, finished);
+        if (fin) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd((uint32_t *)&ctrl[PIPE_DONE_TAIL], (uint32_t)__popc(fin));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (finished) {
+                __threadfence(); /* the hit record before the entry that announces it */
+                wp.done_q[base + (uint32_t)__popc(fin & lt_mask)] = slot;
+            }
+        }
+        if (tracing) continue;
+        /* ---- this warp holds no ray: shade a batch of traced samples, if there is one ---- */
+        int got;
+        const uint32_t dbase = pipe_claim(ctrl, PIPE_DONE_HEAD, PIPE_DONE_TAIL, 32, lane, &got);
+        if (got) {
+            idle_polls = 0;
+            bool more = false, mine = lane < got;
+            uint32_t s = 0;
+            if (mine) {
+                s = pipe_wait(done_q, dbase + (uint32_t)lane);
+                const uint32_t gid = sample_ids ? sample_ids[s] : s;
+                uint2 sd = __ldcg(reinterpret_cast<const uint2 *>(seeds) + s);
+                uint32_t seed0 = sd.x, seed1 = sd.y;
+                more = wavefront_shade_sample<COUNT, SOA>(s, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt);
+                if (seed0 != sd.x || seed1 != sd.y) reinterpret_cast<uint2 *>(seeds)[s] = make_uint2(seed0, seed1);
+            }
+            const unsigned staying = __ballot_sync(0xffffffffu, more);
+            const unsigned ended = __ballot_sync(0xffffffffu, mine && !more);
+            if (staying) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd((uint32_t *)&ctrl[PIPE_TRACE_TAIL], (uint32_t)__popc(staying));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (more) {
+                    __threadfence(); /* walk state, seeds and vertex records before the entry that announces the next ray */
+                    wp.trace_q[base + (uint32_t)__popc(staying & lt_mask) - wp.n0] = s;
+                }
+            }
+            if (ended && lane == 0) atomicSub((uint32_t *)&ctrl[PIPE_LIVE], (uint32_t)__popc(ended));
+            continue;
+        }
+        /* ---- nothing to do right now ---- */
+        if (ctrl[PIPE_LIVE] == 0u || ctrl[PIPE_ERROR] != 0u) break;
+        if (++idle_polls > (1u << 22)) { /* watchdog: seconds without work while samples are alive = a lost entry */
+            if (lane == 0) ctrl[PIPE_ERROR] = 1u;
+            break;
+        }
+        __nanosleep(256);
     }
     flush_counters<COUNT>(cnt, counters);
 }
@@ -1343,7 +1504,7 @@ extern "C" int clv_light_image_splat(clv_ctx *c, uint32_t n_entries, uint32_t n_
  * section 5: fused renderer
  * ------------------------------------------------------------------------------------------------------------- */
 /* kernels of a fused pass as the timing interface names them (clv_renderer_kernel_times) */
-enum { TK_FUSED_WALKS = 0, TK_ENUMERATE, TK_RAYS, TK_FINISH, TK_FINALIZE, TK_WALK_TRACE, TK_WALK_SHADE, CLV_TIMED_KERNELS };
+enum { TK_FUSED_WALKS = 0, TK_ENUMERATE, TK_RAYS, TK_FINISH, TK_FINALIZE, TK_WALK_TRACE, TK_WALK_SHADE, TK_WALK_PIPELINE, CLV_TIMED_KERNELS };
 #define CLV_PASS_KERNELS CLV_TIMED_KERNELS
 struct clv_renderer {
     clv_ctx *ctx;
@@ -1384,6 +1545,9 @@ struct clv_renderer {
     float *d_walk_jitter;  /* [n_local][2] */
     uint32_t *d_walk_queue; /* 2 x n_local */
     uint32_t *d_walk_counters; /* CLV_MAX_SLICES x CLV_WALK_COUNTER_WORDS */
+    uint32_t *d_pipe_queues;   /* pipelined walks: trace entries (11 per sample) then done entries (12 per sample) */
+    uint32_t *d_pipe_ctrl;     /* CLV_MAX_SLICES x 8 */
+    int pipe_blocks_per_sm;
     unsigned long long timed_passes;
 };
 
@@ -1400,6 +1564,7 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     dev_free(r->ctx, r->d_tone_image);
     dev_free(r->ctx, r->d_walk_state); dev_free(r->ctx, r->d_walk_jitter); dev_free(r->ctx, r->d_walk_queue);
     dev_free(r->ctx, r->d_walk_counters);
+    dev_free(r->ctx, r->d_pipe_queues); dev_free(r->ctx, r->d_pipe_ctrl);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     clv_accel_destroy(const_cast<clv_accel *>(r->accel)); /* drops the renderer's reference */
     delete r;
@@ -1482,6 +1647,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     TRY(zalloc((void **)&r->d_tone_sum, 16));
     TRY(zalloc((void **)&r->d_tone_image, (size_t)n_pixels * 3));
     r->d_walk_state = nullptr; r->d_walk_jitter = nullptr; r->d_walk_queue = nullptr; r->d_walk_counters = nullptr;
+    r->d_pipe_queues = nullptr; r->d_pipe_ctrl = nullptr; r->pipe_blocks_per_sm = 0;
     TRY(load_seeds(r, h_seeds));
 #undef TRY
     CK(cudaStreamSynchronize(c->stream));
@@ -1543,6 +1709,14 @@ static int ensure_walk_buffers(clv_renderer *r) {
     CK(cudaMemsetAsync(r->d_walk_counters, 0, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t), c->stream));
     return CLV_OK;
 }
+static int ensure_pipe_buffers(clv_renderer *r) {
+    if (r->d_pipe_queues) return CLV_OK;
+    clv_ctx *c = r->ctx;
+    CK(dev_alloc(c, &r->d_pipe_queues, (size_t)r->n_local * 23 * sizeof(uint32_t)));
+    CK(dev_alloc(c, &r->d_pipe_ctrl, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(r->d_pipe_ctrl, 0, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t), c->stream));
+    return CLV_OK;
+}
 
 /* persistent grid of k_walk_trace: every SM filled with the resident blocks of the flavour, never more warps than rays */
 template <typename K>
@@ -1576,11 +1750,43 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
     wq.cursor = wq.count + (CLV_WALK_ROUNDS + 1);
     static_assert(2 * CLV_WALK_ROUNDS + 1 <= CLV_WALK_COUNTER_WORDS, "walk counters");
     Counters *ctr = c->d_counters + COUNTERS_WALK;
-    if (soa) k_walk_init<true><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq);
-    else k_walk_init<false><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq);
+    const bool pipelined = c->walk_mode == 3 || (c->walk_mode == 0 && CLV_PIPELINE_BY_DEFAULT);
+    uint32_t *pipe_ctrl = nullptr;
+    WalkPipe wp;
+    memset(&wp, 0, sizeof wp);
+    if (pipelined) {
+        pipe_ctrl = r->d_pipe_ctrl + (size_t)slice * 8;
+        wp.ctrl = pipe_ctrl;
+        wp.trace_q = r->d_pipe_queues + (size_t)first * 11;
+        wp.done_q = r->d_pipe_queues + n * 11 + (size_t)first * 12;
+        wp.n0 = len;
+        wp.first = first;
+        /* every entry starts as EMPTY; a slot word written into it makes it valid */
+        CK(cudaMemsetAsync(wp.trace_q, 0xff, (size_t)len * 11 * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(wp.done_q, 0xff, (size_t)len * 12 * sizeof(uint32_t), st));
+    }
+    if (soa) k_walk_init<true><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq, pipe_ctrl);
+    else k_walk_init<false><<<GRID(len), CLV_BLOCK, 0, st>>>(first, end, r->d_light_triangles, r->d_light_areas, r->d_light_tri_idx, r->light_count, r->d_materials, r->d_seeds, store, ws, wq, pipe_ctrl);
     LAUNCHED(c);
     int rc = mark(r, st, TK_WALK_SHADE);
     if (rc != CLV_OK) return rc;
+    if (pipelined) {
+        const bool pl = r->accel->large != 0;
+        /* persistent grid: every SM filled once with the resident blocks of the kernel (halved under slices, like the trace
+         * grid), never more warps than samples */
+#define PIPE(CT, SO, LG) k_walk_pipeline<CT, SO, LG>
+#define PIPE_GO(CT, SO, LG) do { \
+            if (!r->pipe_blocks_per_sm) { int per_sm = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PIPE(CT, SO, LG), CLV_BLOCK, 0)); r->pipe_blocks_per_sm = per_sm > 0 ? per_sm : 1; } \
+            const uint64_t resident = std::max<uint64_t>(1, (uint64_t)c->sm_count * (uint64_t)r->pipe_blocks_per_sm / (uint64_t)(sliced ? std::max(1, c->walk_grid_divisor) : 1)); \
+            const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(resident, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK)); \
+            PIPE(CT, SO, LG)<<<pgrid, CLV_BLOCK, 0, st>>>(wp, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr, c->walk_refill_below, c->walk_schedule); } while (0)
+        if (c->counting) { if (soa) { if (pl) PIPE_GO(true, true, 1); else PIPE_GO(true, true, 0); } else { if (pl) PIPE_GO(true, false, 1); else PIPE_GO(true, false, 0); } }
+        else { if (soa) { if (pl) PIPE_GO(false, true, 1); else PIPE_GO(false, true, 0); } else { if (pl) PIPE_GO(false, false, 1); else PIPE_GO(false, false, 0); } }
+#undef PIPE_GO
+#undef PIPE
+        LAUNCHED(c);
+        return mark(r, st, TK_WALK_PIPELINE);
+    }
     /* the trace kernel's flavour follows the scene (not the path layout or the counters): an instrumented run counts
      * the records of the very search the timed run performs */
     const bool tl = r->accel->large != 0;
@@ -1633,8 +1839,9 @@ static int launch_pass(clv_renderer *r) {
     /* stages 1-4 as wavefront rounds or as the megakernel.  The wavefront kernels exist for the ORDERED traversal only (the
      * reference-order mode is a parity instrument, not a product path).  Automatic: see clv_ctx_walk_mode */
     const bool wavefront = r->mode == CLV_TRAVERSE_ORDERED &&
-                           (c->walk_mode == 2 || (c->walk_mode == 0 && CLV_WAVEFRONT_BY_DEFAULT(r->accel->large)));
+                           (c->walk_mode >= 2 || (c->walk_mode == 0 && CLV_WAVEFRONT_BY_DEFAULT(r->accel->large)));
     if (wavefront && (rc = ensure_walk_buffers(r)) != CLV_OK) return rc;
+    if (wavefront && (c->walk_mode == 3 || (c->walk_mode == 0 && CLV_PIPELINE_BY_DEFAULT)) && (rc = ensure_pipe_buffers(r)) != CLV_OK) return rc;
     /* slices: whole blocks each; one slice (everything on the context's stream) when per-kernel events are wanted */
     int slices = c->pass_slices > 0 ? c->pass_slices : (n >= (uint32_t)c->sm_count * 1024u ? 3 : 1);
     if (r->timing) slices = 1;
@@ -1733,7 +1940,7 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
  * k_walk_shade).  < 0 only queries.  Results are bit-identical in both. */
 extern "C" int clv_ctx_walk_mode(clv_ctx *c, int mode, int *current_out) {
     REQUIRE(c, "null ctx");
-    REQUIRE(mode <= 2, "walk mode is 0 (automatic), 1 (megakernel) or 2 (wavefront)");
+    REQUIRE(mode <= 3, "walk mode is 0 (automatic), 1 (megakernel), 2 (wavefront rounds) or 3 (wavefront, pipelined)");
     if (mode >= 0) c->walk_mode = mode;
     if (current_out) *current_out = c->walk_mode;
     return CLV_OK;
@@ -1832,6 +2039,13 @@ extern "C" int clv_renderer_read(clv_renderer *r, int buffer_id, void *h_dst, si
     REQUIRE(r && h_dst, "null");
     clv_ctx *c = r->ctx;
     CK(cudaSetDevice(c->device));
+    if (r->d_pipe_ctrl) { /* the pipelined walk kernel's watchdog: a lost queue entry must not pass as a result */
+        uint32_t ctrl[CLV_MAX_SLICES * 8];
+        CK(cudaMemcpyAsync(ctrl, r->d_pipe_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < CLV_MAX_SLICES; k++)
+            if (ctrl[8 * k + PIPE_ERROR]) return fail(CLV_ERR_CUDA, "k_walk_pipeline gave up waiting for work with %u samples alive (slice %d)", ctrl[8 * k + PIPE_LIVE], k);
+    }
     size_t np = r->n_pixels;
     if (buffer_id <= CLV_BUF_UNIDIRECTIONAL) {
         static const size_t per_pixel[4] = {12, 4, 4, 12};

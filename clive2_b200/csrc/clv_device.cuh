@@ -173,6 +173,23 @@ CLV_HD void prefetch_ref(const V4 *nodes, const V4 *tris, int ref) {
     (void)nodes; (void)tris; (void)ref;
 #endif
 }
+/* 16-byte load / store that bypass L1 (served by L2, the point of coherence between SMs): for records one SM writes and
+ * another reads INSIDE one kernel (walk state and hit records of the pipelined walks) */
+CLV_HD V4 ldcg4(const V4 *p) {
+#if defined(__CUDA_ARCH__)
+    float4 f = __ldcg(reinterpret_cast<const float4 *>(p));
+    return v4(f.x, f.y, f.z, f.w);
+#else
+    return *p;
+#endif
+}
+CLV_HD void stcg4(V4 *p, V4 v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(reinterpret_cast<float4 *>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+    *p = v;
+#endif
+}
 CLV_HD int f2i(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_int(f);
@@ -1755,10 +1772,10 @@ template <> struct SinkOf<false> {
 };
 
 CLV_HD void walk_state_save(const WalkState &ws, uint32_t slot, const WalkRegs &W, int which, int bounce) {
-    ws.s0[slot] = v4(W.o.x, W.o.y, W.o.z, W.ray_tot);
-    ws.s1[slot] = v4(W.d.x, W.d.y, W.d.z, W.carry_imp);
-    ws.s2[slot] = v4(W.rc.x, W.rc.y, W.rc.z, i2f(which | (bounce << WS_BOUNCE_SHIFT) | (W.uni_found ? WS_UNI_FOUND : 0)));
-    if (which) ws.s3[slot] = v4(W.last_stored_color.x, W.last_stored_color.y, W.last_stored_color.z, i2f(W.ray_hit_light));
+    stcg4(ws.s0 + slot, v4(W.o.x, W.o.y, W.o.z, W.ray_tot));
+    stcg4(ws.s1 + slot, v4(W.d.x, W.d.y, W.d.z, W.carry_imp));
+    stcg4(ws.s2 + slot, v4(W.rc.x, W.rc.y, W.rc.z, i2f(which | (bounce << WS_BOUNCE_SHIFT) | (W.uni_found ? WS_UNI_FOUND : 0))));
+    if (which) stcg4(ws.s3 + slot, v4(W.last_stored_color.x, W.last_stored_color.y, W.last_stored_color.z, i2f(W.ray_hit_light)));
 }
 
 /* start of a sample's pass: both generators in the reference's order (light rays, then camera rays: renderer.py:281-282),
@@ -1780,7 +1797,7 @@ template <bool COUNT, bool SOA>
 CLV_HD bool wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *materials, const Camera &c, const AccelView &A,
                                    uint32_t &seed0, uint32_t &seed1, const PathStore &store, const WalkState &ws, Accum *accum,
                                    Cnt<COUNT> &cnt) {
-    const V4 a0 = ws.s0[slot], a1 = ws.s1[slot], a2 = ws.s2[slot], h = ws.hit[slot];
+    const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot), a2 = ldcg4(ws.s2 + slot), h = ldcg4(ws.hit + slot);
     const int flags = f2i(a2.w);
     const int which = flags & WS_CAMERA, bounce = (flags >> WS_BOUNCE_SHIFT) & 7;
     WalkRegs W;
@@ -1793,7 +1810,7 @@ CLV_HD bool wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *
     W.last_stored_color = v3(0, 0, 0);
     W.ray_hit_light = -1;
     if (which) {
-        const V4 a3 = ws.s3[slot];
+        const V4 a3 = ldcg4(ws.s3 + slot);
         W.last_stored_color = xyz(a3);
         W.ray_hit_light = f2i(a3.w);
     }

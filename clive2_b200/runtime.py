@@ -23,7 +23,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "li
 _lib = None
 
 TRAVERSE_REFERENCE_ORDER, TRAVERSE_ORDERED = 0, 1
-WALK_AUTO, WALK_MEGAKERNEL, WALK_WAVEFRONT = 0, 1, 2  # clv_ctx_walk_mode
+WALK_AUTO, WALK_MEGAKERNEL, WALK_WAVEFRONT, WALK_PIPELINE = 0, 1, 2, 3  # clv_ctx_walk_mode
 BUF_SUMMED_IMAGE, BUF_SUMMED_SAMPLE_COUNTS, BUF_SUMMED_SAMPLE_WEIGHTS, BUF_UNIDIRECTIONAL = 0, 1, 2, 3
 BUF_SEEDS, BUF_ACCUM_PACKED, BUF_LIGHT_PATHS, BUF_CAMERA_PATHS, BUF_AGGREGATORS, BUF_PASS_WEIGHT = 4, 5, 6, 7, 8, 9
 
@@ -664,7 +664,7 @@ class FusedRenderer:
     #: kernels of one pass, in launch order
     KERNELS = ("k_fused_walks", "k_connect_enumerate", "k_connect_rays", "k_connect_finish", "k_fused_finalize")
     #: slots of clv_renderer_kernel_times (the walks are either the megakernel or the two wavefront kernels)
-    TIMED = KERNELS + ("k_walk_trace", "k_walk_shade")
+    TIMED = KERNELS + ("k_walk_trace", "k_walk_shade", "k_walk_pipeline")
 
     def __init__(self, device, accel, arrays, seeds, sample_ids=None):
         self.device, self.accel = device, accel

@@ -264,8 +264,8 @@ CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
 /* per-kernel device time of the fused pass: CUDA events recorded on the launch stream after every launch while
  * enabled (the pass then runs as one slice on one stream); `kernel_times` waits and returns the milliseconds accumulated
  * per kernel — slots: 0 k_fused_walks (megakernel walks), 1 k_connect_enumerate, 2 k_connect_rays, 3 k_connect_finish,
- * 4 k_fused_finalize, 5 k_walk_trace (all rounds), 6 k_walk_init + k_walk_shade (all rounds), 7 unused — and the number of
- * passes they cover */
+ * 4 k_fused_finalize, 5 k_walk_trace (all rounds), 6 k_walk_init + k_walk_shade (all rounds), 7 k_walk_pipeline — and the
+ * number of passes they cover */
 #define CLV_TIMED_KERNEL_SLOTS 8
 CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
 CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_KERNEL_SLOTS], uint64_t *passes_out, int reset);
@@ -273,7 +273,9 @@ CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_K
  * a thread per sample (k_fused_walks), or as wavefront rounds: k_walk_init, then 12 x (k_walk_trace: persistent warps
  * that fetch rays from the round's queue as their lanes finish; k_walk_shade: the bounce of every traced ray).  Same
  * results, bit for bit.  mode 0 = automatic (wavefront for scenes whose traversal records exceed the caches; env
- * CLV_WALK_MODE), 1 = megakernel, 2 = wavefront; < 0 only queries. */
+ * CLV_WALK_MODE), 1 = megakernel, 2 = wavefront rounds, 3 = wavefront as ONE pipelined persistent kernel (k_walk_pipeline:
+ * warps trace rays from a queue and, when they hold none, shade traced samples from a second queue — no round
+ * boundaries); < 0 only queries. */
 CLV_API int clv_ctx_walk_mode(clv_ctx *ctx, int mode, int *current_out);
 /* Scheduling knobs of the two ray kernels, for measurement sweeps (none changes a result): "walk_refill_below" /
  * "connect_refill_below" = lanes still holding a ray below which a warp of k_walk_trace / k_connect_rays fetches new

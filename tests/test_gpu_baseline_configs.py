@@ -75,10 +75,18 @@ def test_c2_ggx_transmission_512x512_vs_checker(dev):
     compare_with_checker(dev, a, passes=4)
 
 
-def test_c3_terrain_1m_256x256_vs_checker(dev):
-    """BASELINE.json configs[2]'s scene (1 002 528-triangle mesh, high-occupancy kernel flavours) at 256x256, 2 passes."""
+@pytest.mark.parametrize("walk_mode", [runtime.WALK_AUTO, runtime.WALK_PIPELINE, runtime.WALK_MEGAKERNEL],
+                         ids=["auto", "pipelined", "megakernel"])
+def test_c3_terrain_1m_256x256_vs_checker(dev, walk_mode):
+    """BASELINE.json configs[2]'s scene (1 002 528-triangle mesh, large-scene kernel flavours) at 256x256, 2 passes, under
+    every driver of the walks."""
     a = scene.preset_arrays("bench-terrain-1m", 256, 256)
-    compare_with_checker(dev, a, passes=2, seed=5)
+    before = dev.walk_mode
+    try:
+        dev.walk_mode = walk_mode
+        compare_with_checker(dev, a, passes=2, seed=5)
+    finally:
+        dev.walk_mode = before
 
 
 def test_c4_terrain_10m_160x90_vs_checker(dev):
@@ -92,20 +100,23 @@ def test_c4_terrain_10m_160x90_vs_checker(dev):
     compare_with_checker(dev, a, passes=2, seed=11)
 
 
+@pytest.mark.parametrize("wave_mode", [runtime.WALK_WAVEFRONT, runtime.WALK_PIPELINE], ids=["rounds", "pipelined"])
 @pytest.mark.parametrize("preset,w,h,passes", [("empty", 256, 256, 4), ("bench-spheres", 512, 512, 3)])
-def test_wavefront_walks_at_bench_size_vs_checker_and_megakernel(dev, preset, w, h, passes):
-    """Stages 1-4 as wavefront rounds (k_walk_init / k_walk_trace / k_walk_shade), forced on the cache-resident
-    configurations where the automatic mode keeps the megakernel: same bits as the checker and as the megakernel."""
+def test_wavefront_walks_at_bench_size_vs_checker_and_megakernel(dev, preset, w, h, passes, wave_mode):
+    """Stages 1-4 as wavefront rounds (k_walk_init / k_walk_trace / k_walk_shade) or as the pipelined persistent kernel
+    (k_walk_pipeline), forced on the cache-resident configurations where the automatic mode keeps the megakernel: same
+    bits as the checker and as the megakernel."""
     a = arrays(preset, w, h)
     b = w * h
     before = dev.walk_mode
     try:
-        dev.walk_mode = runtime.WALK_WAVEFRONT
+        dev.walk_mode = wave_mode
         n0 = dev.launch_count
         compare_with_checker(dev, a, passes=passes, seed=77)
-        assert dev.launch_count - n0 > passes * 25  # init + 12 x (trace, shade) + connection + finalize per slice
+        if wave_mode == runtime.WALK_WAVEFRONT:
+            assert dev.launch_count - n0 > passes * 25  # init + 12 x (trace, shade) + connection + finalize per slice
         outs = []
-        for mode in (runtime.WALK_MEGAKERNEL, runtime.WALK_WAVEFRONT):
+        for mode in (runtime.WALK_MEGAKERNEL, wave_mode):
             dev.walk_mode = mode
             sc = scene.scene_from_arrays(a, dev)
             r = Renderer(sc, seeds=seeds_for(b, seed=78), path_records=True)

@@ -24,6 +24,7 @@ ap.add_argument("--config", default="c4")
 ap.add_argument("--passes", type=int, default=8)
 ap.add_argument("--settings", default="mode=1;mode=2")
 ap.add_argument("--mesh-in-memory", action="store_true")
+ap.add_argument("--tile-shard", type=int, default=0, help="time rank 0's shard of a W-way tile sharding (16x16 tiles) instead of the full frame")
 args = ap.parse_args()
 cfg = bench.CONFIGS[args.config]
 arrays = bench.build_arrays(cfg, via_file=not args.mesh_in_memory)
@@ -41,7 +42,11 @@ for setting in args.settings.split(";"):
     dev.pass_slices = slices
     for k, v in kv.items():
         dev.knob(k, int(v))
-    r = Renderer(sc, seeds=seeds)
+    ids = None
+    if args.tile_shard > 1:
+        from clive2_b200 import sharding
+        ids = sharding.tile_ids(cfg["width"], cfg["height"], 0, args.tile_shard, 16)
+    r = Renderer(sc, seeds=seeds, sample_ids=ids)
     for _ in range(3):
         r.run_sample()
     dev.synchronize()
@@ -57,9 +62,10 @@ for setting in args.settings.split(";"):
         r.run_sample()
     km, n = r._fr.kernel_times(reset=True)
     r._fr.kernel_timing(False)
-    state = r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * batch)
+    n_local = batch if ids is None else len(ids)
+    state = r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * n_local)
     same = True if ref_state is None else bool(np.array_equal(ref_state, state))
     ref_state = state if ref_state is None else ref_state
-    print(json.dumps({"config": args.config, "setting": setting, "ms_per_pass": ms, "msamples_per_s": batch / ms / 1e3,
+    print(json.dumps({"config": args.config, "setting": setting, "ms_per_pass": ms, "msamples_per_s": n_local / ms / 1e3, "samples_per_pass": n_local,
                       "kernel_ms": {k: round(v / max(n, 1), 4) for k, v in km.items()}, "same_rng_state_as_first": same}), flush=True)
     r.release()
