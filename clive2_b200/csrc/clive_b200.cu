@@ -66,6 +66,7 @@ struct clv_ctx {
     int trace_blocks_per_sm[2];           /* resident blocks of k_walk_trace (cache-resident / large flavour) */
     int connect_dynamic_fetch, rays_blocks_per_sm[2]; /* k_connect_rays: dynamic work fetch on a persistent grid */
     int finish_cooperative;                           /* k_connect_finish: warp-cooperative form */
+    int pipe_shade_every;                             /* k_walk_pipeline: every k-th block only shades (0: dual-role warps) */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
@@ -136,6 +137,7 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
      * C2 0.95 -> 0.85; C1 126 -> 136 Msamples/s */
     c->connect_dynamic_fetch = getenv("CLV_CONNECT_DYNAMIC") ? atoi(getenv("CLV_CONNECT_DYNAMIC")) : 1;
     c->finish_cooperative = getenv("CLV_FINISH_COOPERATIVE") ? atoi(getenv("CLV_FINISH_COOPERATIVE")) : 0;
+    c->pipe_shade_every = getenv("CLV_PIPE_SHADE_EVERY") ? atoi(getenv("CLV_PIPE_SHADE_EVERY")) : 5;
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -908,6 +910,8 @@ k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, cons
  *   k_walk_shade  one thread per traced ray: BSDF sampling, vertex store, next ray; survivors are appended to the next
  *                 round's queue (one atomicAdd per warp)
  * Same per-ray operations in the same order as the megakernel: bit-identical results. */
+/* control words of the pipelined form (k_walk_pipeline, below) */
+enum { PIPE_TRACE_TAIL = 0, PIPE_TRACE_HEAD, PIPE_TRACE_AVAIL, PIPE_DONE_TAIL, PIPE_DONE_HEAD, PIPE_DONE_AVAIL, PIPE_LIVE, PIPE_ERROR };
 struct WalkQueues {
     uint32_t *q[2];   /* ping-pong lists of sample slots */
     uint32_t *count;  /* [CLV_WALK_ROUNDS + 1]: entries of round r's list (round 0 = every sample of the slice, implicit) */
@@ -923,7 +927,7 @@ k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, con
     const uint32_t id = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x < CLV_WALK_COUNTER_WORDS) wq.count[threadIdx.x] = 0u; /* count[] and cursor[] are one block */
     if (pipe_ctrl && blockIdx.x == 0 && threadIdx.x < 8) /* pipelined form: every sample's first ray is an implicit entry */
-        pipe_ctrl[threadIdx.x] = (threadIdx.x == 0 /* trace tail */ || threadIdx.x == 4 /* live */) ? n_end - first : 0u;
+        pipe_ctrl[threadIdx.x] = (threadIdx.x == PIPE_TRACE_TAIL || threadIdx.x == PIPE_TRACE_AVAIL || threadIdx.x == PIPE_LIVE) ? n_end - first : 0u;
     if (id >= n_end) return;
     uint2 sd = reinterpret_cast<uint2 *>(seeds)[id];
     uint32_t seed0 = sd.x, seed1 = sd.y;
@@ -1047,31 +1051,39 @@ k_walk_shade(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
  * ends when the count of live samples reaches zero.  Same per-ray / per-bounce operations as the other two forms:
  * bit-identical results. */
 struct WalkPipe {
-    uint32_t *ctrl;    /* [8]: 0 trace tail (reserved), 1 trace head (claimed), 2 done tail, 3 done head, 4 live samples, 5 error */
+    uint32_t *ctrl;    /* [8]: per queue (trace, done) tail = reserved, head = claimed, avail = published and not claimed;
+                        * live samples; error */
     uint32_t *trace_q; /* explicit entries: index i >= n0 lives at trace_q[i - n0]; capacity 11 * n0 */
     uint32_t *done_q;  /* capacity 12 * n0 */
     uint32_t n0, first;
 };
 #define CLV_PIPE_EMPTY 0xffffffffu
-enum { PIPE_TRACE_TAIL = 0, PIPE_TRACE_HEAD, PIPE_DONE_TAIL, PIPE_DONE_HEAD, PIPE_LIVE, PIPE_ERROR };
 
-/* claim up to `want` entries of a queue: returns the first claimed index and the number claimed (0 when nothing is
- * available or another warp won the race; the caller simply tries again later).  Never claims beyond the tail. */
-__device__ __forceinline__ uint32_t pipe_claim(volatile uint32_t *ctrl, int head_word, int tail_word, int want, int lane, int *got) {
+/* Claim up to `want` entries of a queue (q = PIPE_TRACE_TAIL or PIPE_DONE_TAIL: tail, head, avail follow each other):
+ * returns the first claimed index and the number claimed.  `avail` counts entries that are published and not claimed; a
+ * claimer subtracts what it wants, keeps what the old value covered and gives the rest back — two or three atomics, no
+ * retry loop.  (A compare-and-swap on the head, the first version, lets ONE of thousands of contending warps succeed per
+ * memory round trip: the whole kernel then ran at one claim per microsecond.) */
+__device__ __forceinline__ uint32_t pipe_claim(volatile uint32_t *ctrl, int q, int want, int lane, int *got) {
     uint32_t base = 0;
     int k = 0;
-    if (lane == 0) {
-        const uint32_t head = ctrl[head_word], tail = ctrl[tail_word];
-        const int avail = (int)(tail - head);
-        if (avail > 0) {
-            k = min(want, avail);
-            if (atomicCAS((uint32_t *)&ctrl[head_word], head, head + (uint32_t)k) == head) base = head;
-            else k = 0;
-        }
+    if (lane == 0 && (int)ctrl[q + 2] > 0) { /* a look first: no atomics on an empty queue */
+        const int old = atomicSub((int *)const_cast<uint32_t *>(ctrl) + q + 2, want);
+        k = old < 0 ? 0 : (old < want ? old : want);
+        if (k < want) atomicAdd((int *)const_cast<uint32_t *>(ctrl) + q + 2, want - k);
+        if (k > 0) base = atomicAdd(const_cast<uint32_t *>(ctrl) + q + 1, (uint32_t)k);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     *got = __shfl_sync(0xffffffffu, k, 0);
     return base;
+}
+/* publish `count` entries the warp has just written (every writing lane fenced before its store) */
+__device__ __forceinline__ void pipe_publish(volatile uint32_t *ctrl, int q, int count, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAdd((int *)const_cast<uint32_t *>(ctrl) + q + 2, count);
+    }
 }
 /* the slot word of a claimed entry (the producer reserved it before us and writes it a few instructions later) */
 __device__ __forceinline__ uint32_t pipe_wait(const volatile uint32_t *q, uint32_t index) {
@@ -1084,9 +1096,21 @@ __device__ __forceinline__ uint32_t pipe_wait(const volatile uint32_t *q, uint32
 template <bool COUNT, bool SOA, int LARGE>
 __global__ void __launch_bounds__(CLV_BLOCK, 1024 / CLV_BLOCK)
 k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materials, const Camera *camera, AccelView A,
-                uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters, int refill_below, int schedule) {
+                uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters, int refill_below, int schedule,
+                int shade_every) {
     constexpr bool WIDE = LARGE ? (CLV_TRACE_WIDE_LARGE != 0) : (CLV_TRACE_WIDE != 0);
-    const int lane = threadIdx.x & 31;
+    /* Roles.  shade_every = 0: every warp does both jobs, shading only while it holds no ray — each batch of rays then ends
+     * with the warp draining lane by lane before it may shade (measured: 1.5x slower than the round form).  shade_every =
+     * k > 0: every k-th block only shades, the others only trace and refill their lanes whenever the trace queue has
+     * entries, as in the round form; blocks of both roles alternate in launch order, so any resident prefix of the grid
+     * holds both (the grid never exceeds what the device can hold at once). */
+    const bool shade_role = shade_every > 0 && (blockIdx.x % (unsigned)shade_every) == (unsigned)shade_every - 1u;
+    const bool trace_role = shade_every <= 0 || !shade_role;
+    /* per warp: rays fetched from the trace queue 32 at a time and handed to the lanes without further atomics, and the
+     * slots of finished rays collected until a batch is worth one reservation in the done queue.  (One global atomic per
+     * refill and per finished ray — 10^9 a second on two addresses — made the first version of this kernel 80x slower.) */
+    __shared__ uint32_t in_buf[CLV_WARPS_PER_BLOCK][32], out_buf[CLV_WARPS_PER_BLOCK][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     volatile uint32_t *ctrl = wp.ctrl;
     const volatile uint32_t *trace_q = wp.trace_q, *done_q = wp.done_q;
@@ -1096,29 +1120,59 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
     StackEntry st[CLV_HIT_STACK(WIDE)];
     bool have = false;
     uint32_t slot = 0;
-    unsigned idle_polls = 0;
-    int skip_polls = 0; /* warp-uniform: iterations to go before the trace queue is looked at again after it was found dry */
+    unsigned idle_polls = 0, idle_sleep = 128;
+    int in_pos = 0, in_count = 0, out_count = 0; /* warp-uniform */
+    int skip_polls = 0, backoff = 1;             /* warp-uniform: iterations until the global trace queue is looked at again */
+    auto flush_done = [&]() { /* publish the collected slots of finished rays (their hit records are fenced already) */
+        if (out_count == 0) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd((uint32_t *)&ctrl[PIPE_DONE_TAIL], (uint32_t)out_count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < out_count) {
+            __threadfence();
+            wp.done_q[base + (uint32_t)lane] = out_buf[wib][lane];
+        }
+        pipe_publish(ctrl, PIPE_DONE_TAIL, out_count, lane);
+        out_count = 0;
+    };
     for (;;) {
         const unsigned holding = __ballot_sync(0xffffffffu, have);
-        bool finished = false; /* this lane's ray ended in this iteration: its hit record is written, publish the slot */
-        /* ---- refill: idle lanes take rays from the trace queue ---- */
-        if (skip_polls > 0) skip_polls--;
-        else if (__popc(holding) < refill_below) {
-            const unsigned idle = ~holding;
-            int got;
-            const uint32_t base = pipe_claim(ctrl, PIPE_TRACE_HEAD, PIPE_TRACE_TAIL, __popc(idle), lane, &got);
-            const int rank = __popc(idle & lt_mask);
-            if (!have && rank < got) {
-                const uint32_t index = base + (uint32_t)rank;
-                slot = index < wp.n0 ? wp.first + index : pipe_wait(trace_q, index - wp.n0);
-                const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
-                ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
-                cnt.ray_ref();
-                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) have = true;
-                else { stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f)); finished = true; }
+        bool finished = false; /* this lane's ray ended in this iteration */
+        /* ---- refill the lanes from the warp's fetched entries; fetch 32 more when those are used up ---- */
+        if (trace_role && __popc(holding) < refill_below) {
+            if (in_pos == in_count) {
+                if (skip_polls > 0) skip_polls--;
+                else {
+                    int got;
+                    const uint32_t base = pipe_claim(ctrl, PIPE_TRACE_TAIL, 32, lane, &got);
+                    if (got) {
+                        if (lane < got) {
+                            const uint32_t index = base + (uint32_t)lane;
+                            in_buf[wib][lane] = index < wp.n0 ? wp.first + index : pipe_wait(trace_q, index - wp.n0);
+                        }
+                        __syncwarp();
+                        in_pos = 0; in_count = got;
+                        idle_polls = 0; idle_sleep = 128; backoff = 1;
+                    } else {
+                        skip_polls = backoff;
+                        backoff = min(backoff * 2, 64);
+                    }
+                }
             }
-            if (got) idle_polls = 0;
-            else if (holding) skip_polls = 3; /* a look at the queue is an L2 round trip on the critical path of every lane */
+            if (in_pos < in_count) {
+                const unsigned idle = ~holding;
+                const int rank = __popc(idle & lt_mask);
+                const int take = min(__popc(idle), in_count - in_pos);
+                if (!have && rank < take) {
+                    slot = in_buf[wib][in_pos + rank];
+                    const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
+                    ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
+                    cnt.ray_ref();
+                    if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) have = true;
+                    else { stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f)); finished = true; }
+                }
+                in_pos += take;
+            }
         }
         const unsigned tracing = __ballot_sync(0xffffffffu, have);
         if (tracing) {
@@ -1136,23 +1190,29 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
                 finished = true;
             }
         }
-        /* ---- publish the rays that ended: their samples wait for their bounce in the done queue ---- */
+        /* ---- collect the rays that ended ---- */
         const unsigned fin = __ballot_sync(0xffffffffu, finished);
         if (fin) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd((uint32_t *)&ctrl[PIPE_DONE_TAIL], (uint32_t)__popc(fin));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (out_count + __popc(fin) > 32) flush_done();
             if (finished) {
-                __threadfence(); /* the hit record before the entry that announces it */
-                wp.done_q[base + (uint32_t)__popc(fin & lt_mask)] = slot;
+                __threadfence(); /* the hit record before anything that announces it */
+                out_buf[wib][out_count + __popc(fin & lt_mask)] = slot;
             }
+            __syncwarp();
+            out_count += __popc(fin);
+            if (out_count >= 24) flush_done();
         }
         if (tracing) continue;
-        /* ---- this warp holds no ray: shade a batch of traced samples, if there is one ---- */
-        int got;
-        const uint32_t dbase = pipe_claim(ctrl, PIPE_DONE_HEAD, PIPE_DONE_TAIL, 32, lane, &got);
+        /* ---- this warp holds no ray ---- */
+        flush_done();
+        if (in_pos < in_count) continue; /* fetched entries left: hand them out first */
+        /* shade a batch of traced samples, if there is one */
+        int got = 0;
+        uint32_t dbase = 0;
+        if (shade_every <= 0 || shade_role) dbase = pipe_claim(ctrl, PIPE_DONE_TAIL, 32, lane, &got);
         if (got) {
-            idle_polls = 0;
+            idle_polls = 0; idle_sleep = 128;
+            skip_polls = 0; backoff = 1; /* new rays are about to appear */
             bool more = false, mine = lane < got;
             uint32_t s = 0;
             if (mine) {
@@ -1173,17 +1233,27 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
                     __threadfence(); /* walk state, seeds and vertex records before the entry that announces the next ray */
                     wp.trace_q[base + (uint32_t)__popc(staying & lt_mask) - wp.n0] = s;
                 }
+                pipe_publish(ctrl, PIPE_TRACE_TAIL, __popc(staying), lane);
             }
             if (ended && lane == 0) atomicSub((uint32_t *)&ctrl[PIPE_LIVE], (uint32_t)__popc(ended));
             continue;
         }
-        /* ---- nothing to do right now ---- */
-        if (ctrl[PIPE_LIVE] == 0u || ctrl[PIPE_ERROR] != 0u) break;
-        if (++idle_polls > (1u << 22)) { /* watchdog: seconds without work while samples are alive = a lost entry */
+        /* ---- nothing to do right now: back off (thousands of idle warps polling one line starve the warps that work) ---- */
+        {
+            uint2 le = make_uint2(0u, 0u);
+            if (lane == 0) le = __ldcv(reinterpret_cast<const uint2 *>(const_cast<const uint32_t *>(ctrl) + PIPE_LIVE));
+            le.x = __shfl_sync(0xffffffffu, le.x, 0);
+            le.y = __shfl_sync(0xffffffffu, le.y, 0);
+            if (le.x == 0u || le.y != 0u) break;
+        }
+        idle_polls += idle_sleep >> 7;
+        if (idle_polls > (1u << 24)) { /* watchdog: ~2 s asleep without work while samples are alive = a lost entry */
             if (lane == 0) ctrl[PIPE_ERROR] = 1u;
             break;
         }
-        __nanosleep(256);
+        skip_polls = 0; /* idle: look at the trace queue on the next iteration */
+        __nanosleep(idle_sleep);
+        idle_sleep = min(idle_sleep * 2u, 16384u);
     }
     flush_counters<COUNT>(cnt, counters);
 }
@@ -1779,7 +1849,7 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
             if (!r->pipe_blocks_per_sm) { int per_sm = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PIPE(CT, SO, LG), CLV_BLOCK, 0)); r->pipe_blocks_per_sm = per_sm > 0 ? per_sm : 1; } \
             const uint64_t resident = std::max<uint64_t>(1, (uint64_t)c->sm_count * (uint64_t)r->pipe_blocks_per_sm / (uint64_t)(sliced ? std::max(1, c->walk_grid_divisor) : 1)); \
             const unsigned pgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(resident, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK)); \
-            PIPE(CT, SO, LG)<<<pgrid, CLV_BLOCK, 0, st>>>(wp, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr, c->walk_refill_below, c->walk_schedule); } while (0)
+            PIPE(CT, SO, LG)<<<pgrid, CLV_BLOCK, 0, st>>>(wp, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr, c->walk_refill_below, c->walk_schedule, c->pipe_shade_every); } while (0)
         if (c->counting) { if (soa) { if (pl) PIPE_GO(true, true, 1); else PIPE_GO(true, true, 0); } else { if (pl) PIPE_GO(true, false, 1); else PIPE_GO(true, false, 0); } }
         else { if (soa) { if (pl) PIPE_GO(false, true, 1); else PIPE_GO(false, true, 0); } else { if (pl) PIPE_GO(false, false, 1); else PIPE_GO(false, false, 0); } }
 #undef PIPE_GO
@@ -1927,6 +1997,7 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
     else if (!strcmp(name, "connect_dynamic_fetch")) slot = &c->connect_dynamic_fetch;
     else if (!strcmp(name, "walk_grid_divisor")) slot = &c->walk_grid_divisor;
     else if (!strcmp(name, "finish_cooperative")) slot = &c->finish_cooperative;
+    else if (!strcmp(name, "pipe_shade_every")) slot = &c->pipe_shade_every;
     else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
     if (previous) *previous = *slot;
     if (value >= 0) {
