@@ -21,8 +21,9 @@ Prints ONE JSON line (rank 0):
 `--impl reference` times that CPU code as the reference arm (same config / metric / unit).
 
 N > 1 (torchrun, one rank per GPU): STRONG scaling of one frame.  The K passes of the frame are split over the GPUs by
-sample pass and by image tile (clive2_b200.sharding.shard_plan: pass groups = largest divisor of N that divides K, the
-rest by 16x16 tiles), replicated scene, and ONE NCCL reduce of the packed float accumulators closes the timed region.
+sample pass and by image tile (clive2_b200.sharding.frame_plan: every GPU renders K // N full-frame passes from its own
+RNG streams, the K % N passes left over are shared out as pass groups x 16x16-tile groups), replicated scene, and ONE NCCL
+reduce of the packed float accumulators closes the timed region.
 Extra keys carry the pure tile-sharded and the weak pass-sharded figures measured in the same run.
 """
 import argparse
@@ -208,14 +209,13 @@ def seeds_for(batch, stream):
     return s
 
 
-def config_dict(cfg, arrays_or_none, world, plan):
+def config_dict(cfg, arrays_or_none, world, plan=None):
     """The `config` object, identical in both arms (the driver compares them)."""
-    tile_groups, pass_groups = plan
     if world == 1:
         par = "single GPU"
     else:
-        par = (f"one frame on {world} GPUs: {pass_groups} pass group(s) x {tile_groups} tile group(s) (16x16 tiles, rows "
-               f"rotated), replicated scene, one NCCL reduce of the float accumulators")
+        par = (f"one frame on {world} GPUs: its sample passes dealt to the GPUs whole where they divide, the remainder split "
+               f"by 16x16 image tile (clive2_b200.sharding.frame_plan), replicated scene, one NCCL reduce of the float accumulators")
     batch = cfg["width"] * cfg["height"]
     work = (768 + 200 + 128) * batch
     return {"workload": cfg["workload"], "width": cfg["width"], "height": cfg["height"], "samples_per_step": batch,
@@ -362,28 +362,36 @@ def run_ours(args, cfg, rank, local_rank, world):
     t_up = time.perf_counter()
     sc = scene.scene_from_arrays(arrays, dev)
 
-    # ---- how this rank takes part in the frame ----------------------------------------------------------------------
+    # ---- how this rank takes part in the frame: one or two phases (sharding.frame_plan) ------------------------------------
     if world == 1:
-        ids, seed_stream, my_passes, plan = None, 0, K, (1, 1)
-        if args.tile:
-            tw, th = (int(x) for x in args.tile.lower().split("x"))
-            ids = sharding.tiled_order(width, height, tw, th)
+        phases = [(K, 1, 1)]
     elif args.shard == "tile":
-        ids, seed_stream, my_passes, plan = sharding.tile_ids(width, height, rank, world, 16), 0, K, (world, 1)
+        phases = [(K, world, 1)]
     elif args.shard == "pass":
         if K % world:
             raise SystemExit(f"--shard pass needs --steps divisible by the number of GPUs ({K} % {world})")
-        ids, seed_stream, my_passes, plan = None, rank, K // world, (1, world)
+        phases = [(K // world, 1, world)]
     else:
-        ids, seed_stream, my_passes, tg, pg = sharding.hybrid_shard(width, height, rank, world, K, 16)
-        plan = (tg, pg)
-    seeds = seeds_for(batch, seed_stream)
-    r = Renderer(sc, seeds=seeds, sample_ids=ids)
+        phases = sharding.frame_plan(world, K)
+    parts = []
+    for i, (passes, tile_groups, pass_groups) in enumerate(phases):
+        t, pgroup = rank % tile_groups, rank // tile_groups
+        ids = sharding.tile_ids(width, height, t, tile_groups, 16) if tile_groups > 1 else None
+        if world == 1 and args.tile:
+            tw, th = (int(x) for x in args.tile.lower().split("x"))
+            ids = sharding.tiled_order(width, height, tw, th)
+        seeds_i = seeds_for(batch, 0 if world == 1 else 100 * i + pgroup)  # own RNG streams per pass group and phase
+        parts.append(dict(passes=passes, ids=ids, seeds=seeds_i, n_local=batch if ids is None else len(ids),
+                          r=Renderer(sc, seeds=seeds_i, sample_ids=ids)))
     dev.synchronize()
     t_up = time.perf_counter() - t_up
+    r = parts[0]["r"]                      # phase 0 = the larger share of the work: per-kernel timing and e2e use it
+    my_passes = sum(pt["passes"] for pt in parts)
+    my_samples = sum(pt["passes"] * pt["n_local"] for pt in parts)
+    n_local = parts[0]["n_local"]
+    plan = (phases[-1][1], phases[-1][2])
     accel = dev.accel(sc.boxes, sc.triangles)
     accel_stats = accel.stats()
-    n_local = batch if ids is None else len(ids)
     extras_err = {}
     l2_read_gbs = hbm_read_gbs = None
     if rank == 0:
@@ -395,25 +403,32 @@ def run_ours(args, cfg, rank, local_rank, world):
 
     # ---- 1. instrumented run: work counters of exactly the passes that will be timed (same seeds => same work) ----
     dev.counters_enable(True)
-    for _ in range(W):
-        r.run_sample()
+    for pt in parts:
+        for _ in range(W):
+            pt["r"].run_sample()
     dev.counters(reset=True)
-    for _ in range(my_passes):
+    for _ in range(parts[0]["passes"]):
         r.run_sample()
-    counters = dev.counters(reset=True, per_class=True)
+    counters = dev.counters(reset=True, per_class=True)  # phase 0 only: what the per-kernel roofline figures refer to
+    for pt in parts[1:]:
+        for _ in range(pt["passes"]):
+            pt["r"].run_sample()
+    counters_rest = dev.counters(reset=True, per_class=True)
     dev.counters_enable(False)
-    r._fr.reset(seeds)
+    for pt in parts:
+        pt["r"]._fr.reset(pt["seeds"])
 
     stream = torch.cuda.ExternalStream(dev.stream, device=tdev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
 
-    def timed_passes(rend, n_passes, with_reduce):
-        """(ms of this rank's passes, ms of the reduce, launches): `n_passes` passes + one reduce between CUDA events on the
-        launch stream after W warm-up passes."""
-        for _ in range(W):
-            rend.run_sample()
+    def timed_passes(work, with_reduce):
+        """(ms of this rank's passes, ms of the reduce, launches): the passes of `work` = [(renderer, passes), ...] + one
+        reduce between CUDA events on the launch stream, after W warm-up passes of every renderer."""
+        for rend, _ in work:
+            for _ in range(W):
+                rend.run_sample()
         dev.synchronize()
         if world > 1 and with_reduce:
             with torch.cuda.stream(stream):  # the first reduce on a communicator sets up its channels: not timed
@@ -427,14 +442,17 @@ def run_ours(args, cfg, rank, local_rank, world):
         n0 = dev.launch_count
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
-        for _ in range(n_passes):
-            rend.run_sample()
+        for rend, n_passes in work:
+            for _ in range(n_passes):
+                rend.run_sample()
         e1.record(stream)
         if world > 1 and with_reduce:
             # issued with the renderer's stream as torch's current stream: NCCL's stream waits for the passes and the
             # renderer's stream for the reduce, all on the device (no host synchronisation inside the timed region)
             with torch.cuda.stream(stream):
-                acc = torch.as_tensor(rend.accumulator_buffer(), device=tdev)
+                acc = torch.as_tensor(work[0][0].accumulator_buffer(), device=tdev)
+                for rend, _ in work[1:]:  # a second phase has its own accumulators: one sum per GPU before the one reduce
+                    acc += torch.as_tensor(rend.accumulator_buffer(), device=tdev)
                 dist.reduce(acc, dst=0)
         e2.record(stream)
         dev.synchronize()
@@ -452,7 +470,7 @@ def run_ours(args, cfg, rank, local_rank, world):
         return max(v), sum(v) / len(v)
 
     # ---- 2. device-resident timed run -------------------------------------------------------------------------------
-    pass_ms, reduce_ms, launches = timed_passes(r, my_passes, True)
+    pass_ms, reduce_ms, launches = timed_passes([(pt["r"], pt["passes"]) for pt in parts], True)
     elapsed_ms, _ = over_ranks(pass_ms + reduce_ms)
     pass_ms_max, pass_ms_mean = over_ranks(pass_ms)
     reduce_ms_max, _ = over_ranks(reduce_ms)
@@ -461,7 +479,7 @@ def run_ours(args, cfg, rank, local_rank, world):
     # launch stream.  With events requested the pass runs as ONE slice on ONE stream (in the timed region above the
     # slices of a pass overlap on several streams, where "the duration of a kernel" is not defined).
     r._fr.kernel_timing(True)
-    for _ in range(my_passes):
+    for _ in range(parts[0]["passes"]):
         r.run_sample()
     kernel_ms, timed = r._fr.kernel_times(reset=True)
     r._fr.kernel_timing(False)
@@ -470,9 +488,9 @@ def run_ours(args, cfg, rank, local_rank, world):
     alt = {}
     if world > 1 and args.shard == "auto" and not args.no_alternatives:
         try:
-            if plan != (world, 1):
+            if phases != [(K, world, 1)]:
                 rt = Renderer(sc, seeds=seeds_for(batch, 0), sample_ids=sharding.tile_ids(width, height, rank, world, 16))
-                p_ms, r_ms, _ = timed_passes(rt, K, True)
+                p_ms, r_ms, _ = timed_passes([(rt, K)], True)
                 t_max, _ = over_ranks(p_ms + r_ms)
                 pm, pa = over_ranks(p_ms)
                 alt["tile_sharded"] = {"value": batch * K / (t_max * 1e-3) / 1e6, "unit": "Msamples/s", "scaling": "strong",
@@ -480,8 +498,8 @@ def run_ours(args, cfg, rank, local_rank, world):
                                        "what": f"every pass of the frame split over {world} GPUs by 16x16 tile "
                                                f"({batch // world} samples per GPU and pass), same RNG streams as 1 GPU"}
                 rt.release()
-            rp = Renderer(sc, seeds=seeds_for(batch, 100 + rank))
-            p_ms, r_ms, _ = timed_passes(rp, K, True)
+            rp = Renderer(sc, seeds=seeds_for(batch, 500 + rank))
+            p_ms, r_ms, _ = timed_passes([(rp, K)], True)
             t_max, _ = over_ranks(p_ms + r_ms)
             alt["pass_sharded_weak"] = {"value": batch * K * world / (t_max * 1e-3) / 1e6, "unit": "Msamples/s",
                                         "scaling": "weak", "ms_per_step": t_max / K,
@@ -498,26 +516,29 @@ def run_ours(args, cfg, rank, local_rank, world):
     h_image = runtime.PinnedArray((height, width, 3), np.uint8)
     h_seeds = runtime.PinnedArray((batch, 2), np.uint32)
     h_seeds_b = runtime.PinnedArray((batch, 2), np.uint32)
-    h_seeds.array[:] = seeds
-    h_seeds_b.array[:] = seeds_for(batch, seed_stream + 1000)
+    h_seeds.array[:] = parts[0]["seeds"]
+    h_seeds_b.array[:] = seeds_for(batch, 2000 + rank)
     host_seed_buffers = (h_seeds, h_seeds_b)  # fresh host-side RNG state every step, no host arithmetic in the loop
 
-    def timed_e2e(step):
-        r._fr.reset(seeds)
-        for k in range(W):
-            step(host_seed_buffers[k & 1])
+    def timed_e2e(call):
+        """Every pass of this rank's share of the frame through the public call `call(renderer, host seeds)`."""
+        for pt in parts:
+            pt["r"]._fr.reset(pt["seeds"])
+            for k in range(W):
+                call(pt["r"], host_seed_buffers[k & 1])
         dev.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for k in range(my_passes):
-            step(host_seed_buffers[k & 1])
+        for pt in parts:
+            for k in range(pt["passes"]):
+                call(pt["r"], host_seed_buffers[k & 1])
         dev.synchronize()
         return over_ranks(time.perf_counter() - t0)[0]
 
-    e2e_s = timed_e2e(lambda hs: r.run_sample_preview(hs, h_image))
+    e2e_s = timed_e2e(lambda rr, hs: rr.run_sample_preview(hs, h_image))
     checksum = int(h_image.array.astype(np.int64).sum())
-    e2e_acc_s = timed_e2e(lambda hs: r.run_sample_e2e(hs, h_accum))
+    e2e_acc_s = timed_e2e(lambda rr, hs: rr.run_sample_e2e(hs, h_accum))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- 4. image error against the CPU reference (N = 1) -----------------------------------------------------------------
@@ -532,13 +553,14 @@ def run_ours(args, cfg, rank, local_rank, world):
         samples = batch * K
         value = samples / (elapsed_ms * 1e-3) / 1e6
         e2e_value = samples / e2e_s / 1e6
-        tot = {k: counters["walk"][k] + counters["connect"][k] for k in counters["walk"]}
+        tot = {k: counters["walk"][k] + counters["connect"][k] + counters_rest["walk"][k] + counters_rest["connect"][k]
+               for k in counters["walk"]}
         peak_hbm, peak_src = measured_peaks()
         np_ = max(timed, 1)
         # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
         launches_of = {"k_walk_trace": 12, "k_walk_shade": 13 if "k_walk_trace" in kernel_ms else 1}  # per pass; every other kernel once
-        cw, cc = ({k: v / max(my_passes, 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
+        cw, cc = ({k: v / max(parts[0]["passes"], 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
         NBT = 128 if accel_stats.get("trace_uses_wide") else 64  # ... and the wavefront trace kernel
@@ -613,6 +635,8 @@ def run_ours(args, cfg, rank, local_rank, world):
             "config": config_dict(cfg, arrays, world, plan),
             "run": {"triangles": int(len(arrays.triangles)), "boxes": int(len(arrays.boxes)), "accel_bytes": accel_bytes,
                     "bvh_levels": {"binary": accel_stats.get("binary_depth"), "four_wide": accel_stats.get("wide_depth")},
+                    "phases": [{"passes_per_gpu": pa, "tile_groups": tg, "pass_groups": pg, "samples_per_pass_per_gpu": pt["n_local"]}
+                               for (pa, tg, pg), pt in zip(phases, parts)],
                     "samples_per_pass_per_gpu": n_local, "passes_per_gpu": my_passes,
                     "launches_per_pass": launches // max(my_passes, 1),
                     "kernel_flavour": ("high-occupancy (traversal records exceed the caches)"
@@ -626,19 +650,19 @@ def run_ours(args, cfg, rank, local_rank, world):
                     "rank_pass_ms_max": pass_ms_max, "rank_pass_ms_mean": pass_ms_mean,
                     "rank_pass_ms_max_over_mean": pass_ms_max / max(pass_ms_mean, 1e-9),
                     "reduce_ms": reduce_ms_max, "reduce_bytes": batch * 32 if world > 1 else 0},
-            "mrays_per_s": value * tot["rays_ref"] / max(my_passes, 1) / n_local,
-            "rays_per_sample": tot["rays_ref"] / max(my_passes, 1) / n_local,
+            "mrays_per_s": value * tot["rays_ref"] / max(my_samples, 1),
+            "rays_per_sample": tot["rays_ref"] / max(my_samples, 1),
             "rays_definition": "a ray = one traverse_bvh invocation the reference makes for the same paths (SURVEY.md 8d: "
                                "closest hits of the walks, shadow rays, projections), counted by device counters of an "
                                "instrumented run of the same passes (rank 0's share at N > 1); mrays_per_s = value x "
                                "rays_per_sample",
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": n_local * 8,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": my_samples * 8 // max(my_passes, 1),
                     "d2h_bytes_per_step": batch * 3, "ms_per_step": e2e_s / K * 1e3, "checksum": checksum,
                     "api": "Renderer.run_sample_preview -> clv_renderer_run_sample_preview: pinned host seeds in, one "
                            "pass, device tone map, uint8 preview image out (render.py:31-37)"},
             "e2e_accumulators": {"value": samples / e2e_acc_s / 1e6, "unit": "Msamples/s",
-                                 "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": batch * 32,
+                                 "h2d_bytes_per_step": my_samples * 8 // max(my_passes, 1), "d2h_bytes_per_step": batch * 32,
                                  "api": "Renderer.run_sample_e2e: seeds in, packed float accumulators [H][W][8] out"},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -658,7 +682,8 @@ def run_ours(args, cfg, rank, local_rank, world):
 
     for x in (h_seeds, h_seeds_b, h_accum, h_image):
         x.release()
-    r.release()
+    for pt in parts:
+        pt["r"].release()
     sc.release()
     dev.release()
     if world > 1:
@@ -709,7 +734,7 @@ def main():
     ap.add_argument("--no-alternatives", action="store_true", help="N > 1: skip the pure tile / weak pass measurements")
     ap.add_argument("--mesh-in-memory", action="store_true", help="c3/c4: do not round-trip the mesh through OBJ/PLY")
     ap.add_argument("--shard", choices=("auto", "pass", "tile"), default="auto",
-                    help="N > 1: 'auto' = pass groups x tile groups (sharding.shard_plan, default), 'tile' = every pass split "
+                    help="N > 1: 'auto' = whole passes per GPU + the remainder as pass groups x tile groups (sharding.frame_plan, default), 'tile' = every pass split "
                          "by 16x16 tiles, 'pass' = passes dealt to the GPUs (needs steps % N == 0); all strong scaling")
     ap.add_argument("--tile", default=os.environ.get("CLV_BENCH_TILE", ""),
                     help="N = 1: trace samples in tiles of WxH pixels per warp-sized group (e.g. 8x4); default row-major")

@@ -25,6 +25,22 @@ def test_tiles_partition_the_frame():
         sharding.tile_ids(8, 8, 2, 2)
 
 
+def test_frame_plan_covers_every_pass_of_the_frame_exactly_once():
+    """Every phase (passes per GPU, tile groups, pass groups) uses all GPUs, and the passes add up: a GPU's passes count 1 /
+    tile_groups of a frame each."""
+    for world in (1, 2, 3, 4, 8):
+        for steps in (1, 2, 3, 5, 8, 16, 20, 21, 24, 100):
+            phases = sharding.frame_plan(world, steps)
+            total = 0.0
+            for passes, tile_groups, pass_groups in phases:
+                assert tile_groups * pass_groups == world and passes >= 1
+                total += passes * pass_groups  # whole-frame passes rendered by this phase (tile groups share one pass)
+            assert total == steps, (world, steps, phases)
+    assert sharding.frame_plan(8, 20) == [(2, 1, 8), (1, 2, 4)]
+    assert sharding.frame_plan(4, 20) == [(5, 1, 4)]
+    assert sharding.frame_plan(8, 3) == [(3, 8, 1)]
+
+
 def test_rank_seeds_are_distinct_and_nonzero():
     a, b = sharding.rank_seeds(1000, 5, 0), sharding.rank_seeds(1000, 5, 1)
     assert (a != 0).all() and (b != 0).all() and (a != b).mean() > 0.99
