@@ -286,6 +286,12 @@ extern "C" int clv_host_free(void *h_ptr) {
 #ifndef CLV_WAVEFRONT_BY_DEFAULT
 #define CLV_WAVEFRONT_BY_DEFAULT(large_scene) (large_scene)
 #endif
+/* ... and how many samples a pass (of this renderer: a tile shard has fewer) needs for the wavefront form to pay: every
+ * round ends with a tail of a few long rays whose length does not shrink with the shard.  C4, samples per pass 2 073 600 /
+ * 1 036 800 / 259 200: wavefront 14.7 / 9.2 / 5.2 ms of walks, megakernel 18.9 / ~9.5 / 3.4 */
+#ifndef CLV_WAVEFRONT_MIN_SAMPLES
+#define CLV_WAVEFRONT_MIN_SAMPLES (600u * 1024u)
+#endif
 /* ... and whether the wavefront walks then run as one pipelined kernel (1) or as 12 rounds of trace + shade (0) */
 #ifndef CLV_PIPELINE_BY_DEFAULT
 #define CLV_PIPELINE_BY_DEFAULT 0
@@ -1806,7 +1812,7 @@ static int trace_grid(clv_ctx *c, K kernel, int flavour, uint32_t n_rays, bool s
 
 /* stages 1-4 of the samples [first, end) as wavefront rounds on `st` */
 static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, uint32_t first, uint32_t end, const uint32_t *ids,
-                                  const PathStore &store, bool soa, bool large, bool sliced) {
+                                  const PathStore &store, bool soa, bool /*large: the trace flavour follows the scene*/, bool sliced) {
     clv_ctx *c = r->ctx;
     const uint32_t len = end - first;
     const size_t n = r->n_local;
@@ -1909,7 +1915,8 @@ static int launch_pass(clv_renderer *r) {
     /* stages 1-4 as wavefront rounds or as the megakernel.  The wavefront kernels exist for the ORDERED traversal only (the
      * reference-order mode is a parity instrument, not a product path).  Automatic: see clv_ctx_walk_mode */
     const bool wavefront = r->mode == CLV_TRAVERSE_ORDERED &&
-                           (c->walk_mode >= 2 || (c->walk_mode == 0 && CLV_WAVEFRONT_BY_DEFAULT(r->accel->large)));
+                           (c->walk_mode >= 2 || (c->walk_mode == 0 && CLV_WAVEFRONT_BY_DEFAULT(r->accel->large) &&
+                                                  n >= CLV_WAVEFRONT_MIN_SAMPLES));
     if (wavefront && (rc = ensure_walk_buffers(r)) != CLV_OK) return rc;
     if (wavefront && (c->walk_mode == 3 || (c->walk_mode == 0 && CLV_PIPELINE_BY_DEFAULT)) && (rc = ensure_pipe_buffers(r)) != CLV_OK) return rc;
     /* slices: whole blocks each; one slice (everything on the context's stream) when per-kernel events are wanted */

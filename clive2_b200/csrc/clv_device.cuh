@@ -125,13 +125,36 @@ static_assert(sizeof(Material) == sizeof(clv_Material) && sizeof(Material) == 48
 static_assert(sizeof(Camera) == sizeof(clv_Camera) && sizeof(Camera) == 112, "Camera");
 static_assert(sizeof(WeightAggregator) == sizeof(clv_WeightAggregator) && sizeof(WeightAggregator) == 80, "WA");
 
+/* L2 eviction hints (measured option): BVH node / triangle records are re-read by every ray while the per-sample
+ * records (path vertices, walk state, hit records: GBs per pass) stream through once; with CLV_EVICT_HINTS the former are
+ * loaded with evict_last and the latter stored with the streaming hint, so that they do not push each other out of L2 */
+#ifndef CLV_EVICT_HINTS
+#define CLV_EVICT_HINTS 0
+#endif
 /* read-only 16-byte load through the non-coherent path */
 CLV_HD V4 ld4(const V4 *p) {
 #if defined(__CUDA_ARCH__)
-    float4 f = __ldg(reinterpret_cast<const float4 *>(p));
+#if CLV_EVICT_HINTS
+    float4 f;
+    unsigned long long policy;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p), "l"(policy));
     return v4(f.x, f.y, f.z, f.w);
 #else
+    float4 f = __ldg(reinterpret_cast<const float4 *>(p));
+    return v4(f.x, f.y, f.z, f.w);
+#endif
+#else
     return *p;
+#endif
+}
+/* 16-byte store of a record that is written once and read once much later (path vertices) */
+CLV_HD void st4_stream(V4 *p, V4 v) {
+#if defined(__CUDA_ARCH__) && CLV_EVICT_HINTS
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+    *p = v;
 #endif
 }
 /* Software prefetch of traversal records into L1 (device only; measured options, profiles/r02_notes.md).
@@ -992,10 +1015,10 @@ struct SoaSink {
     int sub;
     CLV_HDM V4 *part(int k, int part_) const { return v + ((size_t)((sub * 6 + k) * 4 + part_) * n + slot); }
     CLV_HDM void store(int i, const Ray &ray) const {
-        *part(i, 0) = v4(ray.origin.x, ray.origin.y, ray.origin.z, ray.tot_importance);
-        *part(i, 1) = v4(ray.normal.x, ray.normal.y, ray.normal.z, fabsf(dot(xyz(ray.direction), xyz(ray.normal))));
-        *part(i, 2) = v4(ray.color.x, ray.color.y, ray.color.z, ray.c_importance);
-        *part(i, 3) = v4(ray.l_importance, i2f(ray.material), i2f(ray.triangle), i2f(ray.hit_light));
+        st4_stream(part(i, 0), v4(ray.origin.x, ray.origin.y, ray.origin.z, ray.tot_importance));
+        st4_stream(part(i, 1), v4(ray.normal.x, ray.normal.y, ray.normal.z, fabsf(dot(xyz(ray.direction), xyz(ray.normal)))));
+        st4_stream(part(i, 2), v4(ray.color.x, ray.color.y, ray.color.z, ray.c_importance));
+        st4_stream(part(i, 3), v4(ray.l_importance, i2f(ray.material), i2f(ray.triangle), i2f(ray.hit_light)));
     }
     CLV_HDM void patch(int i, bool from_camera, float value) const {
         if (from_camera) part(i, 3)->x = value;

@@ -272,7 +272,8 @@ CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_K
 /* Stages 1-4 of the fused pass (ray generation + both random walks; renderer.py:281-285) run either as ONE megakernel,
  * a thread per sample (k_fused_walks), or as wavefront rounds: k_walk_init, then 12 x (k_walk_trace: persistent warps
  * that fetch rays from the round's queue as their lanes finish; k_walk_shade: the bounce of every traced ray).  Same
- * results, bit for bit.  mode 0 = automatic (wavefront for scenes whose traversal records exceed the caches; env
+ * results, bit for bit.  mode 0 = automatic (wavefront for scenes whose traversal records exceed the caches when a pass of
+ * the renderer has at least 600 Ki samples; env
  * CLV_WALK_MODE), 1 = megakernel, 2 = wavefront rounds, 3 = wavefront as ONE pipelined persistent kernel (k_walk_pipeline:
  * warps trace rays from a queue and, when they hold none, shade traced samples from a second queue — no round
  * boundaries); < 0 only queries. */

@@ -75,8 +75,8 @@ def test_c2_ggx_transmission_512x512_vs_checker(dev):
     compare_with_checker(dev, a, passes=4)
 
 
-@pytest.mark.parametrize("walk_mode", [runtime.WALK_AUTO, runtime.WALK_PIPELINE, runtime.WALK_MEGAKERNEL],
-                         ids=["auto", "pipelined", "megakernel"])
+@pytest.mark.parametrize("walk_mode", [runtime.WALK_AUTO, runtime.WALK_WAVEFRONT, runtime.WALK_PIPELINE, runtime.WALK_MEGAKERNEL],
+                         ids=["auto", "rounds", "pipelined", "megakernel"])
 def test_c3_terrain_1m_256x256_vs_checker(dev, walk_mode):
     """BASELINE.json configs[2]'s scene (1 002 528-triangle mesh, large-scene kernel flavours) at 256x256, 2 passes, under
     every driver of the walks."""

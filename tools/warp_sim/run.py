@@ -105,6 +105,14 @@ def main():
                      ("SORTED queue: sync while-while", dict(schedule=0))):
         u, slots = run(**kw)
         print(f"{name:58s} {u:.3f}  {slots / base_slots:.3f}")
+    # K rays per lane (costs as measured in SASS: inner step 70, triangle 85 instructions)
+    real = Costs(70.0, 85.0, 8.0, 35.0, 60.0, 0.0)
+    u1, s1 = run(schedule=2, refill=24, weight=2.0, costs=real)
+    print(f"SASS costs, 1 ray per lane, refill<24, vote: util {u1:.3f}")
+    for K, extra in ((2, 0.0), (2, 30.0), (2, 55.0), (3, 30.0), (4, 30.0)):
+        out = (C.c_double * 4)()
+        lib.sim_run_multi(traces, p(order), C.c_uint32(n), K, int(24 * K), C.c_double(2.0), C.byref(real), C.c_double(extra), 512 * K, out)
+        print(f"{K} rays per lane, +{extra:.0f} slots per iteration for picking the ray: util {out[0]:.3f}, issue slots vs 1 ray per lane {out[3] / s1:.3f}")
     # leaves capped by chaining (synthetic same-box nodes): does a more uniform leaf length pay for the extra inner steps?
     lib.sim_traces_split_leaves.restype = C.c_void_p
     order = np.arange(n, dtype=np.uint32)

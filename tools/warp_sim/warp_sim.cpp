@@ -156,6 +156,55 @@ enum { S_SYNC_WHILE = 0,   /* no refill: 32 rays start together, while-while, wa
 
 struct Lane { const uint8_t *p, *end; int tri_left; bool have; };
 
+/* K rays per lane: a lane runs the voted kind of step on whichever of its rays waits for it (refill below `refill_below`
+ * of the 32*K slots); extra_iter = issue slots per iteration for picking / swapping the ray */
+EXPORT void sim_run_multi(const Traces *T, const uint32_t *order, uint32_t n, int K, int refill_below, double vote_weight,
+                          const Costs *C, double extra_iter, int chunk, double out[4]) {
+    double useful = 0.0, slots = 0.0, iters = 0.0;
+    uint64_t warps = 0;
+    for (uint32_t base = 0; base < n; base += chunk) {
+        const uint32_t end = std::min<uint32_t>(n, base + chunk);
+        uint32_t next = base;
+        std::vector<Lane> L(32 * K);
+        for (auto &l : L) l.have = false;
+        warps++;
+        for (;;) {
+            int holding = 0;
+            for (auto &l : L) holding += l.have;
+            if (next < end && holding < refill_below) {
+                bool any = false;
+                for (auto &l : L) if (!l.have && next < end) {
+                    uint32_t r = order[next++];
+                    l.p = T->steps.data() + T->first[r]; l.end = T->steps.data() + T->first[r + 1];
+                    l.have = l.p < l.end; useful += C->c_fetch; any = true;
+                }
+                if (any) slots += C->c_fetch;
+            } else if (holding == 0) break;
+            iters += 1;
+            slots += C->c_iter + extra_iter;
+            int ni = 0, nl = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                bool ci = false, cl = false;
+                for (int k = 0; k < K; k++) { Lane &l = L[lane * K + k]; if (l.have) { if (*l.p == 0) ci = true; else cl = true; } }
+                ni += ci; nl += cl;
+            }
+            const bool inner = ni * vote_weight >= nl;
+            int m = 0, longest = 0;
+            double u = 0.0;
+            for (int lane = 0; lane < 32; lane++) {
+                for (int k = 0; k < K; k++) {
+                    Lane &l = L[lane * K + k];
+                    if (!l.have) continue;
+                    if (inner && *l.p == 0) { m++; u += C->c_inner; l.p++; if (l.p >= l.end) l.have = false; break; }
+                    if (!inner && *l.p != 0) { int take = *l.p; m++; longest = std::max(longest, take); u += take * C->c_tri + C->c_leaf_setup; l.p++; if (l.p >= l.end) l.have = false; break; }
+                }
+            }
+            if (m) { slots += inner ? C->c_inner : longest * C->c_tri + C->c_leaf_setup; useful += u; }
+        }
+    }
+    out[0] = useful / (32.0 * slots); out[1] = slots / std::max<uint64_t>(1, warps); out[2] = iters / std::max<uint64_t>(1, warps); out[3] = slots;
+}
+
 EXPORT void sim_run(const Traces *T, const uint32_t *order, uint32_t n, int schedule, int refill_below, int tri_batch,
                     double vote_weight, const Costs *C, int chunk, double out[4]) {
     /* rays order[0..n) are dealt to warps in chunks of `chunk` consecutive queue entries (chunk = 32 for S_SYNC_WHILE) */
