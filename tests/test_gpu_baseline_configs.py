@@ -89,15 +89,29 @@ def test_c3_terrain_1m_256x256_vs_checker(dev, walk_mode):
         dev.walk_mode = before
 
 
-def test_c4_terrain_10m_160x90_vs_checker(dev):
-    """BASELINE.json configs[3]'s scene — the north-star configuration's 9 999 392 triangles, i.e. the kernels, tree depth
-    and leaf chains the headline number runs on — at 160x90 (1080p / 12), 2 passes."""
+@pytest.fixture(scope="module")
+def c4_arrays():
+    """BASELINE.json configs[3]'s scene (9 999 392-triangle mesh + enclosure) at a 160x90 frame (1080p / 12): built once."""
     a = scene.preset_arrays("bench-terrain-10m", 160, 90)
     assert len(a.triangles) > 9_900_000
-    sc_stats_dev = runtime.Accel(dev, a.boxes, a.triangles)
-    assert sc_stats_dev.stats()["large_scene_tuning"]
-    sc_stats_dev.release()
-    compare_with_checker(dev, a, passes=2, seed=11)
+    return a
+
+
+@pytest.mark.parametrize("walk_mode", [runtime.WALK_AUTO, runtime.WALK_WAVEFRONT], ids=["auto", "rounds"])
+def test_c4_terrain_10m_160x90_vs_checker(dev, c4_arrays, walk_mode):
+    """The north-star configuration's geometry — i.e. the kernel flavours, the 29-level tree and the 4-wide nodes the
+    headline number runs on — 2 passes against the checker; `rounds` forces the wavefront walks the bench-size frame uses
+    (a 160x90 pass is below the automatic mode's sample threshold)."""
+    acc = runtime.Accel(dev, c4_arrays.boxes, c4_arrays.triangles)
+    st = acc.stats()
+    assert st["large_scene_tuning"] and st["trace_uses_wide"] and 25 <= st["binary_depth"] <= 40 and st["wide_depth"] <= 21
+    acc.release()
+    before = dev.walk_mode
+    try:
+        dev.walk_mode = walk_mode
+        compare_with_checker(dev, c4_arrays, passes=2, seed=11)
+    finally:
+        dev.walk_mode = before
 
 
 @pytest.mark.parametrize("wave_mode", [runtime.WALK_WAVEFRONT, runtime.WALK_PIPELINE], ids=["rounds", "pipelined"])
@@ -175,9 +189,8 @@ def test_ordered_traversal_equals_reference_order_at_bench_size(dev, preset, w, 
     np.testing.assert_allclose(ordered["acc"][..., 0:4], ref_order["acc"][..., 0:4], rtol=5e-4, atol=1e-6)
 
 
-def test_c4_scene_ordered_equals_reference_order(dev):
-    a = scene.preset_arrays("bench-terrain-10m", 320, 180)
-    ref_order, ordered = both_orders(dev, a, 1, seed=41)
+def test_c4_scene_ordered_equals_reference_order(dev, c4_arrays):
+    ref_order, ordered = both_orders(dev, c4_arrays, 2, seed=41)
     assert np.array_equal(ref_order["seeds"], ordered["seeds"])
     assert_paths_equal(ref_order["cam"], ordered["cam"], "camera paths")
     assert_paths_equal(ref_order["lig"], ordered["lig"], "light paths")
