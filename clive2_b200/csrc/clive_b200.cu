@@ -1129,15 +1129,17 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
     unsigned idle_polls = 0, idle_sleep = 128;
     int in_pos = 0, in_count = 0, out_count = 0; /* warp-uniform */
     int skip_polls = 0, backoff = 1;             /* warp-uniform: iterations until the global trace queue is looked at again */
-    auto flush_done = [&]() { /* publish the collected slots of finished rays (their hit records are fenced already) */
+    auto flush_done = [&]() { /* publish the collected slots of finished rays */
         if (out_count == 0) return;
+        /* ONE fence per batch, by every lane (each may have written hit records since the last flush), instead of one per
+         * finished ray: a fence stalls the warp until its stores have landed, and in steady state some lane finishes a ray
+         * in most iterations */
+        __threadfence();
+        __syncwarp();
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd((uint32_t *)&ctrl[PIPE_DONE_TAIL], (uint32_t)out_count);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < out_count) {
-            __threadfence();
-            wp.done_q[base + (uint32_t)lane] = out_buf[wib][lane];
-        }
+        if (lane < out_count) wp.done_q[base + (uint32_t)lane] = out_buf[wib][lane];
         pipe_publish(ctrl, PIPE_DONE_TAIL, out_count, lane);
         out_count = 0;
     };
@@ -1200,10 +1202,7 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
         const unsigned fin = __ballot_sync(0xffffffffu, finished);
         if (fin) {
             if (out_count + __popc(fin) > 32) flush_done();
-            if (finished) {
-                __threadfence(); /* the hit record before anything that announces it */
-                out_buf[wib][out_count + __popc(fin & lt_mask)] = slot;
-            }
+            if (finished) out_buf[wib][out_count + __popc(fin & lt_mask)] = slot;
             __syncwarp();
             out_count += __popc(fin);
             if (out_count >= 24) flush_done();
