@@ -567,8 +567,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         VB = 64  # bytes of one stored path vertex in the renderer's SoA records (four 16-byte parts)
         alg = {
             # node (64 B binary / 128 B 4-wide) + triangle (48 B) records fetched + the hit triangle's shading record
-            # (80 B of the reference Triangle) + path vertices written (64 B) + seeds RMW (16 B) + accumulator RMW (64 B)
-            "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 80 + cw["vertices"] * VB
+            # (64 B) + path vertices written (64 B) + seeds RMW (16 B) + accumulator RMW (64 B)
+            "k_fused_walks": cw["node_fetches"] * NBW + cw["tri_fetches"] * 48 + cw["rays_ref"] * 64 + cw["vertices"] * VB
                              + n_local * (16 + 64),
             # node + triangle records fetched + per task: 4 B task word, origin + triangle parts of two vertices (4 x 16 B)
             "k_connect_rays": cc["node_fetches"] * NBR + cc["tri_fetches"] * 48 + cc["rays_ref"] * (4 + 64),
@@ -582,9 +582,9 @@ def run_ours(args, cfg, rank, local_rank, world):
             # parts read (32 B), hit written (16 B), queue entry (4 B)
             "k_walk_trace": cw["node_fetches"] * NBT + cw["tri_fetches"] * 48 + cw["rays_ref"] * (32 + 16 + 4),
             # shade (+ init): per ray hit (16 B) + walk state read and written (3-4 parts each way, 112 B) + seeds RMW
-            # (16 B) + queue entry read + written (8 B) + the hit triangle's shading record (80 B); path vertices written
+            # (16 B) + queue entry read + written (8 B) + the hit triangle's shading record (64 B); path vertices written
             # (64 B + 4 B patch); per sample: generators (seeds 16 B, jitter 8 B, state 48 B) + accumulator RMW (64 B)
-            "k_walk_shade": cw["rays_ref"] * (16 + 112 + 16 + 8 + 80) + cw["vertices"] * 68 + n_local * (16 + 8 + 48 + 64),
+            "k_walk_shade": cw["rays_ref"] * (16 + 112 + 16 + 8 + 64) + cw["vertices"] * 68 + n_local * (16 + 8 + 48 + 64),
         }
         # the pipelined form runs trace and shade in ONE kernel (plus the separately timed k_walk_init, counted under shade)
         alg["k_walk_pipeline"] = alg["k_walk_trace"] + alg["k_walk_shade"]

@@ -304,7 +304,7 @@ struct clv_accel {
     int refs; /* 1 for the creator + 1 per renderer built on it: clv_accel_destroy only frees at zero, so releasing the
                * scene (or its buffers) before a renderer that still traverses the structure is harmless */
     V4 *d_nodes, *d_wnodes, *d_tris;
-    Triangle *d_ref_triangles;
+    V4 *d_shade; /* compact shading records (AccelView::shade); the reference-layout Triangle[] is not kept on the device */
     int32_t *d_camera_tris;
     AccelView view;
     uint64_t n_nodes, n_wide, n_tris;
@@ -340,7 +340,7 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     a->n_tris = (uint64_t)n_tris;
     size_t nb_nodes = std::max<size_t>(nodes.size(), 1) * sizeof(NodeRec);
     size_t nb_tris = ctris.size() * sizeof(V4);
-    size_t nb_ref = (size_t)n_tris * sizeof(Triangle);
+    size_t nb_ref = (size_t)n_tris * 4 * sizeof(V4);
     size_t nb_cam = std::max<size_t>(camera_tris.size(), 1) * sizeof(int32_t);
     /* on failure free what was allocated so far: the pool never trims, a half-built 10 M-triangle structure would strand
      * its blocks for the life of the process */
@@ -351,11 +351,11 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     CKA(dev_alloc(c, &a->d_wnodes, nb_wide));
     if (!H.wide.empty()) CKA(cudaMemcpyAsync(a->d_wnodes, H.wide.data(), H.wide.size() * sizeof(WideRec), cudaMemcpyHostToDevice, c->stream));
     CKA(dev_alloc(c, &a->d_tris, nb_tris));
-    CKA(dev_alloc(c, &a->d_ref_triangles, nb_ref));
+    CKA(dev_alloc(c, &a->d_shade, nb_ref));
     CKA(dev_alloc(c, &a->d_camera_tris, nb_cam));
     if (!nodes.empty()) CKA(cudaMemcpyAsync(a->d_nodes, nodes.data(), nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, c->stream));
     CKA(cudaMemcpyAsync(a->d_tris, ctris.data(), nb_tris, cudaMemcpyHostToDevice, c->stream));
-    CKA(cudaMemcpyAsync(a->d_ref_triangles, tris, nb_ref, cudaMemcpyHostToDevice, c->stream));
+    CKA(cudaMemcpyAsync(a->d_shade, H.shade.data(), nb_ref, cudaMemcpyHostToDevice, c->stream));
     if (!camera_tris.empty()) CKA(cudaMemcpyAsync(a->d_camera_tris, camera_tris.data(), camera_tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CKA(cudaStreamSynchronize(c->stream));
 #undef CKA
@@ -367,7 +367,7 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     a->binary_depth = H.binary_depth;
     a->wide_depth = H.wide_depth;
     a->view.tris = a->d_tris;
-    a->view.ref_triangles = a->d_ref_triangles;
+    a->view.shade = a->d_shade;
     a->view.root_min = boxes[0].min;
     a->view.root_max = boxes[0].max;
     a->view.root_ref = root_ref;
@@ -385,7 +385,7 @@ extern "C" int clv_accel_destroy(clv_accel *a) {
     dev_free(a->ctx, a->d_nodes);
     dev_free(a->ctx, a->d_wnodes);
     dev_free(a->ctx, a->d_tris);
-    dev_free(a->ctx, a->d_ref_triangles);
+    dev_free(a->ctx, a->d_shade);
     dev_free(a->ctx, a->d_camera_tris);
     delete a;
     return CLV_OK;

@@ -30,6 +30,7 @@ struct HostAccel {
     std::vector<WideRec> wide;        /* collapsed 4-wide nodes */
     int32_t wide_root_ref;
     std::vector<V4> tris;             /* 3 per triangle, reference order */
+    std::vector<V4> shade;            /* 4 per triangle: shading normals, face normal, material and flags (AccelView) */
     std::vector<int32_t> camera_tris; /* indices of is_camera triangles */
     int32_t root_ref;
     int32_t binary_depth, wide_depth; /* inner nodes on the longest root-to-leaf path: what bounds the traversal stacks */
@@ -246,11 +247,19 @@ inline const char *build_host_accel(const Box *boxes, int32_t n_boxes, const Tri
         return why;
     }
     H.tris.resize((size_t)n_tris * 3);
+    H.shade.resize((size_t)n_tris * 4);
     H.camera_tris.clear();
     for (int32_t i = 0; i < n_tris; i++) {
         const Triangle &t = tris[i];
-        float rk;
+        float rk, fm, fl, fc;
         memcpy(&rk, &rank[i], 4);
+        memcpy(&fm, &t.material, 4);
+        memcpy(&fl, &t.is_light, 4);
+        memcpy(&fc, &t.is_camera, 4);
+        H.shade[4 * (size_t)i + 0] = v4(t.n0.x, t.n0.y, t.n0.z, fm);
+        H.shade[4 * (size_t)i + 1] = v4(t.n1.x, t.n1.y, t.n1.z, fl);
+        H.shade[4 * (size_t)i + 2] = v4(t.n2.x, t.n2.y, t.n2.z, fc);
+        H.shade[4 * (size_t)i + 3] = v4(t.normal.x, t.normal.y, t.normal.z, 0.0f);
         H.tris[3 * (size_t)i + 0] = v4(t.v0.x, t.v0.y, t.v0.z, rk);
         H.tris[3 * (size_t)i + 1] = v4(t.v1.x - t.v0.x, t.v1.y - t.v0.y, t.v1.z - t.v0.z, 0.0f);
         H.tris[3 * (size_t)i + 2] = v4(t.v2.x - t.v0.x, t.v2.y - t.v0.y, t.v2.z - t.v0.z, 0.0f);

@@ -267,7 +267,10 @@ struct AccelView {
     const V4 *wnodes;  /* 4-wide nodes of the ORDERED flavour (clv_accel_build.h WideRec), 8 x V4 each */
     int32_t wroot_ref;
     const V4 *tris;
-    const Triangle *ref_triangles; /* shading data (normals, material, flags), reference records */
+    /* shading data of every triangle, 4 x V4 = 64 bytes (one aligned fetch of two sectors instead of the 80 bytes a hit
+     * touches in the reference's 128-byte Triangle record): [n0.xyz material] [n1.xyz is_light] [n2.xyz is_camera]
+     * [normal.xyz -], integers as bits */
+    const V4 *shade;
     V4 root_min, root_max;
     int32_t root_ref;
     int32_t n_camera_tris;
@@ -1074,10 +1077,11 @@ CLV_HD bool walk_bounce(WalkRegs &W, int i, bool from_camera, int best_i, float 
     const V3 o = W.o, d = W.d, rc = W.rc;
     const float ray_tot = W.ray_tot;
 
-    const Triangle *tri = A.ref_triangles + best_i;
-    V3 tn = xyz(ld4(&tri->normal));
-    V3 n0 = xyz(ld4(&tri->n0)), n1 = xyz(ld4(&tri->n1)), n2 = xyz(ld4(&tri->n2));
-    int tri_material = tri->material, tri_is_light = tri->is_light, tri_is_camera = tri->is_camera;
+    const V4 *tri = A.shade + 4 * (size_t)best_i;
+    const V4 s0 = ld4(tri), s1 = ld4(tri + 1), s2 = ld4(tri + 2), s3 = ld4(tri + 3);
+    V3 tn = xyz(s3);
+    V3 n0 = xyz(s0), n1 = xyz(s1), n2 = xyz(s2);
+    int tri_material = f2i(s0.w), tri_is_light = f2i(s1.w), tri_is_camera = f2i(s2.w);
     const Material *mat = materials + tri_material;
     V3 mat_color = xyz(ld4(&mat->color));
     int mat_type = mat->type;
@@ -1352,7 +1356,7 @@ CLV_HD unsigned long long connect_enumerate(const PV &P, const AccelView &A, con
     for (int s = 1; s < len_l + 1; s++) {
         V3 lig_o = P.origin(SUB_LIGHT, s - 1);
         /* t = 1: world_ray_to_camera_ray up to its traversal (:577-586) */
-        if (len_c >= 1 && !(materials[A.ref_triangles[P.triangle(SUB_LIGHT, s - 1)].material].type > 0)) {
+        if (len_c >= 1 && !(materials[f2i(ld4(A.shade + 4 * (size_t)P.triangle(SUB_LIGHT, s - 1)).w)].type > 0)) {
             V3 direction = normalize(xyz(c.focal_point) - lig_o);
             if (!(dot(direction, xyz(c.direction)) > 0.0f)) {
                 cnt.ray_ref();
@@ -1404,7 +1408,7 @@ CLV_HD int connect_ray_begin(int q, const PV &P, TArr Sens, const AccelView &A, 
         int best_i = -1;
         float best_t = CLV_INF, u = 0.0f, v = 0.0f;
         closest_hit<MODE, COUNT>(A, lig_o, direction, rcp(direction), best_i, best_t, u, v, cnt, -CLV_INF, -1);
-        if (best_i == -1 || !A.ref_triangles[best_i].is_camera) return OCC_BLOCKED;
+        if (best_i == -1 || !f2i(ld4(A.shade + 4 * (size_t)best_i + 2).w)) return OCC_BLOCKED;
         Sens[T_SENSOR + s - 1] = best_t;
         Sens[CAM_TRI + s - 1] = i2f(best_i);
         return OCC_CLEAR;

@@ -32,7 +32,7 @@ EXPORT SimAccel *sim_accel_create(const Box *boxes, int32_t n_boxes, const Trian
     a->view.wnodes = a->h.wide.empty() ? nullptr : a->h.wide.data()->q;
     a->view.wroot_ref = a->h.wide_root_ref;
     a->view.tris = a->h.tris.data();
-    a->view.ref_triangles = a->ref.data();
+    a->view.shade = a->h.shade.data();
     a->view.root_min = boxes[0].min;
     a->view.root_max = boxes[0].max;
     a->view.root_ref = a->h.root_ref;
