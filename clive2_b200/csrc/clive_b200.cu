@@ -52,6 +52,13 @@ extern "C" const char *clv_version(void) { return "clive_b200 0.1 (sm_100a, fmad
 /* ---------------------------------------------------------------------------------------------------------------
  * context + memory
  * ------------------------------------------------------------------------------------------------------------- */
+#ifndef CLV_WALK_TAIL_BUDGET
+/* k_walk_trace suspends the searches still running this many iterations after the round's queue ran dry (WalkRecords).
+ * C4, ms per pass, trace rounds alone / whole pass: off 12.71 / 29.30, 256: 12.64 / 29.61, 128: 11.87 / 29.48,
+ * 64: 11.28 / 29.16, 32: 10.87 / 28.97, 16: 11.04 / 30.44 (more suspended searches, more shade work); half-frame shard
+ * off / 32 / 64: 16.49 / 17.47 / 16.12; C3 off / 32 / 64: 13.54 / 13.44 / 13.39 */
+#define CLV_WALK_TAIL_BUDGET 64
+#endif
 #define CLV_MAX_SLICES 8 /* <= 16: one task counter per slice in the 64-byte header of the connect scratch */
 struct clv_ctx {
     int device;
@@ -66,6 +73,7 @@ struct clv_ctx {
     int trace_blocks_per_sm[2];           /* resident blocks of k_walk_trace (cache-resident / large flavour) */
     int connect_dynamic_fetch, rays_blocks_per_sm[2]; /* k_connect_rays: dynamic work fetch on a persistent grid */
     int finish_cooperative;                           /* k_connect_finish: warp-cooperative form */
+    int walk_tail_budget;                 /* k_walk_trace: iterations past the end of a round's queue before searches are suspended; 0 = never */
     int pipe_shade_every;                             /* k_walk_pipeline: every k-th block only shades (0: dual-role warps) */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
@@ -137,6 +145,7 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
      * C2 0.95 -> 0.85; C1 126 -> 136 Msamples/s */
     c->connect_dynamic_fetch = getenv("CLV_CONNECT_DYNAMIC") ? atoi(getenv("CLV_CONNECT_DYNAMIC")) : 1;
     c->finish_cooperative = getenv("CLV_FINISH_COOPERATIVE") ? atoi(getenv("CLV_FINISH_COOPERATIVE")) : 0;
+    c->walk_tail_budget = getenv("CLV_WALK_TAIL_BUDGET") ? std::max(0, atoi(getenv("CLV_WALK_TAIL_BUDGET"))) : CLV_WALK_TAIL_BUDGET;
     c->pipe_shade_every = getenv("CLV_PIPE_SHADE_EVERY") ? atoi(getenv("CLV_PIPE_SHADE_EVERY")) : 5;
     c->cs_mem = nullptr;
     c->cs_capacity = 0;
@@ -920,10 +929,20 @@ k_fused_walks(uint32_t first, uint32_t n_local, const uint32_t *sample_ids, cons
 enum { PIPE_TRACE_TAIL = 0, PIPE_TRACE_HEAD, PIPE_TRACE_AVAIL, PIPE_DONE_TAIL, PIPE_DONE_HEAD, PIPE_DONE_AVAIL, PIPE_LIVE, PIPE_ERROR };
 struct WalkQueues {
     uint32_t *q[2];   /* ping-pong lists of sample slots */
-    uint32_t *count;  /* [CLV_WALK_ROUNDS + 1]: entries of round r's list (round 0 = every sample of the slice, implicit) */
-    uint32_t *cursor; /* [CLV_WALK_ROUNDS]: next unfetched entry of round r's list */
+    uint32_t *count;  /* [CLV_WALK_LAUNCH_ROUNDS + 1]: entries of round r's list (round 0 = every sample of the slice, implicit) */
+    uint32_t *cursor; /* [CLV_WALK_LAUNCH_ROUNDS]: next unfetched entry of round r's list */
+    uint32_t *pool;   /* [CLV_WALK_LAUNCH_ROUNDS]: continuation records round r has taken */
 };
-#define CLV_WALK_COUNTER_WORDS 32 /* per slice: count[13] + cursor[12], padded */
+#define CLV_WALK_SAMPLES_PER_RECORD 32
+#define CLV_WALK_RECORDS_MIN 1024
+#define CLV_WALK_COUNTER_WORDS 64 /* per slice: count[17] + cursor[16] + pool[16], padded; k_walk_init clears them */
+static_assert(3 * CLV_WALK_LAUNCH_ROUNDS + 1 <= CLV_WALK_COUNTER_WORDS && CLV_WALK_COUNTER_WORDS <= CLV_BLOCK, "walk counters");
+/* continuation records of one slice (clv_device.cuh, hit_save): round r writes into half r & 1 and resumes from the other */
+struct WalkRecords {
+    V4 *half[2];
+    uint32_t capacity; /* records per half; a search that finds the pool full simply keeps going */
+    int tail_budget;   /* iterations a warp keeps stepping after the round's queue ran dry before it suspends; 0 = never */
+};
 
 template <bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK)
@@ -954,8 +973,11 @@ k_walk_init(uint32_t first, uint32_t n_end, const Triangle *light_triangles, con
 template <bool COUNT, int LARGE>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_TRACE_MIN_BLOCKS_LARGE : CLV_TRACE_MIN_BLOCKS)
 k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *cursor,
-             WalkState ws, AccelView A, Counters *counters, int refill_below, int schedule) {
-    const uint32_t count = queue ? *count_ptr : n_identity;
+             WalkState ws, AccelView A, Counters *counters, int refill_below, int schedule, const V4 *rec_in,
+             const uint32_t *rec_in_count, V4 *rec_out, uint32_t *pool, uint32_t pool_capacity, int tail_budget) {
+    /* the round's work: first the searches the previous round suspended, then the round's queue */
+    const uint32_t n_resume = rec_in_count ? min(*rec_in_count, pool_capacity) : 0u;
+    const uint32_t count = n_resume + (queue ? *count_ptr : n_identity);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     constexpr bool WIDE = LARGE ? (CLV_TRACE_WIDE_LARGE != 0) : (CLV_TRACE_WIDE != 0);
@@ -964,8 +986,28 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
     StackEntry st[CLV_HIT_STACK(WIDE)];
     bool have = false, exhausted = false; /* exhausted is warp-uniform */
     uint32_t slot = 0;
+    int tail = 0;
     for (;;) {
-        const unsigned holding = __ballot_sync(0xffffffffu, have);
+        unsigned holding = __ballot_sync(0xffffffffu, have);
+        if (exhausted && tail_budget > 0 && ++tail == tail_budget) {
+            /* the round is over for everybody else: suspend the searches still running (a sample may wait
+             * CLV_WALK_MAX_LAG rounds in total; after that its searches run to their end as they always did) */
+            const bool defer = have && ws.lag[slot] < CLV_WALK_MAX_LAG;
+            const unsigned deferring = __ballot_sync(0xffffffffu, defer);
+            if (deferring) {
+                uint32_t base = 0;
+                if (lane == __ffs(deferring) - 1) base = atomicAdd(pool, (uint32_t)__popc(deferring));
+                base = __shfl_sync(0xffffffffu, base, __ffs(deferring) - 1);
+                const uint32_t rec = base + (uint32_t)__popc(deferring & lt_mask);
+                if (defer && rec < pool_capacity) {
+                    hit_save(rec_out + (size_t)rec * CLV_HIT_RECORD_V4, slot, ray, st);
+                    stcg4(ws.hit + slot, v4(i2f(CLV_HIT_PENDING), 0.0f, 0.0f, 0.0f));
+                    ws.lag[slot]++;
+                    have = false;
+                }
+                holding = __ballot_sync(0xffffffffu, have);
+            }
+        }
         if (!exhausted && __popc(holding) < refill_below) {
             /* warp-level work fetch: the idle lanes take the next entries of the round's queue */
             const unsigned idle = ~holding;
@@ -975,15 +1017,20 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
             base = __shfl_sync(0xffffffffu, base, 0);
             const uint32_t my = base + (uint32_t)__popc(idle & lt_mask);
             if (!have && my < count) {
-                slot = queue ? queue[my] : first + my;
-                const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
-                ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
-                cnt.ray_ref();
-                if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) {
+                if (my < n_resume) { /* a search the previous round suspended: go on where it stopped */
+                    slot = hit_restore(rec_in + (size_t)my * CLV_HIT_RECORD_V4, ray, st);
                     have = true;
-                    if (CLV_PREFETCH_NEXT) prefetch_ref<WIDE>(WIDE ? A.wnodes : A.nodes, A.tris, ray.cur);
+                } else {
+                    slot = queue ? queue[my - n_resume] : first + my;
+                    const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot);
+                    ray.o = xyz(a0); ray.d = xyz(a1); ray.inv = rcp(ray.d);
+                    cnt.ray_ref();
+                    if (hit_begin<COUNT, WIDE>(A, ray, cnt) == HIT_RUNNING) {
+                        have = true;
+                        if (CLV_PREFETCH_NEXT) prefetch_ref<WIDE>(WIDE ? A.wnodes : A.nodes, A.tris, ray.cur);
+                    }
+                    else stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f));
                 }
-                else stcg4(ws.hit + slot, v4(i2f(-1), CLV_INF, 0.0f, 0.0f));
             }
             if ((uint64_t)base + (uint64_t)n_idle >= (uint64_t)count) exhausted = true;
         } else if (holding == 0u) {
@@ -1014,30 +1061,34 @@ template <bool COUNT, bool SOA>
 __global__ void __launch_bounds__(CLV_BLOCK, CLV_SHADE_MIN_BLOCKS)
 k_walk_shade(uint32_t first, uint32_t n_identity, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *queue_out,
              uint32_t *count_out, const uint32_t *sample_ids, const Material *materials, const Camera *camera, AccelView A,
-             uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters) {
-    const uint32_t count = queue ? *count_ptr : n_identity;
+             uint32_t *seeds, PathStore store, WalkState ws, Accum *accum, Counters *counters, const V4 *rec_in,
+             const uint32_t *rec_in_count, uint32_t pool_capacity) {
+    /* the same work list as the round's k_walk_trace: the samples of the resumed searches, then the queue */
+    const uint32_t n_resume = rec_in_count ? min(*rec_in_count, pool_capacity) : 0u;
+    const uint32_t count = n_resume + (queue ? *count_ptr : n_identity);
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     Cnt<COUNT> cnt;
     const Camera c = camera[0];
     for (uint64_t w0 = (uint64_t)warp * 32u; w0 < count; w0 += (uint64_t)n_warps * 32u) { /* warp-uniform trip count */
         const uint32_t idx = (uint32_t)w0 + (uint32_t)lane;
-        bool more = false;
+        int next = WALK_OVER;
         uint32_t slot = 0;
         if (idx < count) {
-            slot = queue ? queue[idx] : first + idx;
+            slot = idx < n_resume ? hit_record_slot(rec_in + (size_t)idx * CLV_HIT_RECORD_V4) : (queue ? queue[idx - n_resume] : first + idx);
             const uint32_t gid = sample_ids ? sample_ids[slot] : slot;
             uint2 sd = reinterpret_cast<uint2 *>(seeds)[slot];
             uint32_t seed0 = sd.x, seed1 = sd.y;
-            more = wavefront_shade_sample<COUNT, SOA>(slot, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt);
+            next = wavefront_shade_sample<COUNT, SOA>(slot, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt);
             if (seed0 != sd.x || seed1 != sd.y) reinterpret_cast<uint2 *>(seeds)[slot] = make_uint2(seed0, seed1);
         }
-        const unsigned staying = __ballot_sync(0xffffffffu, more);
+        /* WALK_WAIT: the search was suspended again; its record is already on the next round's list */
+        const unsigned staying = __ballot_sync(0xffffffffu, next == WALK_NEXT);
         if (staying) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(count_out, (uint32_t)__popc(staying));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (more) queue_out[base + (uint32_t)__popc(staying & ((1u << lane) - 1u))] = slot;
+            if (next == WALK_NEXT) queue_out[base + (uint32_t)__popc(staying & ((1u << lane) - 1u))] = slot;
         }
     }
     flush_counters<COUNT>(cnt, counters);
@@ -1225,7 +1276,7 @@ k_walk_pipeline(WalkPipe wp, const uint32_t *sample_ids, const Material *materia
                 const uint32_t gid = sample_ids ? sample_ids[s] : s;
                 uint2 sd = __ldcg(reinterpret_cast<const uint2 *>(seeds) + s);
                 uint32_t seed0 = sd.x, seed1 = sd.y;
-                more = wavefront_shade_sample<COUNT, SOA>(s, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt);
+                more = wavefront_shade_sample<COUNT, SOA>(s, gid, materials, c, A, seed0, seed1, store, ws, accum, cnt) != WALK_OVER;
                 if (seed0 != sd.x || seed1 != sd.y) reinterpret_cast<uint2 *>(seeds)[s] = make_uint2(seed0, seed1);
             }
             const unsigned staying = __ballot_sync(0xffffffffu, more);
@@ -1620,6 +1671,9 @@ struct clv_renderer {
     float *d_walk_jitter;  /* [n_local][2] */
     uint32_t *d_walk_queue; /* 2 x n_local */
     uint32_t *d_walk_counters; /* CLV_MAX_SLICES x CLV_WALK_COUNTER_WORDS */
+    uint8_t *d_walk_lag;       /* [n_local] rounds a sample has waited for a suspended search */
+    V4 *d_walk_records;        /* continuation records: 2 halves x walk_record_capacity x CLV_HIT_RECORD_V4 */
+    size_t walk_record_capacity;
     uint32_t *d_pipe_queues;   /* pipelined walks: trace entries (11 per sample) then done entries (12 per sample) */
     uint32_t *d_pipe_ctrl;     /* CLV_MAX_SLICES x 8 */
     int pipe_blocks_per_sm;
@@ -1638,7 +1692,7 @@ extern "C" int clv_renderer_destroy(clv_renderer *r) {
     dev_free(r->ctx, r->d_tone_sum);
     dev_free(r->ctx, r->d_tone_image);
     dev_free(r->ctx, r->d_walk_state); dev_free(r->ctx, r->d_walk_jitter); dev_free(r->ctx, r->d_walk_queue);
-    dev_free(r->ctx, r->d_walk_counters);
+    dev_free(r->ctx, r->d_walk_counters); dev_free(r->ctx, r->d_walk_lag); dev_free(r->ctx, r->d_walk_records);
     dev_free(r->ctx, r->d_pipe_queues); dev_free(r->ctx, r->d_pipe_ctrl);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     clv_accel_destroy(const_cast<clv_accel *>(r->accel)); /* drops the renderer's reference */
@@ -1722,6 +1776,7 @@ extern "C" int clv_renderer_create(clv_ctx *c, const clv_accel *accel, const clv
     TRY(zalloc((void **)&r->d_tone_sum, 16));
     TRY(zalloc((void **)&r->d_tone_image, (size_t)n_pixels * 3));
     r->d_walk_state = nullptr; r->d_walk_jitter = nullptr; r->d_walk_queue = nullptr; r->d_walk_counters = nullptr;
+    r->d_walk_lag = nullptr; r->d_walk_records = nullptr; r->walk_record_capacity = 0;
     r->d_pipe_queues = nullptr; r->d_pipe_ctrl = nullptr; r->pipe_blocks_per_sm = 0;
     TRY(load_seeds(r, h_seeds));
 #undef TRY
@@ -1782,6 +1837,11 @@ static int ensure_walk_buffers(clv_renderer *r) {
     CK(dev_alloc(c, &r->d_walk_queue, n * 2 * sizeof(uint32_t)));
     CK(dev_alloc(c, &r->d_walk_counters, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t)));
     CK(cudaMemsetAsync(r->d_walk_counters, 0, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t), c->stream));
+    CK(dev_alloc(c, &r->d_walk_lag, n));
+    /* continuation records: a slice [first, end) owns records [first / 32 + slice * 1024, ...) of each half, 1024 +
+     * (end - first) / 32 of them (about 1 % of a round's rays are suspended at the default budget; a full pool is harmless) */
+    r->walk_record_capacity = n / CLV_WALK_SAMPLES_PER_RECORD + (size_t)(CLV_MAX_SLICES + 1) * CLV_WALK_RECORDS_MIN;
+    CK(dev_alloc(c, &r->d_walk_records, 2 * r->walk_record_capacity * CLV_HIT_RECORD_V4 * sizeof(V4)));
     return CLV_OK;
 }
 static int ensure_pipe_buffers(clv_renderer *r) {
@@ -1818,12 +1878,21 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
     WalkState ws;
     ws.s0 = r->d_walk_state; ws.s1 = ws.s0 + n; ws.s2 = ws.s1 + n; ws.s3 = ws.s2 + n; ws.hit = ws.s3 + n;
     ws.jitter = r->d_walk_jitter;
+    ws.lag = r->d_walk_lag;
     WalkQueues wq;
     wq.q[0] = r->d_walk_queue + first;      /* a slice's lists never hold more than its own samples */
     wq.q[1] = r->d_walk_queue + n + first;
     wq.count = r->d_walk_counters + (size_t)slice * CLV_WALK_COUNTER_WORDS;
-    wq.cursor = wq.count + (CLV_WALK_ROUNDS + 1);
-    static_assert(2 * CLV_WALK_ROUNDS + 1 <= CLV_WALK_COUNTER_WORDS, "walk counters");
+    wq.cursor = wq.count + (CLV_WALK_LAUNCH_ROUNDS + 1);
+    wq.pool = wq.cursor + CLV_WALK_LAUNCH_ROUNDS;
+    WalkRecords wr;
+    {
+        const size_t rec0 = (size_t)first / CLV_WALK_SAMPLES_PER_RECORD + (size_t)slice * CLV_WALK_RECORDS_MIN;
+        wr.capacity = (uint32_t)(len / CLV_WALK_SAMPLES_PER_RECORD + CLV_WALK_RECORDS_MIN);
+        wr.half[0] = r->d_walk_records + rec0 * CLV_HIT_RECORD_V4;
+        wr.half[1] = wr.half[0] + r->walk_record_capacity * CLV_HIT_RECORD_V4;
+        wr.tail_budget = c->walk_tail_budget;
+    }
     Counters *ctr = c->d_counters + COUNTERS_WALK;
     const bool pipelined = c->walk_mode == 3 || (c->walk_mode == 0 && CLV_PIPELINE_BY_DEFAULT);
     uint32_t *pipe_ctrl = nullptr;
@@ -1870,17 +1939,21 @@ static int launch_wavefront_walks(clv_renderer *r, cudaStream_t st, int slice, u
     else rc = tl ? trace_grid(c, k_walk_trace<false, 1>, 1, len, sliced, &tgrid) : trace_grid(c, k_walk_trace<false, 0>, 0, len, sliced, &tgrid);
     if (rc != CLV_OK) return rc;
     const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 16u, ((uint64_t)len + CLV_BLOCK - 1) / CLV_BLOCK));
-    for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
+    /* a sample whose searches were suspended k times needs k more rounds */
+    const int rounds = wr.tail_budget > 0 ? CLV_WALK_LAUNCH_ROUNDS : CLV_WALK_ROUNDS;
+    for (int round = 0; round < rounds; round++) {
         const uint32_t *qin = round == 0 ? nullptr : wq.q[round & 1];
         uint32_t *qout = wq.q[(round + 1) & 1];
         const uint32_t n_identity = round == 0 ? len : 0u;
-#define TRACE(CT, LG) k_walk_trace<CT, LG><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule)
+        const V4 *rec_in = wr.half[round & 1];
+        const uint32_t *rec_in_count = round > 0 && wr.tail_budget > 0 ? wq.pool + round - 1 : nullptr;
+#define TRACE(CT, LG) k_walk_trace<CT, LG><<<tgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, wq.cursor + round, ws, r->accel->view, ctr, c->walk_refill_below, c->walk_schedule, rec_in, rec_in_count, wr.half[(round + 1) & 1], wq.pool + round, wr.capacity, wr.tail_budget)
         if (c->counting) { if (tl) TRACE(true, 1); else TRACE(true, 0); }
         else { if (tl) TRACE(false, 1); else TRACE(false, 0); }
 #undef TRACE
         LAUNCHED(c);
         if ((rc = mark(r, st, TK_WALK_TRACE)) != CLV_OK) return rc;
-#define SHADE(CT, SO) k_walk_shade<CT, SO><<<sgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, qout, wq.count + round + 1, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr)
+#define SHADE(CT, SO) k_walk_shade<CT, SO><<<sgrid, CLV_BLOCK, 0, st>>>(first, n_identity, qin, wq.count + round, qout, wq.count + round + 1, ids, r->d_materials, r->d_camera, r->accel->view, r->d_seeds, store, ws, r->d_accum, ctr, rec_in, rec_in_count, wr.capacity)
         if (soa) { if (c->counting) SHADE(true, true); else SHADE(false, true); }
         else { if (c->counting) SHADE(true, false); else SHADE(false, false); }
 #undef SHADE
@@ -2004,6 +2077,7 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
     else if (!strcmp(name, "walk_grid_divisor")) slot = &c->walk_grid_divisor;
     else if (!strcmp(name, "finish_cooperative")) slot = &c->finish_cooperative;
     else if (!strcmp(name, "pipe_shade_every")) slot = &c->pipe_shade_every;
+    else if (!strcmp(name, "walk_tail_budget")) slot = &c->walk_tail_budget;
     else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
     if (previous) *previous = *slot;
     if (value >= 0) {

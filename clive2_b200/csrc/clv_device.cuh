@@ -555,6 +555,38 @@ CLV_HD int hit_leaf_step(const AccelView &A, HitRay &r, const StackEntry *st, Cn
     return status;
 }
 
+/* ---- continuation of a closest-hit search across wavefront rounds ------------------------------------------------------ *
+ * A round of the wavefront walks cannot end before its longest ray, and fewer than 1 % of the rays — the ones still running
+ * 64 iterations after every other ray of the round is done — held 20 % of the trace time (profiles/r02_notes.md).  Such a
+ * search is suspended: its scalars and the live part of its stack go to a continuation record and its hit record says
+ * PENDING.  The records of round r are the FIRST work of round r + 1 — trace resumes each search exactly where it stopped
+ * (long searches start early instead of forming the next tail), shade then treats the sample like any other of that round —
+ * so the sample simply waits one round.  The search itself is unchanged — same steps in the same order — and so is its result.
+ * Record: 4 x V4 header [o.xyz best_t] [d.xyz best_rank] [bu bv best_i cur] [sp slot - -], then the stack entries. */
+#define CLV_HIT_PENDING (-2)
+#define CLV_WALK_MAX_LAG 4              /* rounds a sample may fall behind; the walks run CLV_WALK_ROUNDS + this many rounds */
+#define CLV_HIT_RECORD_V4 (4 + (CLV_STACK > CLV_OCC_STACK ? CLV_STACK : CLV_OCC_STACK) / 2) /* record stride, 16-byte units */
+CLV_HD void hit_save(V4 *rec, uint32_t slot, const HitRay &r, const StackEntry *st) {
+    stcg4(rec + 0, v4(r.o.x, r.o.y, r.o.z, r.best_t));
+    stcg4(rec + 1, v4(r.d.x, r.d.y, r.d.z, i2f(r.best_rank)));
+    stcg4(rec + 2, v4(r.bu, r.bv, i2f(r.best_i), i2f(r.cur)));
+    stcg4(rec + 3, v4(i2f(r.sp), i2f((int)slot), 0.0f, 0.0f));
+    StackEntry *dst = reinterpret_cast<StackEntry *>(rec + 4);
+    for (int k = 0; k < r.sp; k++) dst[k] = st[k];
+}
+CLV_HD uint32_t hit_record_slot(const V4 *rec) { return (uint32_t)f2i(ldcg4(rec + 3).y); }
+CLV_HD uint32_t hit_restore(const V4 *rec, HitRay &r, StackEntry *st) { /* returns the sample slot */
+    const V4 a = ldcg4(rec + 0), b = ldcg4(rec + 1), c = ldcg4(rec + 2), d = ldcg4(rec + 3);
+    r.o = xyz(a); r.best_t = a.w;
+    r.d = xyz(b); r.best_rank = f2i(b.w);
+    r.inv = rcp(r.d);
+    r.bu = c.x; r.bv = c.y; r.best_i = f2i(c.z); r.cur = f2i(c.w);
+    r.sp = f2i(d.x);
+    const StackEntry *src = reinterpret_cast<const StackEntry *>(rec + 4);
+    for (int k = 0; k < r.sp; k++) st[k] = src[k];
+    return (uint32_t)f2i(d.y);
+}
+
 /* ---- occlusion query (predicate rays of the connection stage) ---------------------------------------------------- *
  * Both predicates of connect_paths ask whether ONE known triangle is the closest hit of a ray: visibility_test
  * (trace.metal:178-197: closest hit must be b's triangle) and world_ray_to_camera_ray (:569-617: closest hit must be a
@@ -1776,9 +1808,11 @@ CLV_HD void fused_walk_sample(uint32_t slot, uint32_t gid, const Triangle *light
 struct WalkState {
     V4 *s0, *s1, *s2, *s3, *hit;
     float *jitter; /* [n][2] */
+    uint8_t *lag;  /* [n]: rounds the sample has fallen behind because a search of its was suspended */
 };
 enum { WS_CAMERA = 1, WS_BOUNCE_SHIFT = 1, WS_UNI_FOUND = 16 };
 #define CLV_WALK_ROUNDS (2 * CLV_MAX_BOUNCES)
+#define CLV_WALK_LAUNCH_ROUNDS (CLV_WALK_ROUNDS + CLV_WALK_MAX_LAG) /* with suspended searches a sample may need more rounds */
 
 template <bool SOA> struct SinkOf;
 template <> struct SinkOf<true> {
@@ -1812,6 +1846,7 @@ CLV_HD void wavefront_init_sample(uint32_t slot, const Triangle *light_triangles
                                   const int32_t *light_triangle_indices, int light_count, const Material *materials,
                                   uint32_t &seed0, uint32_t &seed1, const PathStore &store, const WalkState &ws) {
     Ray lray = make_light_ray(light_triangles, surface_areas, light_triangle_indices, materials, light_count, seed0, seed1);
+    ws.lag[slot] = 0;
     ws.jitter[2 * (size_t)slot] = xorshift_random(seed0); /* make_camera_ray's two draws */
     ws.jitter[2 * (size_t)slot + 1] = xorshift_random(seed1);
     WalkRegs W;
@@ -1819,12 +1854,16 @@ CLV_HD void wavefront_init_sample(uint32_t slot, const Triangle *light_triangles
     walk_state_save(ws, slot, W, SUB_LIGHT, 0);
 }
 
-/* one bounce of a sample given the hit of its current ray; returns true while the sample has another ray to trace */
+/* one bounce of a sample given the hit of its current ray: WALK_NEXT while the sample has another ray to trace, WALK_WAIT
+ * when the search for this hit was suspended (the sample waits a round and the search is resumed), else WALK_OVER */
+enum { WALK_OVER = 0, WALK_NEXT = 1, WALK_WAIT = 2 };
 template <bool COUNT, bool SOA>
-CLV_HD bool wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *materials, const Camera &c, const AccelView &A,
+CLV_HD int wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *materials, const Camera &c, const AccelView &A,
                                    uint32_t &seed0, uint32_t &seed1, const PathStore &store, const WalkState &ws, Accum *accum,
                                    Cnt<COUNT> &cnt) {
-    const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot), a2 = ldcg4(ws.s2 + slot), h = ldcg4(ws.hit + slot);
+    const V4 h = ldcg4(ws.hit + slot);
+    if (f2i(h.x) == CLV_HIT_PENDING) return WALK_WAIT;
+    const V4 a0 = ldcg4(ws.s0 + slot), a1 = ldcg4(ws.s1 + slot), a2 = ldcg4(ws.s2 + slot);
     const int flags = f2i(a2.w);
     const int which = flags & WS_CAMERA, bounce = (flags >> WS_BOUNCE_SHIFT) & 7;
     WalkRegs W;
@@ -1859,16 +1898,16 @@ CLV_HD bool wavefront_shade_sample(uint32_t slot, uint32_t gid, const Material *
     }
     if (more) {
         walk_state_save(ws, slot, W, which, bounce + 1);
-        return true;
+        return WALK_NEXT;
     }
     if (!which) { /* light walk over: the camera walk starts with the RNG state the light walk leaves */
         Ray cray = camera_ray_from_jitter(c, (int)gid, ws.jitter[2 * (size_t)slot], ws.jitter[2 * (size_t)slot + 1]);
         walk_begin(cray, SinkOf<SOA>::make(store, slot, SUB_CAMERA), W);
         walk_state_save(ws, slot, W, SUB_CAMERA, 0);
-        return true;
+        return WALK_NEXT;
     }
     accum[gid].count += 1.0f;
-    return false;
+    return WALK_OVER;
 }
 
 /* stages 6-8 for one pixel: adaptive_finalize_samples with identity bins, the light image the connect kernel

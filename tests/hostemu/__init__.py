@@ -95,13 +95,15 @@ class HostEmu:
         return out
 
     def fused_pass(self, arrays, accel, seeds, light_paths, camera_paths, aggs, light_image, accum, sample_ids=None,
-                   mode=MODE_ORDERED, soa=None, soa_len=None, wavefront=False):
+                   mode=MODE_ORDERED, soa=None, soa_len=None, wavefront=False, suspend_after=0):
         """One fused pass.  With `soa` (float32 (2*6*4*n_local, 4)) and `soa_len` (int32 (2*n_local,)) the renderer's compact
         SoA vertex records are used instead of the Path arrays.  `wavefront`: stages 1-4 as the rounds of k_walk_init /
-        k_walk_trace / k_walk_shade instead of the per-sample megakernel (2: the trace steps over the 4-wide nodes)."""
+        k_walk_trace / k_walk_shade instead of the per-sample megakernel (2: the trace steps over the 4-wide nodes);
+        `suspend_after` > 0: a search still running after that many steps is suspended into a continuation record and
+        resumed by the next round (hit_save / hit_restore), as k_walk_trace does with the searches that outlast a round."""
         n_local = len(seeds)
         self.lib.emu_fused_pass(C.c_uint32(n_local), _p(sample_ids), _p(arrays.light_triangles),
                                 _p(arrays.light_surface_areas), _p(arrays.light_triangle_indices),
                                 C.c_int(int(arrays.light_counts)), _p(arrays.materials), _p(arrays.camera), accel,
                                 _p(seeds), _p(light_paths), _p(camera_paths), _p(aggs), _p(light_image), _p(accum),
-                                C.c_int(mode), _p(soa), _p(soa_len), C.c_int(int(wavefront)))
+                                C.c_int(mode), _p(soa), _p(soa_len), C.c_int(int(wavefront) | (int(suspend_after) << 8)))

@@ -211,12 +211,17 @@ EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAc
 template <bool SOA>
 static void wavefront_walks(uint32_t n_local, const uint32_t *sample_ids, const Triangle *lt, const float *areas,
                             const int32_t *lti, int light_count, const Material *mats, const Camera *cam, const EmuAccel *a,
-                            uint32_t *seeds, PathStore store, Accum *accum, Cnt<true> &cnt, bool wide) {
+                            uint32_t *seeds, PathStore store, Accum *accum, Cnt<true> &cnt, bool wide, int suspend_after) {
     std::vector<V4> state((size_t)n_local * 5);
     std::vector<float> jitter((size_t)n_local * 2);
+    std::vector<uint8_t> lag(n_local);
     WalkState ws;
     ws.s0 = state.data(); ws.s1 = ws.s0 + n_local; ws.s2 = ws.s1 + n_local; ws.s3 = ws.s2 + n_local; ws.hit = ws.s3 + n_local;
     ws.jitter = jitter.data();
+    ws.lag = lag.data();
+    /* continuation records (hit_save / hit_restore): a search that has not ended after `suspend_after` steps is suspended
+     * and resumed by the next round, the way k_walk_trace treats the searches that outlast a round */
+    std::vector<V4> records[2];
     std::vector<uint32_t> queue(n_local), next;
     for (uint32_t id = 0; id < n_local; id++) {
         uint32_t s0 = seeds[2 * (size_t)id], s1 = seeds[2 * (size_t)id + 1];
@@ -224,31 +229,59 @@ static void wavefront_walks(uint32_t n_local, const uint32_t *sample_ids, const 
         seeds[2 * (size_t)id] = s0; seeds[2 * (size_t)id + 1] = s1;
         queue[id] = id;
     }
-    for (int round = 0; round < CLV_WALK_ROUNDS; round++) {
+    const int rounds = suspend_after > 0 ? CLV_WALK_LAUNCH_ROUNDS : CLV_WALK_ROUNDS;
+    for (int round = 0; round < rounds; round++) {
         /* a later round's queue is in whatever order the warps of the previous one appended to it: reverse it here so that
          * a dependence on the order would show */
         if (round & 1) std::reverse(queue.begin(), queue.end());
-        for (uint32_t slot : queue) { /* k_walk_trace */
+        std::vector<V4> &rec_out = records[(round + 1) & 1];
+        const std::vector<V4> &rec_in = records[round & 1];
+        rec_out.clear();
+        /* the round's work list: the searches the previous round suspended, then the queue */
+        const size_t n_resume = rec_in.size() / CLV_HIT_RECORD_V4, n_work = n_resume + queue.size();
+        for (size_t w = 0; w < n_work; w++) { /* k_walk_trace */
             HitRay ray;
-            StackEntry st[CLV_HIT_STACK(true)];
-            ray.o = xyz(ws.s0[slot]); ray.d = xyz(ws.s1[slot]); ray.inv = rcp(ray.d);
-            cnt.ray_ref();
-            int status = wide ? hit_begin<true, true>(a->view, ray, cnt) : hit_begin<true, false>(a->view, ray, cnt);
+            StackEntry st[CLV_HIT_STACK(true) > CLV_HIT_STACK(false) ? CLV_HIT_STACK(true) : CLV_HIT_STACK(false)];
+            int status = HIT_RUNNING;
+            uint32_t slot;
+            if (w < n_resume) {
+                slot = hit_restore(rec_in.data() + w * CLV_HIT_RECORD_V4, ray, st);
+            } else {
+                slot = queue[w - n_resume];
+                ray.o = xyz(ws.s0[slot]); ray.d = xyz(ws.s1[slot]); ray.inv = rcp(ray.d);
+                cnt.ray_ref();
+                status = wide ? hit_begin<true, true>(a->view, ray, cnt) : hit_begin<true, false>(a->view, ray, cnt);
+            }
+            int steps = 0;
+            bool suspended = false;
             while (status == HIT_RUNNING) {
+                if (suspend_after > 0 && steps == suspend_after && ws.lag[slot] < CLV_WALK_MAX_LAG) {
+                    const size_t rec = rec_out.size() / CLV_HIT_RECORD_V4;
+                    rec_out.resize(rec_out.size() + CLV_HIT_RECORD_V4);
+                    hit_save(rec_out.data() + rec * CLV_HIT_RECORD_V4, slot, ray, st);
+                    ws.hit[slot] = v4(i2f(CLV_HIT_PENDING), 0.0f, 0.0f, 0.0f);
+                    ws.lag[slot]++;
+                    suspended = true;
+                    break;
+                }
                 if (ray.cur < 0) status = hit_leaf_step<true>(a->view, ray, st, cnt);
                 else status = wide ? hit_inner_step_wide<true>(a->view, ray, st, cnt) : hit_inner_step<true>(a->view, ray, st, cnt);
+                steps++;
             }
-            ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
+            if (!suspended) ws.hit[slot] = v4(i2f(ray.best_i), ray.best_t, ray.bu, ray.bv);
         }
         next.clear();
-        for (uint32_t slot : queue) { /* k_walk_shade */
+        for (size_t w = 0; w < n_work; w++) { /* k_walk_shade */
+            const uint32_t slot = w < n_resume ? hit_record_slot(rec_in.data() + w * CLV_HIT_RECORD_V4) : queue[w - n_resume];
             uint32_t gid = sample_ids ? sample_ids[slot] : slot;
             uint32_t s0 = seeds[2 * (size_t)slot], s1 = seeds[2 * (size_t)slot + 1];
-            if (wavefront_shade_sample<true, SOA>(slot, gid, mats, cam[0], a->view, s0, s1, store, ws, accum, cnt)) next.push_back(slot);
+            const int more = wavefront_shade_sample<true, SOA>(slot, gid, mats, cam[0], a->view, s0, s1, store, ws, accum, cnt);
+            if (more == WALK_NEXT) next.push_back(slot); /* WALK_WAIT: its new record is on the next round's list already */
             seeds[2 * (size_t)slot] = s0; seeds[2 * (size_t)slot + 1] = s1;
         }
         queue.swap(next);
     }
+    if (!queue.empty() || !records[rounds & 1].empty()) abort(); /* every sample ends within the launched rounds */
 }
 
 template <int MODE, bool SOA>
@@ -258,7 +291,7 @@ static void fused_pass(uint32_t n_local, const uint32_t *sample_ids, const Trian
     uint32_t n_pixels = (uint32_t)(cam[0].pixel_width * cam[0].pixel_height);
     if (wavefront) {
         Cnt<true> cnt;
-        wavefront_walks<SOA>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, accum, cnt, wavefront == 2);
+        wavefront_walks<SOA>(n_local, sample_ids, lt, areas, lti, light_count, mats, cam, a, seeds, store, accum, cnt, (wavefront & 3) == 2, wavefront >> 8);
         merge(cnt);
     }
 #pragma omp parallel

@@ -89,6 +89,24 @@ def test_c3_terrain_1m_256x256_vs_checker(dev, walk_mode):
         dev.walk_mode = before
 
 
+@pytest.mark.parametrize("budget", [1, 16, 64])
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_suspended_searches_vs_checker(dev, which, budget):
+    """k_walk_trace suspends the searches still running `walk_tail_budget` iterations after their round's queue ran dry
+    (continuation records, resumed by the next round).  Budget 1 suspends every search a warp still holds at that moment,
+    up to CLV_WALK_MAX_LAG times per sample; 64 is the production value.  Same bits as the checker under every budget, on
+    the binary nodes (c2) and the 4-wide nodes (c3)."""
+    a = arrays("bench-spheres", 512, 512) if which == "c2" else scene.preset_arrays("bench-terrain-1m", 256, 256)
+    before, before_budget = dev.walk_mode, dev.knob("walk_tail_budget", -1)
+    try:
+        dev.walk_mode = runtime.WALK_WAVEFRONT
+        dev.knob("walk_tail_budget", budget)
+        compare_with_checker(dev, a, passes=2, seed=17)
+    finally:
+        dev.walk_mode = before
+        dev.knob("walk_tail_budget", before_budget)
+
+
 @pytest.fixture(scope="module")
 def c4_arrays():
     """BASELINE.json configs[3]'s scene (9 999 392-triangle mesh + enclosure) at a 160x90 frame (1080p / 12): built once."""
@@ -97,8 +115,9 @@ def c4_arrays():
     return a
 
 
-@pytest.mark.parametrize("walk_mode", [runtime.WALK_AUTO, runtime.WALK_WAVEFRONT], ids=["auto", "rounds"])
-def test_c4_terrain_10m_160x90_vs_checker(dev, c4_arrays, walk_mode):
+@pytest.mark.parametrize("walk_mode,budget", [(runtime.WALK_AUTO, None), (runtime.WALK_WAVEFRONT, 0), (runtime.WALK_WAVEFRONT, 8)],
+                         ids=["auto", "rounds", "rounds_suspending"])
+def test_c4_terrain_10m_160x90_vs_checker(dev, c4_arrays, walk_mode, budget):
     """The north-star configuration's geometry — i.e. the kernel flavours, the 29-level tree and the 4-wide nodes the
     headline number runs on — 2 passes against the checker; `rounds` forces the wavefront walks the bench-size frame uses
     (a 160x90 pass is below the automatic mode's sample threshold)."""
@@ -106,12 +125,15 @@ def test_c4_terrain_10m_160x90_vs_checker(dev, c4_arrays, walk_mode):
     st = acc.stats()
     assert st["large_scene_tuning"] and st["trace_uses_wide"] and 25 <= st["binary_depth"] <= 40 and st["wide_depth"] <= 21
     acc.release()
-    before = dev.walk_mode
+    before, before_budget = dev.walk_mode, dev.knob("walk_tail_budget", -1)
     try:
         dev.walk_mode = walk_mode
+        if budget is not None:
+            dev.knob("walk_tail_budget", budget)
         compare_with_checker(dev, c4_arrays, passes=2, seed=11)
     finally:
         dev.walk_mode = before
+        dev.knob("walk_tail_budget", before_budget)
 
 
 @pytest.mark.parametrize("wave_mode", [runtime.WALK_WAVEFRONT, runtime.WALK_PIPELINE], ids=["rounds", "pipelined"])

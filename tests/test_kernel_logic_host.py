@@ -483,7 +483,7 @@ def test_light_counts_bit_exact(O, E, n_extra):
     assert len(np.unique(R.light_rays["triangle"])) == int(a.light_counts)  # every light gets picked
 
 
-def _fused_vs_oracle_renderer(E, a, seeds, passes=3, wavefront=False):
+def _fused_vs_oracle_renderer(E, a, seeds, passes=3, wavefront=False, suspend_after=0):
     b = a.pixel_width * a.pixel_height
     ref = OracleRenderer(a, seeds, shared_math=True)
     s = seeds.copy()
@@ -496,7 +496,8 @@ def _fused_vs_oracle_renderer(E, a, seeds, passes=3, wavefront=False):
     try:
         for _ in range(passes):
             ref.run_sample()
-            E.fused_pass(a, acc, s, None, None, aggs, light_image, accum, soa=soa, soa_len=soa_len, wavefront=wavefront)
+            E.fused_pass(a, acc, s, None, None, aggs, light_image, accum, soa=soa, soa_len=soa_len, wavefront=wavefront,
+                         suspend_after=suspend_after)
     finally:
         E.accel_destroy(acc)
     assert_bits_equal(ref.buffer("rand", np.uint32).reshape(b, 2), s, "RNG state")
@@ -531,6 +532,16 @@ def test_wavefront_walks_vs_oracle_renderer(E, preset, w, h, wavefront):
     """Stages 1-4 as wavefront rounds (the logic of k_walk_init / k_walk_trace / k_walk_shade: resumable single-step
     closest-hit search, per-bounce walk state in memory, live-sample queues) against the oracle renderer."""
     _fused_vs_oracle_renderer(E, arrays(preset, w, h), seeds_for(w * h, seed=12), passes=3, wavefront=wavefront)
+
+
+@pytest.mark.parametrize("suspend_after", [1, 3, 9])
+@pytest.mark.parametrize("wavefront", [1, 2], ids=["binary_nodes", "wide_nodes"])
+def test_suspended_searches_resume_to_the_same_hit(E, wavefront, suspend_after):
+    """k_walk_trace suspends the searches that outlast their round (continuation records: scalars + live stack, resumed by
+    the next round while the sample waits).  Here every search longer than 1 / 3 / 9 steps is suspended, up to
+    CLV_WALK_MAX_LAG times per sample: images, records and RNG rows still equal the oracle renderer's bit for bit."""
+    _fused_vs_oracle_renderer(E, arrays("bench-spheres", 48, 36), seeds_for(48 * 36, seed=13), passes=2, wavefront=wavefront,
+                              suspend_after=suspend_after)
 
 
 @pytest.mark.parametrize("use_soa", [False, True], ids=["path_records", "soa_records"])

@@ -17,6 +17,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from clive2_b200 import runtime, scene  # noqa: E402
+from clive2_b200 import struct_types as T  # noqa: E402
 from clive2_b200.renderer import Renderer  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -35,6 +36,7 @@ sc = scene.scene_from_arrays(arrays, dev)
 import torch  # noqa: E402
 stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", 0))
 ref_state = None
+ref_aggs = None
 for setting in args.settings.split(";"):
     kv = dict(x.split("=") for x in setting.split(",") if x)
     dev.walk_mode = int(kv.pop("mode", 0))
@@ -66,6 +68,10 @@ for setting in args.settings.split(";"):
     state = r._fr.read(runtime.BUF_SEEDS, np.uint32, 2 * n_local)
     same = True if ref_state is None else bool(np.array_equal(ref_state, state))
     ref_state = state if ref_state is None else ref_state
+    # the last pass's aggregators (every connection weight and colour of every pixel) are order independent, too
+    aggs = r._fr.read(runtime.BUF_AGGREGATORS, np.uint8, batch * T.WeightAggregator.itemsize) if ids is None else None
+    same_aggs = None if aggs is None else (True if ref_aggs is None else bool(np.array_equal(ref_aggs, aggs)))
+    ref_aggs = aggs if ref_aggs is None else ref_aggs
     print(json.dumps({"config": args.config, "setting": setting, "ms_per_pass": ms, "msamples_per_s": n_local / ms / 1e3, "samples_per_pass": n_local,
-                      "kernel_ms": {k: round(v / max(n, 1), 4) for k, v in km.items()}, "same_rng_state_as_first": same}), flush=True)
+                      "kernel_ms": {k: round(v / max(n, 1), 4) for k, v in km.items()}, "same_rng_state_as_first": same, "same_aggregators_as_first": same_aggs}), flush=True)
     r.release()
