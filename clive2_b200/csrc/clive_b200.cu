@@ -579,7 +579,9 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
 #define CLV_RAYS_MIN_BLOCKS 1 /* no register cap: the kernel takes 63 */
 #endif
 #ifndef CLV_RAYS_MIN_BLOCKS_LARGE
-#define CLV_RAYS_MIN_BLOCKS_LARGE (1280 / CLV_BLOCK) /* = 48 registers per thread */
+/* C4, ms per pass of k_connect_rays at 40 / 48 / 56 / 64 registers: 11.22 / 10.80 / 10.55 / 11.20 (before the nearest-child
+ * selection of the occlusion step stopped indexing its arrays at run time, which had put them in local memory: 11.07 at 48) */
+#define CLV_RAYS_MIN_BLOCKS_LARGE (1152 / CLV_BLOCK) /* = 56 registers per thread */
 #endif
 template <int MODE, bool COUNT, bool SOA, int LARGE = 0>
 __global__ void __launch_bounds__(CLV_BLOCK, LARGE ? CLV_RAYS_MIN_BLOCKS_LARGE : CLV_RAYS_MIN_BLOCKS)

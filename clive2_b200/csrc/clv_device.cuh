@@ -629,15 +629,19 @@ CLV_HD int occ_round(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> &cnt)
             wide_test(A.wnodes + 8 * (size_t)cur, r.o, r.inv, r.t_bound, tk, rk);
             cnt.node();
             /* any order finds an occluder; take the nearest surviving child, keep the rest */
-            int near = 0;
+            /* (selects, not tk[near]: an index computed at run time would put both arrays in local memory) */
+            int near = 0, rn = rk[0];
+            float tn = tk[0];
 #pragma unroll
-            for (int k = 1; k < 4; k++)
-                if (tk[k] < tk[near]) near = k;
-            const bool any = tk[near] < CLV_INF;
+            for (int k = 1; k < 4; k++) {
+                const bool closer = tk[k] < tn;
+                tn = closer ? tk[k] : tn; rn = closer ? rk[k] : rn; near = closer ? k : near;
+            }
+            const bool any = tn < CLV_INF;
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 if (k != near && tk[k] < CLV_INF && sp < CLV_OCC_STACK) stack[sp++] = rk[k];
-            if (any) cur = rk[near];
+            if (any) cur = rn;
             else if (sp > 0) cur = stack[--sp];
             else status = OCC_CLEAR;
             continue;
@@ -689,14 +693,19 @@ CLV_HD int occ_inner_step(const AccelView &A, OccRay &r, int *stack, Cnt<COUNT> 
         int rk[4];
         wide_test(A.wnodes + 8 * (size_t)r.cur, r.o, r.inv, r.t_bound, tk, rk);
         cnt.node();
-        int near = 0;
+        /* the nearest surviving child by selects: tk[near] with a run-time index would put both arrays in local memory
+         * (it did: 2 x STL.128 + 5 LDL per step, 45 % of the L1 wavefronts of k_connect_rays) */
+        int near = 0, rn = rk[0];
+        float tn = tk[0];
 #pragma unroll
-        for (int k = 1; k < 4; k++)
-            if (tk[k] < tk[near]) near = k;
+        for (int k = 1; k < 4; k++) {
+            const bool closer = tk[k] < tn;
+            tn = closer ? tk[k] : tn; rn = closer ? rk[k] : rn; near = closer ? k : near;
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (k != near && tk[k] < CLV_INF && r.sp < CLV_OCC_STACK) stack[r.sp++] = rk[k];
-        if (tk[near] < CLV_INF) r.cur = rk[near];
+        if (tn < CLV_INF) r.cur = rn;
         else if (r.sp > 0) r.cur = stack[--r.sp];
         else return OCC_CLEAR;
         if (CLV_PREFETCH_NEXT) prefetch_ref<true>(A.wnodes, A.tris, r.cur);
