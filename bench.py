@@ -559,7 +559,8 @@ def run_ours(args, cfg, rank, local_rank, world):
         np_ = max(timed, 1)
         # the dominant kernel of the pass (by its own CUDA-event time) and its algorithmic bytes
         dom = max(kernel_ms, key=lambda k: kernel_ms[k])
-        launches_of = {"k_walk_trace": 12, "k_walk_shade": 13 if "k_walk_trace" in kernel_ms else 1}  # per pass; every other kernel once
+        # per pass; every other kernel once.  12 bounce rounds + 4 short ones for the samples whose searches were suspended
+        launches_of = {"k_walk_trace": 16, "k_walk_shade": 17 if "k_walk_trace" in kernel_ms else 1}
         cw, cc = ({k: v / max(parts[0]["passes"], 1) for k, v in counters[x].items()} for x in ("walk", "connect"))
         NBW = 128 if accel_stats["closest_uses_wide"] else 64   # bytes of the node record the walks fetch
         NBR = 128 if accel_stats["occlusion_uses_wide"] else 64  # ... and the connection rays (4-wide node = 128 B)
@@ -578,8 +579,9 @@ def run_ours(args, cfg, rank, local_rank, world):
             "k_connect_enumerate": cc["vertices"] * 48 + cc["rays_ref"] * 4 + n_local * (48 + 8),
             # 9 aggregators read (80 B), light image RMW (32 B), accumulator RMW (64 B) per pixel
             "k_fused_finalize": batch * (9 * 80 + 32 + 64),
-            # wavefront walks, all 12 rounds of a pass.  trace: node + triangle records fetched + per ray origin/direction
-            # parts read (32 B), hit written (16 B), queue entry (4 B)
+            # wavefront walks, all rounds of a pass.  trace: node + triangle records fetched + per ray origin/direction
+            # parts read (32 B), hit written (16 B), queue entry (4 B).  (The continuation records of the < 1 % of the
+            # searches that are suspended, <= 576 B written and read each, are not counted.)
             "k_walk_trace": cw["node_fetches"] * NBT + cw["tri_fetches"] * 48 + cw["rays_ref"] * (32 + 16 + 4),
             # shade (+ init): per ray hit (16 B) + walk state read and written (3-4 parts each way, 112 B) + seeds RMW
             # (16 B) + queue entry read + written (8 B) + the hit triangle's shading record (64 B); path vertices written
@@ -612,7 +614,8 @@ def run_ours(args, cfg, rank, local_rank, world):
                     "traffic_source": traffic_note,
                     "launches_per_pass_of_this_kernel": launches_of.get(dom, 1),
                     "per_launch_definition": "bytes, time and traffic are per PASS: the sum over this kernel's launches of one "
-                                             "pass (the wavefront walk kernels run once per bounce round, 12 rounds)"
+                                             "pass (the wavefront walk kernels run once per bounce round: 12 rounds + 4 short ones "
+                                             "for samples whose searches were suspended)"
                                              if dom in launches_of else "one launch per pass",
                     "traversal_records_bytes": accel_bytes, "traversal_records_l2_resident": bool(resident),
                     "l2_read_peak_gbs_measured_here": l2_read_gbs, "hbm_read_peak_gbs_measured_here": hbm_read_gbs,
@@ -641,7 +644,7 @@ def run_ours(args, cfg, rank, local_rank, world):
                     "launches_per_pass": launches // max(my_passes, 1),
                     "kernel_flavour": ("high-occupancy (traversal records exceed the caches)"
                                        if accel_stats["large_scene_tuning"] else "cache-resident"),
-                    "walks": "wavefront (k_walk_init + 12 x (k_walk_trace, k_walk_shade))" if "k_walk_trace" in kernel_ms
+                    "walks": "wavefront (k_walk_init + (12 + 4) x (k_walk_trace, k_walk_shade))" if "k_walk_trace" in kernel_ms
                              else "wavefront, pipelined (k_walk_init + k_walk_pipeline)" if "k_walk_pipeline" in kernel_ms
                              else "megakernel (k_fused_walks)",
                     "mesh_source": "in-memory" if (args.mesh_in_memory or not cfg.get("mesh")) else

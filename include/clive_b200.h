@@ -270,8 +270,9 @@ CLV_API int clv_counters_read(clv_ctx *ctx, uint64_t out[10], int reset);
 CLV_API int clv_renderer_kernel_timing(clv_renderer *r, int enabled);
 CLV_API int clv_renderer_kernel_times(clv_renderer *r, double ms_out[CLV_TIMED_KERNEL_SLOTS], uint64_t *passes_out, int reset);
 /* Stages 1-4 of the fused pass (ray generation + both random walks; renderer.py:281-285) run either as ONE megakernel,
- * a thread per sample (k_fused_walks), or as wavefront rounds: k_walk_init, then 12 x (k_walk_trace: persistent warps
- * that fetch rays from the round's queue as their lanes finish; k_walk_shade: the bounce of every traced ray).  Same
+ * a thread per sample (k_fused_walks), or as wavefront rounds: k_walk_init, then 12 (+ 4) x (k_walk_trace: persistent warps
+ * that fetch rays from the round's queue as their lanes finish; k_walk_shade: the bounce of every traced ray; a search
+ * that outlasts its round is suspended and resumed first thing in the next one, up to 4 times per sample).  Same
  * results, bit for bit.  mode 0 = automatic (wavefront for scenes whose traversal records exceed the caches when a pass of
  * the renderer has at least 600 Ki samples; env
  * CLV_WALK_MODE), 1 = megakernel, 2 = wavefront rounds, 3 = wavefront as ONE pipelined persistent kernel (k_walk_pipeline:
@@ -283,7 +284,9 @@ CLV_API int clv_ctx_walk_mode(clv_ctx *ctx, int mode, int *current_out);
  * rays (1..32); "walk_schedule" / "connect_schedule" = vote weight w, an inner-node step wins when
  * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form); "connect_dynamic_fetch" = 1: k_connect_rays as
  * persistent warps that fetch tasks with one atomicAdd per refill, 0: static 512-task chunks per warp; "walk_grid_divisor" =
- * k_walk_trace's persistent grid is the resident blocks / divisor.  value < 0 only queries. */
+ * k_walk_trace's persistent grid is the resident blocks / divisor; "walk_tail_budget" = iterations a warp of k_walk_trace
+ * keeps stepping after its round's queue ran dry before it suspends the searches it still holds into continuation records
+ * (0 = never; default 64); "finish_cooperative", "pipe_shade_every": see DESIGN.md section 5.  value < 0 only queries. */
 CLV_API int clv_ctx_set_knob(clv_ctx *ctx, const char *name, int value, int *previous);
 /* streaming-read bandwidth (GB/s) of a scratch buffer of nbytes read iters times: the L2 read peak for nbytes well
  * below the 126 MB L2 (the bound of the cache-resident configurations), the HBM read peak for nbytes >> L2 */
