@@ -77,6 +77,7 @@ struct clv_ctx {
     int pipe_shade_every;                             /* k_walk_pipeline: every k-th block only shades (0: dual-role warps) */
     int refill_below;    /* k_connect_rays: hand out new rays when fewer lanes than this hold one */
     int ray_schedule;    /* k_connect_rays: 0 = rounds; w > 0 = majority vote, inner steps win when n_inner*w >= n_leaf*4 */
+    int ray_schedule_large; /* ... of the large-scene flavour, whose leaf steps are warp-cooperative */
     /* scratch of the stage-level clv_connect_paths (grown on demand) */
     void *cs_mem;
     uint32_t cs_capacity;
@@ -134,7 +135,12 @@ extern "C" int clv_ctx_create(int device, clv_ctx **out) {
     c->walk_mode = getenv("CLV_WALK_MODE") ? atoi(getenv("CLV_WALK_MODE")) : 0;
     c->walk_refill_below = getenv("CLV_WALK_REFILL_BELOW") ? atoi(getenv("CLV_WALK_REFILL_BELOW")) : 24;
     if (c->walk_refill_below < 1) c->walk_refill_below = 1;
-    c->walk_schedule = getenv("CLV_WALK_SCHEDULE") ? atoi(getenv("CLV_WALK_SCHEDULE")) : 8;
+    /* with leaves tested by the whole warp a leaf step is cheap per triangle, so it may win the vote earlier.  C4, ms per
+     * pass (k_walk_trace / k_connect_rays) at weight 1 / 2 / 4 / 6 / 8 / 16 / 32: 10.69 / 10.39 / 10.32 / 10.41 / 10.52 /
+     * 11.08 / 12.05 and 9.61 / 9.54 / 9.60 / 9.76 / 9.96 / 10.81 / 12.39; C3 at 2 / 4 / 8 / 16: 4.14 / 4.12 / 4.23 / 4.47
+     * and 5.22 / 5.26 / 5.47 / 5.98 */
+    c->walk_schedule = getenv("CLV_WALK_SCHEDULE") ? atoi(getenv("CLV_WALK_SCHEDULE")) : 4;
+    c->ray_schedule_large = getenv("CLV_RAY_SCHEDULE") ? atoi(getenv("CLV_RAY_SCHEDULE")) : 4;
     /* with the pass cut into slices, a trace grid of HALF the resident blocks lets the kernels of two slices share the SMs,
      * so one slice's tail (a few long rays, latency bound) overlaps another's work: C4, 3 slices, divisor 1 / 2 / 3 ->
      * 29.7 / 28.8 / 30.2 ms per pass; 2 slices divisor 1: 28.9; 4 slices divisor 1 / 2: 30.6 / 29.5 */
@@ -586,6 +592,9 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
 #ifndef CLV_COOP_LEAVES
 #define CLV_COOP_LEAVES 1
 #endif
+#ifndef CLV_COOP_LEAVES_RESIDENT
+#define CLV_COOP_LEAVES_RESIDENT 0 /* k_connect_rays of the cache-resident flavour (C1 / C2) keeps the per-lane leaf loop */
+#endif
 struct LeafDeal { int incl, excl, first, total; };
 __device__ __forceinline__ LeafDeal leaf_deal(bool at_leaf, int cur, int lane) {
     const int code = ~cur;
@@ -752,7 +761,7 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
             const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
             const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && !at_inner));
             if (n_inner * schedule >= n_leaf * 4) { if (at_inner) st = occ_inner_step<COUNT>(A, ray, stack, cnt); }
-            else if (CLV_COOP_LEAVES && LARGE) st = occ_leaf_step_warp<COUNT>(A, ray, stack, have && !at_inner, lane, cnt);
+            else if (CLV_COOP_LEAVES && (LARGE || CLV_COOP_LEAVES_RESIDENT)) st = occ_leaf_step_warp<COUNT>(A, ray, stack, have && !at_inner, lane, cnt);
             else if (have && !at_inner) st = occ_leaf_step<COUNT>(A, ray, stack, cnt);
         }
         if (st != OCC_RUNNING) {
@@ -1592,7 +1601,7 @@ static int launch_connect(clv_ctx *c, cudaStream_t stream, int mode, bool splat,
     }
     if (large_flavour) {
         /* the renderer's default configuration on a scene larger than the caches: high-occupancy flavour */
-        k_connect_rays<TRAVERSE_ORDERED, false, true, 1><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule, dyn);
+        k_connect_rays<TRAVERSE_ORDERED, false, true, 1><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule_large, dyn);
     } else {
 #define CALL(M, CT, SO) k_connect_rays<M, CT, SO><<<ray_blocks, CLV_BLOCK, 0, stream>>>(store, view, cam, cs, ctr, c->refill_below, c->ray_schedule, dyn)
         DISPATCH_MCS(mode, c->counting, soa, CALL);
@@ -2192,6 +2201,7 @@ extern "C" int clv_ctx_set_knob(clv_ctx *c, const char *name, int value, int *pr
     else if (!strcmp(name, "walk_tail_budget")) slot = &c->walk_tail_budget;
     else return fail(CLV_ERR_INVALID, "clv_ctx_set_knob: unknown knob '%s'", name);
     if (previous) *previous = *slot;
+    if (value >= 0 && slot == &c->ray_schedule) c->ray_schedule_large = value; /* one knob for both flavours */
     if (value >= 0) {
         if ((slot == &c->walk_refill_below || slot == &c->walk_schedule) && value < 1) value = 1;
         *slot = value;
