@@ -595,20 +595,24 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
 #ifndef CLV_COOP_LEAVES_RESIDENT
 #define CLV_COOP_LEAVES_RESIDENT 0 /* k_connect_rays of the cache-resident flavour (C1 / C2) keeps the per-lane leaf loop */
 #endif
-struct LeafDeal { int incl, excl, first, total; };
+struct LeafDeal { int incl, excl, first_minus_excl, total; };
 __device__ __forceinline__ LeafDeal leaf_deal(bool at_leaf, int cur, int lane) {
     const int code = ~cur;
     LeafDeal D;
-    D.first = code >> 4;
     const int count = at_leaf ? (code & 15) : 0;
-    D.incl = count;
+    /* prefix sum of the leaf sizes (< 16: four bits) from four ballots — the shuffles of a scan would run on the LSU pipe,
+     * which is what bounds these kernels */
+    const unsigned below = (1u << lane) - 1u;
+    D.excl = 0;
+    D.total = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, D.incl, d);
-        if (lane >= d) D.incl += v;
+    for (int b = 0; b < 4; b++) {
+        const unsigned has = __ballot_sync(0xffffffffu, (count >> b) & 1);
+        D.excl += __popc(has & below) << b;
+        D.total += __popc(has) << b;
     }
-    D.excl = D.incl - count;
-    D.total = __shfl_sync(0xffffffffu, D.incl, 31);
+    D.incl = D.excl + count;
+    D.first_minus_excl = (code >> 4) - D.excl;
     return D;
 }
 /* the lane that owns pair p: the first one whose inclusive sum exceeds p (lanes without a leaf own nothing) */
@@ -632,7 +636,7 @@ __device__ __forceinline__ int hit_leaf_step_warp(const AccelView &A, HitRay &r,
     for (int base = 0; base < D.total; base += 32) {
         const int p = base + lane;
         const int owner = leaf_owner(D, p);
-        const int i = __shfl_sync(0xffffffffu, D.first, owner) + (p - __shfl_sync(0xffffffffu, D.excl, owner));
+        const int i = __shfl_sync(0xffffffffu, D.first_minus_excl, owner) + p;
         const V3 o = shfl3(r.o, owner), d = shfl3(r.d, owner);
         bool hit = false;
         float t = CLV_INF, u = 0.0f, v = 0.0f;
@@ -668,7 +672,7 @@ __device__ __forceinline__ int occ_leaf_step_warp(const AccelView &A, OccRay &r,
     for (int base = 0; base < D.total; base += 32) {
         const int p = base + lane;
         const int owner = leaf_owner(D, p);
-        const int i = __shfl_sync(0xffffffffu, D.first, owner) + (p - __shfl_sync(0xffffffffu, D.excl, owner));
+        const int i = __shfl_sync(0xffffffffu, D.first_minus_excl, owner) + p;
         const V3 o = shfl3(r.o, owner), d = shfl3(r.d, owner);
         const float t_bound = __shfl_sync(0xffffffffu, r.t_bound, owner);
         const int rank_bound = __shfl_sync(0xffffffffu, r.rank_bound, owner), skip = __shfl_sync(0xffffffffu, r.skip, owner);

@@ -107,6 +107,41 @@ def test_suspended_searches_vs_checker(dev, which, budget):
         dev.knob("walk_tail_budget", before_budget)
 
 
+def test_tile_shards_under_wavefront_walks_sum_to_the_full_frame(dev):
+    """Two tile shards (16x16 tiles, the multi-GPU split) of C3's scene at 256x256, each rendered by the wavefront walks with
+    searches suspended early: the shards' accumulators add up to the full-frame render (counts and the unidirectional image
+    bit for bit — every sample consumed its 1-GPU RNG stream and found its 1-GPU hits — the atomically splatted sums within
+    float reordering)."""
+    from clive2_b200 import sharding
+    w = h = 256
+    a = scene.preset_arrays("bench-terrain-1m", w, h)
+    b = w * h
+    seeds = seeds_for(b, seed=23)
+    sc = scene.scene_from_arrays(a, dev)
+    before, before_budget = dev.walk_mode, dev.knob("walk_tail_budget", -1)
+    try:
+        dev.walk_mode = runtime.WALK_WAVEFRONT
+        dev.knob("walk_tail_budget", 8)
+        full = Renderer(sc, seeds=seeds)
+        parts = [Renderer(sc, seeds=seeds, sample_ids=sharding.tile_ids(w, h, k, 2, 16)) for k in (0, 1)]
+        for _ in range(2):
+            full.run_sample()
+            for p in parts:
+                p.run_sample()
+        acc_full = full._accum()
+        total = parts[0]._accum() + parts[1]._accum()
+        assert np.array_equal(total[..., 7], acc_full[..., 7])
+        assert_bits_equal(np.ascontiguousarray(total[..., 4:7]).reshape(b, 3), np.ascontiguousarray(acc_full[..., 4:7]).reshape(b, 3),
+                          "unidirectional image", nan_equal=True)
+        np.testing.assert_allclose(total[..., 0:4], acc_full[..., 0:4], rtol=5e-4, atol=1e-6)
+        for r in parts + [full]:
+            r.release()
+    finally:
+        dev.walk_mode = before
+        dev.knob("walk_tail_budget", before_budget)
+        sc.release()
+
+
 @pytest.fixture(scope="module")
 def c4_arrays():
     """BASELINE.json configs[3]'s scene (9 999 392-triangle mesh + enclosure) at a 160x90 frame (1080p / 12): built once."""
