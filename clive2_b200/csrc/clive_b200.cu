@@ -378,7 +378,8 @@ extern "C" int clv_accel_create(clv_ctx *c, const clv_Box *h_boxes_, int32_t n_b
     a->view.wnodes = a->d_wnodes;
     a->view.wroot_ref = H.wide_root_ref;
     a->n_wide = H.wide.size();
-    a->large = (nb_nodes + nb_wide + nb_tris) > (size_t)CLV_LARGE_SCENE_BYTES;
+    /* (env CLV_LARGE_SCENE_BYTES: test hook — lets a small scene run the large-scene kernel flavours) */
+    a->large = (nb_nodes + nb_wide + nb_tris) > (getenv("CLV_LARGE_SCENE_BYTES") ? (size_t)strtoull(getenv("CLV_LARGE_SCENE_BYTES"), nullptr, 10) : (size_t)CLV_LARGE_SCENE_BYTES);
     a->binary_depth = H.binary_depth;
     a->wide_depth = H.wide_depth;
     a->view.tris = a->d_tris;

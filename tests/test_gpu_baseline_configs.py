@@ -142,6 +142,32 @@ def test_tile_shards_under_wavefront_walks_sum_to_the_full_frame(dev):
         sc.release()
 
 
+def test_cooperative_leaf_steps_with_leaves_of_up_to_15_triangles(dev, monkeypatch):
+    """The warp-cooperative leaf steps of k_walk_trace / k_connect_rays deal (ray, triangle) pairs by a 4-bit prefix sum of
+    the leaf sizes.  The reference's builder stops at 8 triangles per leaf; here C2's scene is built with leaves of up to 15
+    (the largest a leaf reference can encode) and run through the large-scene kernel flavours (threshold lowered by the
+    test hook), wavefront walks with searches suspended early: same bits as the checker."""
+    from clive2_b200 import bvh
+    monkeypatch.setattr(bvh, "MAX_MEMBERS", 15)
+    monkeypatch.setenv("CLV_LARGE_SCENE_BYTES", "1")
+    a = arrays("bench-spheres", 160, 120)
+    leaves = a.boxes[a.boxes["right"] != 0]
+    sizes = leaves["right"] - leaves["left"]
+    assert sizes.max() == 15 and (sizes > 8).sum() > 100
+    acc = runtime.Accel(dev, a.boxes, a.triangles)
+    st = acc.stats()
+    acc.release()
+    assert st["large_scene_tuning"] and st["trace_uses_wide"] and st["occlusion_uses_wide"]
+    before, before_budget = dev.walk_mode, dev.knob("walk_tail_budget", -1)
+    try:
+        dev.walk_mode = runtime.WALK_WAVEFRONT
+        dev.knob("walk_tail_budget", 4)
+        compare_with_checker(dev, a, passes=3, seed=29)
+    finally:
+        dev.walk_mode = before
+        dev.knob("walk_tail_budget", before_budget)
+
+
 @pytest.fixture(scope="module")
 def c4_arrays():
     """BASELINE.json configs[3]'s scene (9 999 392-triangle mesh + enclosure) at a 160x90 frame (1080p / 12): built once."""
