@@ -582,120 +582,21 @@ k_connect_enumerate(uint32_t first, uint32_t n, PathStore store, AccelView A, co
     flush_counters<COUNT>(cnt, counters);
 }
 
-/* ---- leaves tested by the whole warp (k_walk_trace, k_connect_rays) ------------------------------------------------- *
- * A ray of the 10 M-triangle scene meets 7 node records but 19 triangle records, and a leaf step that lets every lane loop
- * over its own leaf runs as long as the longest leaf of the warp (up to 15 triangles) with only the lanes at leaves busy.
- * Here the (ray, triangle) pairs of all lanes at leaves are dealt to ALL 32 lanes: pair p belongs to the lane whose
- * inclusive prefix sum of leaf sizes first exceeds p (binary search by shuffles), the tester borrows that lane's ray by
- * shuffles and runs the SAME tri_test on the SAME operands, so every pair yields the bits it yields in the sequential
- * loop; a leaf's result is the lexicographic minimum (t, rank) of its accepted pairs and the running best — the
- * sequential loop's result, whatever the order (ranks are unique; t = +INF is never accepted, as there). */
+/* the warp primitives behind the cooperative leaf steps of clv_device.cuh (tests/hostemu supplies 32 host threads in
+ * lockstep instead) */
 #ifndef CLV_COOP_LEAVES
-#define CLV_COOP_LEAVES 1
+#define CLV_COOP_LEAVES 1 /* leaves tested by the whole warp (hit_leaf_step_warp / occ_leaf_step_warp, clv_device.cuh) */
 #endif
 #ifndef CLV_COOP_LEAVES_RESIDENT
 #define CLV_COOP_LEAVES_RESIDENT 0 /* k_connect_rays of the cache-resident flavour (C1 / C2) keeps the per-lane leaf loop */
 #endif
-struct LeafDeal { int incl, excl, first_minus_excl, total; };
-__device__ __forceinline__ LeafDeal leaf_deal(bool at_leaf, int cur, int lane) {
-    const int code = ~cur;
-    LeafDeal D;
-    const int count = at_leaf ? (code & 15) : 0;
-    /* prefix sum of the leaf sizes (< 16: four bits) from four ballots — the shuffles of a scan would run on the LSU pipe,
-     * which is what bounds these kernels */
-    const unsigned below = (1u << lane) - 1u;
-    D.excl = 0;
-    D.total = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const unsigned has = __ballot_sync(0xffffffffu, (count >> b) & 1);
-        D.excl += __popc(has & below) << b;
-        D.total += __popc(has) << b;
-    }
-    D.incl = D.excl + count;
-    D.first_minus_excl = (code >> 4) - D.excl;
-    return D;
-}
-/* the lane that owns pair p: the first one whose inclusive sum exceeds p (lanes without a leaf own nothing) */
-__device__ __forceinline__ int leaf_owner(const LeafDeal &D, int p) {
-    int owner = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, D.incl, owner + step - 1);
-        if (v <= p) owner += step;
-    }
-    return owner;
-}
-__device__ __forceinline__ V3 shfl3(V3 a, int src) {
-    return v3(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src));
-}
-/* closest hit: all 32 lanes call; returns the lane's status after its leaf (HIT_RUNNING for lanes that held none) */
-template <bool COUNT>
-__device__ __forceinline__ int hit_leaf_step_warp(const AccelView &A, HitRay &r, const StackEntry *st, bool at_leaf, int lane,
-                                                  Cnt<COUNT> &cnt) {
-    const LeafDeal D = leaf_deal(at_leaf, r.cur, lane);
-    for (int base = 0; base < D.total; base += 32) {
-        const int p = base + lane;
-        const int owner = leaf_owner(D, p);
-        const int i = __shfl_sync(0xffffffffu, D.first_minus_excl, owner) + p;
-        const V3 o = shfl3(r.o, owner), d = shfl3(r.d, owner);
-        bool hit = false;
-        float t = CLV_INF, u = 0.0f, v = 0.0f;
-        int rank = 0;
-        if (p < D.total) {
-            const V4 *tp = A.tris + 3 * (size_t)i;
-            const V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-            cnt.tri();
-            rank = f2i(a.w);
-            hit = tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v) && t < CLV_INF;
-        }
-        /* accepted pairs are rare (a ray has ONE closest hit): hand each to its owner in turn */
-        unsigned hits = __ballot_sync(0xffffffffu, hit);
-        while (hits) {
-            const int src = __ffs(hits) - 1;
-            hits &= hits - 1u;
-            const int own_s = __shfl_sync(0xffffffffu, owner, src);
-            const float t_s = __shfl_sync(0xffffffffu, t, src), u_s = __shfl_sync(0xffffffffu, u, src), v_s = __shfl_sync(0xffffffffu, v, src);
-            const int rank_s = __shfl_sync(0xffffffffu, rank, src), i_s = __shfl_sync(0xffffffffu, i, src);
-            if (lane == own_s && (t_s < r.best_t || (t_s == r.best_t && rank_s < r.best_rank))) {
-                r.best_i = i_s; r.best_t = t_s; r.bu = u_s; r.bv = v_s; r.best_rank = rank_s;
-            }
-        }
-    }
-    return at_leaf ? hit_pop(r, st) : HIT_RUNNING;
-}
-/* occlusion: a leaf blocks when any of its pairs does */
-template <bool COUNT>
-__device__ __forceinline__ int occ_leaf_step_warp(const AccelView &A, OccRay &r, const int *stack, bool at_leaf, int lane,
-                                                  Cnt<COUNT> &cnt) {
-    const LeafDeal D = leaf_deal(at_leaf, r.cur, lane);
-    bool blocked = false;
-    for (int base = 0; base < D.total; base += 32) {
-        const int p = base + lane;
-        const int owner = leaf_owner(D, p);
-        const int i = __shfl_sync(0xffffffffu, D.first_minus_excl, owner) + p;
-        const V3 o = shfl3(r.o, owner), d = shfl3(r.d, owner);
-        const float t_bound = __shfl_sync(0xffffffffu, r.t_bound, owner);
-        const int rank_bound = __shfl_sync(0xffffffffu, r.rank_bound, owner), skip = __shfl_sync(0xffffffffu, r.skip, owner);
-        bool blocks = false;
-        if (p < D.total) {
-            const V4 *tp = A.tris + 3 * (size_t)i;
-            const V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-            cnt.tri();
-            float t, u, v;
-            blocks = i != skip && tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v) &&
-                     (t < t_bound || (t == t_bound && f2i(a.w) < rank_bound));
-        }
-        /* my pairs of this round sit in lanes [excl - base, incl - base) */
-        const unsigned blocking = __ballot_sync(0xffffffffu, blocks);
-        const int lo = max(D.excl - base, 0), hi = min(D.incl - base, 32);
-        if (hi > lo && (blocking & ((hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u)))) blocked = true;
-    }
-    if (!at_leaf) return OCC_RUNNING;
-    if (blocked) return OCC_BLOCKED;
-    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
-    return OCC_CLEAR;
-}
+struct DeviceWarp {
+    int lane_;
+    __device__ __forceinline__ int lane() const { return lane_; }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+};
 
 #ifndef CLV_RAYS_MIN_BLOCKS
 #define CLV_RAYS_MIN_BLOCKS 1 /* no register cap: the kernel takes 63 */
@@ -766,7 +667,7 @@ k_connect_rays(PathStore store, AccelView A, const Camera *camera, ConnectScratc
             const int n_inner = __popc(__ballot_sync(0xffffffffu, at_inner));
             const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && !at_inner));
             if (n_inner * schedule >= n_leaf * 4) { if (at_inner) st = occ_inner_step<COUNT>(A, ray, stack, cnt); }
-            else if (CLV_COOP_LEAVES && (LARGE || CLV_COOP_LEAVES_RESIDENT)) st = occ_leaf_step_warp<COUNT>(A, ray, stack, have && !at_inner, lane, cnt);
+            else if (CLV_COOP_LEAVES && (LARGE || CLV_COOP_LEAVES_RESIDENT)) { DeviceWarp w{lane}; st = occ_leaf_step_warp<COUNT>(w, A, ray, stack, have && !at_inner, cnt); }
             else if (have && !at_inner) st = occ_leaf_step<COUNT>(A, ray, stack, cnt);
         }
         if (st != OCC_RUNNING) {
@@ -1168,7 +1069,7 @@ k_walk_trace(uint32_t first, uint32_t n_identity, const uint32_t *queue, const u
         int status = HIT_RUNNING;
         if (n_inner * schedule >= n_leaf * 4) {
             if (at_inner) status = WIDE ? hit_inner_step_wide<COUNT>(A, ray, st, cnt) : hit_inner_step<COUNT>(A, ray, st, cnt);
-        } else if (CLV_COOP_LEAVES) status = hit_leaf_step_warp<COUNT>(A, ray, st, have && !at_inner, lane, cnt);
+        } else if (CLV_COOP_LEAVES) { DeviceWarp w{lane}; status = hit_leaf_step_warp<COUNT>(w, A, ray, st, have && !at_inner, cnt); }
         else if (have && !at_inner) status = hit_leaf_step<COUNT, WIDE>(A, ray, st, cnt);
         if (status == HIT_DONE) {
             have = false;

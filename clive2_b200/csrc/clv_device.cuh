@@ -555,6 +555,99 @@ CLV_HD int hit_leaf_step(const AccelView &A, HitRay &r, const StackEntry *st, Cn
     return status;
 }
 
+/* ---- leaves tested by the whole warp (k_walk_trace, k_connect_rays) ------------------------------------------------- *
+ * A ray of the 10 M-triangle scene meets 7 node records but 19 triangle records, and a leaf step that lets every lane loop
+ * over its own leaf runs as long as the longest leaf of the warp (up to 15 triangles) with only the lanes at leaves busy.
+ * Here the (ray, triangle) pairs of all lanes at leaves are dealt to ALL 32 lanes: pair p belongs to the lane whose
+ * inclusive prefix sum of leaf sizes first exceeds p (binary search by shuffles), the tester borrows that lane's ray by
+ * shuffles and runs the SAME tri_test on the SAME operands, so every pair yields the bits it yields in the sequential
+ * loop; a leaf's result is the lexicographic minimum (t, rank) of its accepted pairs and the running best — the
+ * sequential loop's result, whatever the order (ranks are unique; t = +INF is never accepted, as there).
+ * `W` supplies the warp: lane(), ballot(pred), shfl(value, source lane), all 32 lanes calling together — the hardware
+ * intrinsics in the kernels (DeviceWarp, clive_b200.cu), 32 host threads in lockstep in tests/hostemu. */
+CLV_HD int clv_popc(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+CLV_HD int clv_ffs(unsigned v) { /* 1-based position of the lowest set bit, 0 for none */
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v);
+#else
+    return __builtin_ffs((int)v);
+#endif
+}
+struct LeafDeal { int incl, excl, first_minus_excl, total; };
+template <class W>
+CLV_HD LeafDeal leaf_deal(const W &w, bool at_leaf, int cur) {
+    const int code = ~cur;
+    LeafDeal D;
+    const int count = at_leaf ? (code & 15) : 0;
+    /* prefix sum of the leaf sizes (< 16: four bits) from four ballots — the shuffles of a scan would run on the LSU pipe,
+     * which is what bounds these kernels */
+    const unsigned below = (1u << w.lane()) - 1u;
+    D.excl = 0;
+    D.total = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const unsigned has = w.ballot(((count >> b) & 1) != 0);
+        D.excl += clv_popc(has & below) << b;
+        D.total += clv_popc(has) << b;
+    }
+    D.incl = D.excl + count;
+    D.first_minus_excl = (code >> 4) - D.excl;
+    return D;
+}
+/* the lane that owns pair p: the first one whose inclusive sum exceeds p (lanes without a leaf own nothing) */
+template <class W>
+CLV_HD int leaf_owner(const W &w, const LeafDeal &D, int p) {
+    int owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int v = w.shfl(D.incl, owner + step - 1);
+        if (v <= p) owner += step;
+    }
+    return owner;
+}
+template <class W>
+CLV_HD V3 shfl3(const W &w, V3 a, int src) { return v3(w.shfl(a.x, src), w.shfl(a.y, src), w.shfl(a.z, src)); }
+/* closest hit: all 32 lanes call; returns the lane's status after its leaf (HIT_RUNNING for lanes that held none) */
+template <bool COUNT, class W>
+CLV_HD int hit_leaf_step_warp(const W &w, const AccelView &A, HitRay &r, const StackEntry *st, bool at_leaf, Cnt<COUNT> &cnt) {
+    const LeafDeal D = leaf_deal(w, at_leaf, r.cur);
+    for (int base = 0; base < D.total; base += 32) {
+        const int p = base + w.lane();
+        const int owner = leaf_owner(w, D, p);
+        const int i = w.shfl(D.first_minus_excl, owner) + p;
+        const V3 o = shfl3(w, r.o, owner), d = shfl3(w, r.d, owner);
+        bool hit = false;
+        float t = CLV_INF, u = 0.0f, v = 0.0f;
+        int rank = 0;
+        if (p < D.total) {
+            const V4 *tp = A.tris + 3 * (size_t)i;
+            const V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+            cnt.tri();
+            rank = f2i(a.w);
+            hit = tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v) && t < CLV_INF;
+        }
+        /* accepted pairs are rare (a ray has ONE closest hit): hand each to its owner in turn */
+        unsigned hits = w.ballot(hit);
+        while (hits) {
+            const int src = clv_ffs(hits) - 1;
+            hits &= hits - 1u;
+            const int own_s = w.shfl(owner, src);
+            const float t_s = w.shfl(t, src), u_s = w.shfl(u, src), v_s = w.shfl(v, src);
+            const int rank_s = w.shfl(rank, src), i_s = w.shfl(i, src);
+            if (w.lane() == own_s && (t_s < r.best_t || (t_s == r.best_t && rank_s < r.best_rank))) {
+                r.best_i = i_s; r.best_t = t_s; r.bu = u_s; r.bv = v_s; r.best_rank = rank_s;
+            }
+        }
+    }
+    return at_leaf ? hit_pop(r, st) : HIT_RUNNING;
+}
+
 /* ---- continuation of a closest-hit search across wavefront rounds ------------------------------------------------------ *
  * A round of the wavefront walks cannot end before its longest ray, and fewer than 1 % of the rays — the ones still running
  * 64 iterations after every other ray of the round is done — held 20 % of the trace time (profiles/r02_notes.md).  Such a
@@ -751,6 +844,38 @@ CLV_HD int occ_leaf_step(const AccelView &A, OccRay &r, const int *stack, Cnt<CO
         if (CLV_PREFETCH_NEXT) prefetch_ref<CLV_WIDE_OCCLUSION != 0>(CLV_WIDE_OCCLUSION ? A.wnodes : A.nodes, A.tris, r.cur);
         return OCC_RUNNING;
     }
+    return OCC_CLEAR;
+}
+
+/* ... the same for the occlusion queries (k_connect_rays): a leaf blocks when any of its pairs does */
+template <bool COUNT, class W>
+CLV_HD int occ_leaf_step_warp(const W &w, const AccelView &A, OccRay &r, const int *stack, bool at_leaf, Cnt<COUNT> &cnt) {
+    const LeafDeal D = leaf_deal(w, at_leaf, r.cur);
+    bool blocked = false;
+    for (int base = 0; base < D.total; base += 32) {
+        const int p = base + w.lane();
+        const int owner = leaf_owner(w, D, p);
+        const int i = w.shfl(D.first_minus_excl, owner) + p;
+        const V3 o = shfl3(w, r.o, owner), d = shfl3(w, r.d, owner);
+        const float t_bound = w.shfl(r.t_bound, owner);
+        const int rank_bound = w.shfl(r.rank_bound, owner), skip = w.shfl(r.skip, owner);
+        bool blocks = false;
+        if (p < D.total) {
+            const V4 *tp = A.tris + 3 * (size_t)i;
+            const V4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+            cnt.tri();
+            float t, u, v;
+            blocks = i != skip && tri_test(o, d, xyz(a), xyz(b), xyz(c), t, u, v) &&
+                     (t < t_bound || (t == t_bound && f2i(a.w) < rank_bound));
+        }
+        /* my pairs of this round sit in lanes [excl - base, incl - base) */
+        const unsigned blocking = w.ballot(blocks);
+        const int lo = D.excl - base > 0 ? D.excl - base : 0, hi = D.incl - base < 32 ? D.incl - base : 32;
+        if (hi > lo && (blocking & ((hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u)))) blocked = true;
+    }
+    if (!at_leaf) return OCC_RUNNING;
+    if (blocked) return OCC_BLOCKED;
+    if (r.sp > 0) { r.cur = stack[--r.sp]; return OCC_RUNNING; }
     return OCC_CLEAR;
 }
 

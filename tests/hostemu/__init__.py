@@ -94,6 +94,20 @@ class HostEmu:
         self.lib.emu_visibility(C.c_uint32(len(a)), _p(a), _p(b), accel, _p(out), C.c_int(mode))
         return out
 
+    def coop_hit_leaves(self, rays, accel, wide=False):
+        """hit_leaf_step_warp (the warp-cooperative leaf step of k_walk_trace) on 32 host threads in lockstep against the
+        per-lane hit_leaf_step, leaf by leaf: dict(compared, mismatches, max_pairs, wrong_hits); None without 32 threads."""
+        out = (C.c_int64 * 4)()
+        rc = self.lib.emu_coop_hit_leaves(C.c_uint32(len(rays)), _p(rays), accel, C.c_int(int(wide)), out)
+        return None if rc else dict(zip(("compared", "mismatches", "max_pairs", "wrong_hits"), (int(x) for x in out)))
+
+    def coop_occ_leaves(self, rays, t_bound, rank_bound, skip, accel):
+        """occ_leaf_step_warp (k_connect_rays) against occ_leaf_step, the same way."""
+        out = (C.c_int64 * 4)()
+        t_bound, rank_bound, skip = (np.ascontiguousarray(x) for x in (t_bound, rank_bound, skip))
+        rc = self.lib.emu_coop_occ_leaves(C.c_uint32(len(rays)), _p(rays), _p(t_bound), _p(rank_bound), _p(skip), accel, out)
+        return None if rc else dict(zip(("compared", "mismatches", "max_pairs", "wrong_verdicts"), (int(x) for x in out)))
+
     def fused_pass(self, arrays, accel, seeds, light_paths, camera_paths, aggs, light_image, accum, sample_ids=None,
                    mode=MODE_ORDERED, soa=None, soa_len=None, wavefront=False, suspend_after=0):
         """One fused pass.  With `soa` (float32 (2*6*4*n_local, 4)) and `soa_len` (int32 (2*n_local,)) the renderer's compact

@@ -183,6 +183,175 @@ EXPORT void emu_traverse_counts(uint32_t n, const Ray *rays, const EmuAccel *a, 
     }
 }
 
+/* ---- the warp-cooperative leaf steps (hit_leaf_step_warp / occ_leaf_step_warp) on 32 host threads in lockstep ----------- *
+ * The kernels run them with shuffles and ballots; here a "warp" is an OpenMP team of 32 threads and every warp primitive
+ * is a write to a shared slot between two barriers, so the very same source runs (and is compared, leaf by leaf, with the
+ * per-lane sequential loop it replaces). */
+#include <omp.h>
+struct HostWarpShared { uint32_t slot[32]; };
+struct HostWarp {
+    HostWarpShared *s;
+    int lane_;
+    int lane() const { return lane_; }
+    unsigned ballot(bool p) const {
+        s->slot[lane_] = p ? 1u : 0u;
+#pragma omp barrier
+        unsigned m = 0;
+        for (int k = 0; k < 32; k++) m |= (s->slot[k] & 1u) << k;
+#pragma omp barrier
+        return m;
+    }
+    uint32_t shfl_bits(uint32_t v, int src) const {
+        s->slot[lane_] = v;
+#pragma omp barrier
+        const uint32_t r = s->slot[src & 31];
+#pragma omp barrier
+        return r;
+    }
+    int shfl(int v, int src) const { return (int)shfl_bits((uint32_t)v, src); }
+    float shfl(float v, int src) const { return i2f((int)shfl_bits((uint32_t)f2i(v), src)); }
+};
+static bool same_bits(float a, float b) { return f2i(a) == f2i(b); }
+
+/* closest hit: rays in groups of 32; per group every lane walks down to its next leaf on its own, then the leaves of the
+ * group are tested (a) lane by lane with hit_leaf_step and (b) together with hit_leaf_step_warp; states must agree bit
+ * for bit after every leaf.  out: [0] leaf states compared, [1] mismatches, [2] largest number of pairs in one step,
+ * [3] final hits that differ from closest_hit<ORDERED>; returns 0, or -1 when no team of 32 threads could be had */
+EXPORT int emu_coop_hit_leaves(uint32_t n, const Ray *rays, const EmuAccel *a, int wide, int64_t out[4]) {
+    int64_t compared = 0, mismatches = 0, max_pairs = 0, wrong_hits = 0;
+    bool team_ok = true;
+    omp_set_dynamic(0);
+    for (uint32_t g0 = 0; g0 < n; g0 += 32) {
+        HostWarpShared shared;
+        int64_t c_cmp = 0, c_mis = 0, c_max = 0, c_wrong = 0;
+#pragma omp parallel num_threads(32) reduction(+ : c_cmp, c_mis, c_wrong) reduction(max : c_max)
+        {
+            if (omp_get_num_threads() != 32) {
+#pragma omp single
+                team_ok = false;
+            } else {
+                HostWarp w{&shared, omp_get_thread_num()};
+                Cnt<true> cnt;
+                const uint32_t id = g0 + (uint32_t)w.lane();
+                HitRay ray;
+                StackEntry st[CLV_HIT_STACK(true) > CLV_HIT_STACK(false) ? CLV_HIT_STACK(true) : CLV_HIT_STACK(false)];
+                bool have = false;
+                if (id < n) {
+                    ray.o = xyz(rays[id].origin); ray.d = xyz(rays[id].direction); ray.inv = rcp(ray.d);
+                    have = (wide ? hit_begin<true, true>(a->view, ray, cnt) : hit_begin<true, false>(a->view, ray, cnt)) == HIT_RUNNING;
+                }
+                for (;;) {
+                    while (have && ray.cur >= 0) /* own inner steps down to the next leaf */
+                        have = (wide ? hit_inner_step_wide<true>(a->view, ray, st, cnt) : hit_inner_step<true>(a->view, ray, st, cnt)) == HIT_RUNNING;
+                    const unsigned at_leaf_lanes = w.ballot(have);
+                    if (!at_leaf_lanes) break;
+                    HitRay seq = ray;
+                    int status_seq = HIT_RUNNING;
+                    if (have) status_seq = hit_leaf_step<true>(a->view, seq, st, cnt);
+                    const int pairs = have ? ((~ray.cur) & 15) : 0;
+                    int total = 0;
+                    for (int k = 0; k < 32; k++) total += w.shfl(pairs, k);
+                    const int status_warp = hit_leaf_step_warp<true>(w, a->view, ray, st, have, cnt);
+                    if (have) {
+                        c_cmp++;
+                        if (total > c_max) c_max = total;
+                        if (status_warp != status_seq || ray.best_i != seq.best_i || !same_bits(ray.best_t, seq.best_t) ||
+                            !same_bits(ray.bu, seq.bu) || !same_bits(ray.bv, seq.bv) || ray.best_rank != seq.best_rank ||
+                            ray.sp != seq.sp || (status_warp == HIT_RUNNING && ray.cur != seq.cur)) c_mis++;
+                        have = status_warp == HIT_RUNNING;
+                    } else if (status_warp != HIT_RUNNING) c_mis++;
+                }
+                if (id < n) {
+                    int best_i = -1;
+                    float best_t = CLV_INF, bu = 0.0f, bv = 0.0f;
+                    closest_hit<TRAVERSE_ORDERED, true>(a->view, xyz(rays[id].origin), xyz(rays[id].direction), rcp(xyz(rays[id].direction)),
+                                                        best_i, best_t, bu, bv, cnt, -CLV_INF, -1);
+                    if (best_i != ray.best_i || !same_bits(best_t, ray.best_t) || !same_bits(bu, ray.bu) || !same_bits(bv, ray.bv)) c_wrong++;
+                }
+            }
+        }
+        if (!team_ok) return -1;
+        compared += c_cmp; mismatches += c_mis; wrong_hits += c_wrong;
+        if (c_max > max_pairs) max_pairs = c_max;
+    }
+    out[0] = compared; out[1] = mismatches; out[2] = max_pairs; out[3] = wrong_hits;
+    return 0;
+}
+
+/* occlusion queries: ray id runs from rays[id].origin along rays[id].direction, bounded by (t_bound[id], rank_bound[id]),
+ * skipping triangle skip[id]; same comparison, occ_leaf_step against occ_leaf_step_warp.  out as above ([3]: final
+ * verdicts that differ between the two) */
+EXPORT int emu_coop_occ_leaves(uint32_t n, const Ray *rays, const float *t_bound, const int32_t *rank_bound, const int32_t *skip,
+                               const EmuAccel *a, int64_t out[4]) {
+    int64_t compared = 0, mismatches = 0, max_pairs = 0, wrong = 0;
+    bool team_ok = true;
+    omp_set_dynamic(0);
+    for (uint32_t g0 = 0; g0 < n; g0 += 32) {
+        HostWarpShared shared;
+        int64_t c_cmp = 0, c_mis = 0, c_max = 0, c_wrong = 0;
+#pragma omp parallel num_threads(32) reduction(+ : c_cmp, c_mis, c_wrong) reduction(max : c_max)
+        {
+            if (omp_get_num_threads() != 32) {
+#pragma omp single
+                team_ok = false;
+            } else {
+                HostWarp w{&shared, omp_get_thread_num()};
+                Cnt<true> cnt;
+                const uint32_t id = g0 + (uint32_t)w.lane();
+                OccRay ray, solo;
+                int stack[CLV_OCC_STACK], solo_stack[CLV_OCC_STACK];
+                bool have = false;
+                int verdict = OCC_CLEAR, solo_verdict = OCC_CLEAR;
+                if (id < n) {
+                    ray.o = xyz(rays[id].origin); ray.d = xyz(rays[id].direction); ray.inv = rcp(ray.d);
+                    ray.t_bound = t_bound[id]; ray.rank_bound = rank_bound[id]; ray.skip = skip[id];
+                    solo = ray;
+                    const int st0 = occ_begin<true>(a->view, ray, cnt);
+                    have = st0 == OCC_RUNNING;
+                    if (!have) verdict = st0;
+                    /* the same query on its own, per-lane steps only */
+                    int st1 = occ_begin<true>(a->view, solo, cnt);
+                    while (st1 == OCC_RUNNING)
+                        st1 = solo.cur >= 0 ? occ_inner_step<true>(a->view, solo, solo_stack, cnt) : occ_leaf_step<true>(a->view, solo, solo_stack, cnt);
+                    solo_verdict = st1;
+                }
+                for (;;) {
+                    while (have && ray.cur >= 0) {
+                        const int st1 = occ_inner_step<true>(a->view, ray, stack, cnt);
+                        have = st1 == OCC_RUNNING;
+                        if (!have) verdict = st1;
+                    }
+                    if (!w.ballot(have)) break;
+                    OccRay seq = ray;
+                    int seq_stack[CLV_OCC_STACK];
+                    int status_seq = OCC_RUNNING;
+                    if (have) {
+                        for (int k = 0; k < ray.sp; k++) seq_stack[k] = stack[k];
+                        status_seq = occ_leaf_step<true>(a->view, seq, seq_stack, cnt);
+                    }
+                    const int pairs = have ? ((~ray.cur) & 15) : 0;
+                    int total = 0;
+                    for (int k = 0; k < 32; k++) total += w.shfl(pairs, k);
+                    const int status_warp = occ_leaf_step_warp<true>(w, a->view, ray, stack, have, cnt);
+                    if (have) {
+                        c_cmp++;
+                        if (total > c_max) c_max = total;
+                        if (status_warp != status_seq || (status_warp == OCC_RUNNING && (ray.cur != seq.cur || ray.sp != seq.sp))) c_mis++;
+                        have = status_warp == OCC_RUNNING;
+                        if (!have) verdict = status_warp;
+                    } else if (status_warp != OCC_RUNNING) c_mis++;
+                }
+                if (id < n && verdict != solo_verdict) c_wrong++;
+            }
+        }
+        if (!team_ok) return -1;
+        compared += c_cmp; mismatches += c_mis; wrong += c_wrong;
+        if (c_max > max_pairs) max_pairs = c_max;
+    }
+    out[0] = compared; out[1] = mismatches; out[2] = max_pairs; out[3] = wrong;
+    return 0;
+}
+
 EXPORT void emu_visibility(uint32_t n, const Ray *ra, const Ray *rb, const EmuAccel *a, int32_t *visible, int mode) {
 #pragma omp parallel
     {

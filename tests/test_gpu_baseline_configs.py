@@ -150,7 +150,7 @@ def test_cooperative_leaf_steps_with_leaves_of_up_to_15_triangles(dev, monkeypat
     from clive2_b200 import bvh
     monkeypatch.setattr(bvh, "MAX_MEMBERS", 15)
     monkeypatch.setenv("CLV_LARGE_SCENE_BYTES", "1")
-    a = arrays("bench-spheres", 160, 120)
+    a = scene.preset_arrays("bench-spheres", 160, 120, bvh_builder="numpy")  # not tests.common.arrays: that one caches
     leaves = a.boxes[a.boxes["right"] != 0]
     sizes = leaves["right"] - leaves["left"]
     assert sizes.max() == 15 and (sizes > 8).sum() > 100

@@ -544,6 +544,41 @@ def test_suspended_searches_resume_to_the_same_hit(E, wavefront, suspend_after):
                               suspend_after=suspend_after)
 
 
+@pytest.mark.parametrize("max_members", [8, 15], ids=["leaves_le_8", "leaves_le_15"])
+@pytest.mark.parametrize("wide", [False, True], ids=["binary_nodes", "wide_nodes"])
+def test_cooperative_leaf_steps_in_lockstep_on_the_host(E, monkeypatch, wide, max_members):
+    """hit_leaf_step_warp / occ_leaf_step_warp — the warp-cooperative leaf steps of k_walk_trace / k_connect_rays (pairs
+    dealt to all 32 lanes by ballots and shuffles) — run here as the very same source on 32 host threads in lockstep and
+    are compared, after every leaf, with the per-lane loops they replace: same best hit / verdict, same stack, same next
+    node, bit for bit; the searches end at closest_hit's hits.  Leaves of the reference's size (<= 8) and of the largest
+    size a leaf reference encodes (15)."""
+    from clive2_b200 import bvh
+    from clive2_b200 import scene
+    monkeypatch.setattr(bvh, "MAX_MEMBERS", max_members)
+    a = scene.preset_arrays("bench-spheres", 48, 32, bvh_builder="numpy")  # not tests.common.arrays: that one caches
+    sizes = (a.boxes["right"] - a.boxes["left"])[a.boxes["right"] != 0]
+    assert sizes.max() == max_members
+    rays = random_rays(32 * 40 - 5, [-9, -1.9, -9], [9, 9, 9], seed=21)  # a ragged last group
+    acc = E.accel(a.boxes, a.triangles)
+    try:
+        r = E.coop_hit_leaves(rays, acc, wide=wide)
+        if r is None:
+            pytest.skip("no team of 32 OpenMP threads")
+        assert r["compared"] > len(rays) and r["mismatches"] == 0 and r["wrong_hits"] == 0, r
+        assert r["max_pairs"] > 64, r  # several rounds of 32 pairs in one step
+        if not wide:
+            # occlusion queries bounded at random distances, some skipping a triangle, some with a rank bound that matters
+            rng = np.random.default_rng(5)
+            tri, t, _, _ = E.traverse(rays, acc)
+            t_bound = np.where(rng.random(len(rays)) < 0.5, t, rng.uniform(0.5, 12.0, len(rays))).astype(np.float32)
+            rank_bound = np.where(rng.random(len(rays)) < 0.5, 0x7FFFFFFF, rng.integers(0, len(a.triangles), len(rays))).astype(np.int32)
+            skip = np.where(rng.random(len(rays)) < 0.5, tri, -1).astype(np.int32)
+            q = E.coop_occ_leaves(rays, t_bound, rank_bound, skip, acc)
+            assert q["compared"] > len(rays) and q["mismatches"] == 0 and q["wrong_verdicts"] == 0, q
+    finally:
+        E.accel_destroy(acc)
+
+
 @pytest.mark.parametrize("use_soa", [False, True], ids=["path_records", "soa_records"])
 def test_wavefront_walks_write_the_same_records_as_the_megakernel(E, use_soa):
     """Same Path records / SoA vertex records, lengths, RNG state, aggregators and accumulators from both drivers of the
