@@ -1856,27 +1856,41 @@ static int mark(clv_renderer *r, cudaStream_t st, int kernel) {
 
 /* buffers of the wavefront walks, allocated the first time a pass runs in that mode */
 static int ensure_walk_buffers(clv_renderer *r) {
-    if (r->d_walk_state) return CLV_OK;
+    if (r->d_walk_records) return CLV_OK; /* the last one allocated: all or nothing */
     clv_ctx *c = r->ctx;
     const size_t n = r->n_local;
-    CK(dev_alloc(c, &r->d_walk_state, n * 5 * sizeof(V4)));
-    CK(dev_alloc(c, &r->d_walk_jitter, n * 2 * sizeof(float)));
-    CK(dev_alloc(c, &r->d_walk_queue, n * 2 * sizeof(uint32_t)));
-    CK(dev_alloc(c, &r->d_walk_counters, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(r->d_walk_counters, 0, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t), c->stream));
-    CK(dev_alloc(c, &r->d_walk_lag, n));
     /* continuation records: a slice [first, end) owns records [first / 32 + slice * 1024, ...) of each half, 1024 +
      * (end - first) / 32 of them (about 1 % of a round's rays are suspended at the default budget; a full pool is harmless) */
     r->walk_record_capacity = n / CLV_WALK_SAMPLES_PER_RECORD + (size_t)(CLV_MAX_SLICES + 1) * CLV_WALK_RECORDS_MIN;
-    CK(dev_alloc(c, &r->d_walk_records, 2 * r->walk_record_capacity * CLV_HIT_RECORD_V4 * sizeof(V4)));
+    cudaError_t e = dev_alloc(c, &r->d_walk_state, n * 5 * sizeof(V4));
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_walk_jitter, n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_walk_queue, n * 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_walk_counters, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->d_walk_counters, 0, (size_t)CLV_MAX_SLICES * CLV_WALK_COUNTER_WORDS * sizeof(uint32_t), c->stream);
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_walk_lag, n);
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_walk_records, 2 * r->walk_record_capacity * CLV_HIT_RECORD_V4 * sizeof(V4));
+    if (e != cudaSuccess) { /* a renderer with some of them would read null pointers on the next pass */
+        dev_free(c, r->d_walk_state); dev_free(c, r->d_walk_jitter); dev_free(c, r->d_walk_queue); dev_free(c, r->d_walk_counters);
+        dev_free(c, r->d_walk_lag); dev_free(c, r->d_walk_records);
+        r->d_walk_state = nullptr; r->d_walk_jitter = nullptr; r->d_walk_queue = nullptr; r->d_walk_counters = nullptr;
+        r->d_walk_lag = nullptr; r->d_walk_records = nullptr;
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CLV_ERR_NOMEM : CLV_ERR_CUDA, "wavefront walk buffers: %s", cudaGetErrorString(e));
+    }
     return CLV_OK;
 }
 static int ensure_pipe_buffers(clv_renderer *r) {
-    if (r->d_pipe_queues) return CLV_OK;
+    if (r->d_pipe_ctrl) return CLV_OK; /* the last one allocated: all or nothing */
     clv_ctx *c = r->ctx;
-    CK(dev_alloc(c, &r->d_pipe_queues, (size_t)r->n_local * 23 * sizeof(uint32_t)));
-    CK(dev_alloc(c, &r->d_pipe_ctrl, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(r->d_pipe_ctrl, 0, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t), c->stream));
+    cudaError_t e = dev_alloc(c, &r->d_pipe_queues, (size_t)r->n_local * 23 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(c, &r->d_pipe_ctrl, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->d_pipe_ctrl, 0, (size_t)CLV_MAX_SLICES * 8 * sizeof(uint32_t), c->stream);
+    if (e != cudaSuccess) {
+        dev_free(c, r->d_pipe_queues); dev_free(c, r->d_pipe_ctrl);
+        r->d_pipe_queues = nullptr; r->d_pipe_ctrl = nullptr;
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CLV_ERR_NOMEM : CLV_ERR_CUDA, "pipelined walk buffers: %s", cudaGetErrorString(e));
+    }
     return CLV_OK;
 }
 
