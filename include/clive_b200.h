@@ -282,7 +282,9 @@ CLV_API int clv_ctx_walk_mode(clv_ctx *ctx, int mode, int *current_out);
 /* Scheduling knobs of the two ray kernels, for measurement sweeps (none changes a result): "walk_refill_below" /
  * "connect_refill_below" = lanes still holding a ray below which a warp of k_walk_trace / k_connect_rays fetches new
  * rays (1..32); "walk_schedule" / "connect_schedule" = vote weight w, an inner-node step wins when
- * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form); "connect_dynamic_fetch" = 1: k_connect_rays as
+ * lanes_at_inner * w >= lanes_at_leaf * 4 (connect_schedule 0 = round form; defaults: 4 where the leaves are tested by
+ * the whole warp — k_walk_trace and the large-scene flavour of k_connect_rays — 8 for the cache-resident flavour;
+ * setting connect_schedule sets both flavours, a query returns the cache-resident one); "connect_dynamic_fetch" = 1: k_connect_rays as
  * persistent warps that fetch tasks with one atomicAdd per refill, 0: static 512-task chunks per warp; "walk_grid_divisor" =
  * k_walk_trace's persistent grid is the resident blocks / divisor; "walk_tail_budget" = iterations a warp of k_walk_trace
  * keeps stepping after its round's queue ran dry before it suspends the searches it still holds into continuation records
